@@ -1,0 +1,885 @@
+// libjmmgpu.so — C ABI of the B200-native jmmOneDMC hot path (see include/jmm_gpu.h).
+// Host-side orchestration only; the arithmetic is in chains.cuh / sweep.cuh / pot.cuh / rng.cuh.
+// There is no CPU fallback anywhere in this file: without a usable CUDA device every entry point
+// that computes returns JMM_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/jmm_gpu.h"
+#include "chains.cuh"
+#include "sweep.cuh"
+
+using namespace jmm;
+
+static thread_local std::string g_err;
+
+static jmm_status fail(jmm_status code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(JMM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+struct jmm_handle {
+    jmm_config cfg{};
+    ChainsDev S{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint64_t sn = 0, launches = 0;
+    // many-chain launch shape
+    int block = 32, pos_in_smem = 1;
+    size_t smem = 0;
+    // recorded stream
+    uint32_t *d_stream = nullptr;
+    uint64_t stream_cap = 0;
+    uint64_t *d_cursor = nullptr;
+    int *d_err = nullptr;
+    uint64_t cursor = 0;
+    // scratch
+    double *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    uint8_t *d_log = nullptr;
+    size_t log_bytes = 0;
+    double *d_partial = nullptr;
+    size_t partial_bytes = 0;
+    // checkerboard mode: chain-major positions, double-buffered
+    double *cb_r[2] = {nullptr, nullptr};
+    int cb_cur = 0;
+    double *cb_tot = nullptr, *cb_acc = nullptr;
+    unsigned long long *cb_counts = nullptr;
+    uint64_t halfsweeps = 0;
+    std::vector<void *> allocs;
+};
+
+template <class T>
+static cudaError_t dalloc(jmm_handle *h, T **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) {
+        h->allocs.push_back(*p);
+        e = cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream);
+    }
+    return e;
+}
+
+static jmm_status ensure_stage(jmm_handle *h, size_t bytes) {
+    if (h->stage_bytes >= bytes) return JMM_OK;
+    if (h->d_stage) CK(cudaFree(h->d_stage));
+    h->d_stage = nullptr; h->stage_bytes = 0;
+    CK(cudaMalloc((void **) &h->d_stage, bytes));
+    h->stage_bytes = bytes;
+    return JMM_OK;
+}
+
+static bool is_cb(const jmm_handle *h) { return h->cfg.mode == JMM_MODE_CHECKERBOARD; }
+static unsigned nblk(uint64_t n, unsigned b) { return (unsigned) ((n + b - 1) / b); }
+
+static void tick(jmm_handle *h) { if (!h->timed) { cudaEventRecord(h->ev0, h->stream); h->timed = true; } }
+static void tock(jmm_handle *h) { cudaEventRecord(h->ev1, h->stream); }
+
+// ------------------------------------------------------------------------------------------------
+// readInput(), src/readInput.cpp:8-262
+// ------------------------------------------------------------------------------------------------
+extern "C" jmm_status jmm_read_input(const char *path, jmm_config *cfg, jmm_deck *deck) {
+    if (!path || !cfg) return fail(JMM_ERR_INVALID, "jmm_read_input: null argument");
+    FILE *f = fopen(path, "r");
+    if (!f) return fail(JMM_ERR_IO, std::string("FATAL ERROR: INPUT not found: ") + path);   // :51-54
+    jmm_deck dk;
+    memset(&dk, 0, sizeof dk);
+    memset(cfg, 0, sizeof *cfg);
+    cfg->cutoff = INFINITY;
+    cfg->ensemble = JMM_ENS_NPT;                       // default "NPT", :57
+    cfg->nchains = 1;
+    cfg->rng_kind = JMM_RNG_PHILOX;
+    cfg->mode = JMM_MODE_RECOMPUTE;
+    cfg->adapt = JMM_ADAPT_DEVICE;
+    strncpy(dk.ensemble_str, "NPT", sizeof dk.ensemble_str - 1);
+    char line[512];
+    const char *delim = "[ \t\n]";                     // :43 (the brackets are delimiters too)
+    while (fgets(line, sizeof line, f)) {
+        char *tok[32];
+        int n = 0;
+        for (char *t = strtok(line, delim); t && n < 31; t = strtok(nullptr, delim)) tok[n++] = t;
+        tok[n] = nullptr;
+        if (n == 0) continue;                          // the reference dereferences NULL here (:69)
+        const std::string k = tok[0];
+        auto num = [&](int i) { return (i < n) ? strtod(tok[i], nullptr) : 0.0; };
+        if (k == "RESTART") {
+            dk.is_restart = 1;
+            if (n > 1 && (!strcmp(tok[1], "FALSE") || !strcmp(tok[1], "False") || !strcmp(tok[1], "false"))) dk.is_restart = 0;
+        } else if (k == "N") cfg->N = (uint64_t) num(1);
+        else if (k == "P") cfg->P = num(1);
+        else if (k == "L") cfg->L = num(1);
+        else if (k == "T") cfg->T = num(1);
+        else if (k == "NBN") cfg->nbn = (int32_t) num(1);
+        else if (k == "NUMSTEPS") dk.numsteps = (uint64_t) num(1);
+        else if (k == "POT") {                         // :108-131
+            const char *name = n > 1 ? tok[1] : "";
+            if (!strcmp(name, "LJcut")) cfg->pot = JMM_POT_LJCUT;
+            else if (!strcmp(name, "LJ")) cfg->pot = JMM_POT_LJ;
+            else if (!strcmp(name, "HARMONIC")) cfg->pot = JMM_POT_HARMONIC;
+            else {
+                printf("Unknown potential type requested (%s). Using Lennard-Jones potential with no cut-off.\n", name);
+                cfg->pot = JMM_POT_LJ; name = "LJ";
+            }
+            strncpy(dk.pot_str, name, sizeof dk.pot_str - 1);
+            cfg->cutoff = (n > 2) ? strtod(tok[2], nullptr) : INFINITY;
+        } else if (k == "MAXSTEP") cfg->maxStep = num(1);
+        else if (k == "MAXDV") cfg->maxdl = num(1);
+        else if (k == "CPI") dk.cpi = (uint64_t) num(1);
+        else if (k == "TPI") dk.tpi = (uint64_t) num(1);
+        else if (k == "GPI") dk.gpi = (uint64_t) num(1);
+        else if (k == "RHOPI") dk.rhopi = (uint64_t) num(1);
+        else if (k == "RBW") dk.rbw = num(1);
+        else if (k == "RHONB") dk.rhonb = (uint64_t) num(1);
+        else if (k == "GBW") dk.gbw = num(1);
+        else if (k == "GNB") dk.gnb = (uint64_t) num(1);
+        else if (k == "GSW") dk.gsw = num(1);
+        else if (k == "GNS") dk.gns = (int32_t) num(1);
+        else if (k == "SEED") cfg->seed = (uint64_t) num(1);
+        else if (k == "ENGCHECK") cfg->eci = (uint64_t) num(1);
+        else if (k == "DADJ") cfg->mdai = (uint64_t) num(1);
+        else if (k == "VADJ") cfg->mvai = (uint64_t) num(1);
+        else if (k == "RELAX") cfg->relax = 1;
+        else if (k == "ENSEMBLE") {                    // :201-226
+            const char *name = n > 1 ? tok[1] : "";
+            if (!strcmp(name, "NPT")) cfg->ensemble = JMM_ENS_NPT;
+            else if (!strcmp(name, "NLT")) cfg->ensemble = JMM_ENS_NLT;
+            else {
+                printf("Unknown ensemble type requested (%s). Using NPT ensemble.\n", name);
+                cfg->ensemble = JMM_ENS_NPT; name = "NPT";
+            }
+            strncpy(dk.ensemble_str, name, sizeof dk.ensemble_str - 1);
+        } else if (k == "COMPUTE" || k == "compute") {
+            // `Compute` objects are constructed and never invoked by the reference: ignored
+        } else if (k == "NCHAINS") cfg->nchains = (uint64_t) num(1);   // extension keywords: the reference
+        else if (k == "GPU") cfg->device = (int32_t) num(1);           // answers these with "not understood"
+        else if (k == "RNG") {
+            if (n > 1 && !strcmp(tok[1], "TAUS2")) cfg->rng_kind = JMM_RNG_TAUS2;
+            else cfg->rng_kind = JMM_RNG_PHILOX;
+        } else {
+            printf("Property command %s not understood.\n", tok[0]);   // :254-256
+            dk.n_unknown++;
+        }
+    }
+    fclose(f);
+    if (cfg->pot == JMM_POT_LJ) cfg->cutoff = INFINITY;                // src/jmmMCState.cpp:294
+    if (deck) *deck = dk;
+    return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// setupMCS / freeMCS
+// ------------------------------------------------------------------------------------------------
+static jmm_status validate(const jmm_config *c) {
+    if (c->N < 2) return fail(JMM_ERR_INVALID, "N must be >= 2");
+    if (c->N > 0x7fffffffull) return fail(JMM_ERR_INVALID, "N too large");
+    if (c->nchains < 1) return fail(JMM_ERR_INVALID, "nchains must be >= 1");
+    if (c->pot < JMM_POT_LJ || c->pot > JMM_POT_HARMONIC)
+        return fail(JMM_ERR_UNKNOWN_POT, "FATAL ERROR: Unknown potential.");
+    if (c->ensemble != JMM_ENS_NPT && c->ensemble != JMM_ENS_NLT)
+        return fail(JMM_ERR_UNKNOWN_ENS, "FATAL ERROR: Unknown ensemble.");
+    if (c->rng_kind < JMM_RNG_TAUS2 || c->rng_kind > JMM_RNG_RECORDED) return fail(JMM_ERR_INVALID, "bad rng_kind");
+    if (c->mode < JMM_MODE_TABLE || c->mode > JMM_MODE_CHECKERBOARD) return fail(JMM_ERR_INVALID, "bad mode");
+    if (c->rng_kind == JMM_RNG_RECORDED && c->nchains != 1)
+        return fail(JMM_ERR_INVALID, "a recorded stream drives exactly one chain");
+    if (c->mode == JMM_MODE_CHECKERBOARD) {
+        if (c->nbn < 1) return fail(JMM_ERR_INVALID, "checkerboard sweeps need NBN >= 1 (colours = NBN+1)");
+        if (c->ensemble != JMM_ENS_NLT) return fail(JMM_ERR_INVALID, "checkerboard sweeps are NLT (fixed L) only");
+        if (c->rng_kind != JMM_RNG_PHILOX) return fail(JMM_ERR_INVALID, "checkerboard sweeps need the Philox stream");
+        if (c->N >= 0xffffffffull) return fail(JMM_ERR_INVALID, "N too large");
+    }
+    if (c->mode == JMM_MODE_TABLE) {
+        const double bytes = 8.0 * (double) c->nchains * (double) c->N * (double) (c->N - 1) / 2.0;
+        if (bytes > 64e9) return fail(JMM_ERR_INVALID, "rij table would exceed 64 GB; use JMM_MODE_RECOMPUTE");
+    }
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_destroy(jmm_handle *h) {
+    if (!h) return JMM_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_log) cudaFree(h->d_log);
+    if (h->d_partial) cudaFree(h->d_partial);
+    if (h->d_stream) cudaFree(h->d_stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
+    if (!cfg || !out) return fail(JMM_ERR_INVALID, "jmm_create: null argument");
+    *out = nullptr;
+    jmm_status st = validate(cfg);
+    if (st != JMM_OK) return st;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(JMM_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(JMM_ERR_INVALID, "device ordinal out of range");
+    CK(cudaSetDevice(cfg->device));
+
+    jmm_handle *h = new jmm_handle;
+    h->cfg = *cfg;
+    if (h->cfg.pot == JMM_POT_LJ) h->cfg.cutoff = INFINITY;
+    if (h->cfg.ensemble == JMM_ENS_NLT) h->cfg.relax = 0;           // src/jmmMCState.cpp:416-420
+    auto bail = [&](jmm_status s) { jmm_destroy(h); return s; };
+#define CKH(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) { fail(JMM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return bail(JMM_ERR_CUDA); } \
+    } while (0)
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    CKH(cudaEventCreate(&h->ev0));
+    CKH(cudaEventCreate(&h->ev1));
+
+    const uint64_t C = cfg->nchains, N = cfg->N;
+    ChainsDev &S = h->S;
+    S.nchains = C; S.N = N; S.npairs = N * (N - 1) / 2;
+    S.numTrialTypes = (cfg->ensemble == JMM_ENS_NPT) ? N + 1 : N;   // :405,415
+    S.nbn = cfg->nbn; S.ensemble = cfg->ensemble; S.relax = h->cfg.relax; S.pot = cfg->pot;
+    S.cutoff = h->cfg.cutoff; S.seed = cfg->seed; S.chain_id0 = cfg->chain_id0;
+    CKH(dalloc(h, &S.l, C)); CKH(dalloc(h, &S.P, C)); CKH(dalloc(h, &S.T, C));
+    CKH(dalloc(h, &S.maxStep, C)); CKH(dalloc(h, &S.maxdl, C));
+
+    std::vector<double> v(C);
+    auto fill = [&](double *d, double x) {
+        std::fill(v.begin(), v.end(), x);
+        return cudaMemcpyAsync(d, v.data(), C * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    };
+    const double l0 = (cfg->ensemble == JMM_ENS_NPT) ? (double) N : cfg->L;   // :553, :414
+    CKH(fill(S.l, l0)); CKH(cudaStreamSynchronize(h->stream));
+    CKH(fill(S.P, cfg->P)); CKH(cudaStreamSynchronize(h->stream));
+    CKH(fill(S.T, cfg->T)); CKH(cudaStreamSynchronize(h->stream));
+    CKH(fill(S.maxStep, cfg->maxStep)); CKH(cudaStreamSynchronize(h->stream));
+    CKH(fill(S.maxdl, cfg->maxdl)); CKH(cudaStreamSynchronize(h->stream));
+
+    if (is_cb(h)) {
+        CKH(dalloc(h, &h->cb_r[0], C * N)); CKH(dalloc(h, &h->cb_r[1], C * N));
+        CKH(dalloc(h, &h->cb_tot, C * 9)); CKH(dalloc(h, &h->cb_acc, C * 12));
+        CKH(dalloc(h, &h->cb_counts, C * 2));
+        // lattice, chain-major: same formula as :561 (k_lattice with nchains = 1 per chain)
+        for (uint64_t c = 0; c < C; ++c) {
+            k_lattice<<<nblk(N, 256), 256, 0, h->stream>>>(h->cb_r[0] + c * N, S.l + c, 1, N);
+            h->launches++;
+        }
+        CKH(cudaGetLastError());
+    } else {
+        CKH(dalloc(h, &S.r, C * N));
+        CKH(dalloc(h, &S.tot, C * 9)); CKH(dalloc(h, &S.acc, C * 12));
+        CKH(dalloc(h, &S.cnt, C * 4)); CKH(dalloc(h, &S.vAErr, C)); CKH(dalloc(h, &S.echeck, C * 2));
+        CKH(dalloc(h, &S.taus, C * 3));
+        if (cfg->mode == JMM_MODE_TABLE) CKH(dalloc(h, &S.rij, C * S.npairs));
+        CKH(dalloc(h, &h->d_cursor, 1)); CKH(dalloc(h, &h->d_err, 1));
+        // sentinels of :302-307, :542-544
+        std::vector<double> t(C * 9);
+        const double init[9] = {10E10, 10E10, 5E10, 5E10, -5E10, -5E10, 10E10, 5E10, -5E10};
+        for (int k = 0; k < 9; ++k) std::fill(t.begin() + k * C, t.begin() + (k + 1) * C, init[k]);
+        CKH(cudaMemcpyAsync(S.tot, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CKH(cudaStreamSynchronize(h->stream));
+        // taus2 state per chain, gsl_rng_set(seed) :781; chain c uses seed + chain_id0 + c
+        std::vector<uint32_t> ts(C * 3);
+        for (uint64_t c = 0; c < C; ++c) {
+            uint32_t a, b, d;
+            taus2_seed(cfg->seed + cfg->chain_id0 + c, a, b, d);
+            ts[c] = a; ts[C + c] = b; ts[2 * C + c] = d;
+        }
+        CKH(cudaMemcpyAsync(S.taus, ts.data(), ts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        CKH(cudaStreamSynchronize(h->stream));
+        k_lattice<<<nblk(C * N, 256), 256, 0, h->stream>>>(S.r, S.l, C, N);
+        h->launches++;
+        CKH(cudaGetLastError());
+        // one warp per block spreads few chains over as many SMs as possible; positions live in
+        // shared memory when an [N][32] tile fits
+        h->block = 32;
+        h->smem = (size_t) N * h->block * sizeof(double);
+        h->pos_in_smem = h->smem <= 200 * 1024;
+        if (!h->pos_in_smem) h->smem = 0;
+    }
+    CKH(cudaStreamSynchronize(h->stream));
+#undef CKH
+    *out = h;
+    return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch over (POT, TABLE, RNG)
+// ------------------------------------------------------------------------------------------------
+template <int POT, bool TABLE>
+static cudaError_t launch_start(jmm_handle *h, bool relax_only) {
+    auto kern = relax_only ? k_chains_relax<POT, TABLE> : k_chains_start<POT, TABLE>;
+    if (h->smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<nblk(h->S.nchains, h->block), h->block, h->smem, h->stream>>>(h->S, h->pos_in_smem);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <int POT, bool TABLE, int RNG>
+static cudaError_t launch_step_rng(jmm_handle *h, const StepArgs &a) {
+    auto kern = k_chains_step<POT, TABLE, RNG>;
+    if (h->smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<nblk(h->S.nchains, h->block), h->block, h->smem, h->stream>>>(h->S, a);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <int POT, bool TABLE>
+static cudaError_t launch_step_table(jmm_handle *h, const StepArgs &a) {
+    switch (h->cfg.rng_kind) {
+        case JMM_RNG_TAUS2: return launch_step_rng<POT, TABLE, kRngTaus2>(h, a);
+        case JMM_RNG_PHILOX: return launch_step_rng<POT, TABLE, kRngPhilox>(h, a);
+        default: return launch_step_rng<POT, TABLE, kRngRecorded>(h, a);
+    }
+}
+
+#define DISPATCH_POT_TABLE(h, FN, ...)                                                              \
+    ([&]() -> cudaError_t {                                                                         \
+        const bool tbl = (h)->cfg.mode == JMM_MODE_TABLE;                                           \
+        switch ((h)->cfg.pot) {                                                                     \
+            case JMM_POT_LJ: return tbl ? FN<kPotLJ, true>(__VA_ARGS__) : FN<kPotLJ, false>(__VA_ARGS__);               \
+            case JMM_POT_LJCUT: return tbl ? FN<kPotLJcut, true>(__VA_ARGS__) : FN<kPotLJcut, false>(__VA_ARGS__);      \
+            default: return tbl ? FN<kPotHarmonic, true>(__VA_ARGS__) : FN<kPotHarmonic, false>(__VA_ARGS__);           \
+        }                                                                                           \
+    })()
+
+// ------------------------------------------------------------------------------------------------
+// state in / out
+// ------------------------------------------------------------------------------------------------
+static jmm_status upload_transposed(jmm_handle *h, const double *src, double *dst, uint64_t n) {
+    const uint64_t C = h->S.nchains;
+    jmm_status st = ensure_stage(h, C * n * sizeof(double));
+    if (st != JMM_OK) return st;
+    CK(cudaMemcpyAsync(h->d_stage, src, C * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_transpose_in<<<nblk(C * n, 256), 256, 0, h->stream>>>(h->d_stage, dst, C, n);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));          // the caller may reuse src right away
+    return JMM_OK;
+}
+
+static jmm_status download_transposed(jmm_handle *h, const double *src, double *dst, uint64_t n) {
+    const uint64_t C = h->S.nchains;
+    jmm_status st = ensure_stage(h, C * n * sizeof(double));
+    if (st != JMM_OK) return st;
+    k_transpose_out<<<nblk(C * n, 256), 256, 0, h->stream>>>(src, h->d_stage, C, n);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, h->d_stage, C * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_set_state(jmm_handle *h, const double *r, const double *l, const double *P, const double *T) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains, N = h->S.N;
+    if (r) {
+        if (is_cb(h)) {
+            CK(cudaMemcpyAsync(h->cb_r[h->cb_cur], r, C * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        } else {
+            jmm_status st = upload_transposed(h, r, h->S.r, N);
+            if (st != JMM_OK) return st;
+        }
+    }
+    if (l) CK(cudaMemcpyAsync(h->S.l, l, C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (P) CK(cudaMemcpyAsync(h->S.P, P, C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (T) CK(cudaMemcpyAsync(h->S.T, T, C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_set_step_sizes(jmm_handle *h, const double *maxStep, const double *maxdl) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains;
+    if (maxStep) CK(cudaMemcpyAsync(h->S.maxStep, maxStep, C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (maxdl) CK(cudaMemcpyAsync(h->S.maxdl, maxdl, C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_get_step_sizes(jmm_handle *h, double *maxStep, double *maxdl) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains;
+    if (maxStep) CK(cudaMemcpyAsync(maxStep, h->S.maxStep, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (maxdl) CK(cudaMemcpyAsync(maxdl, h->S.maxdl, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_get_state(jmm_handle *h, double *r, double *l, double *totals, double *accum, uint64_t *counters) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains, N = h->S.N;
+    jmm_status st;
+    if (is_cb(h)) {
+        if (r) CK(cudaMemcpyAsync(r, h->cb_r[h->cb_cur], C * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (totals) CK(cudaMemcpyAsync(totals, h->cb_tot, C * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (accum) CK(cudaMemcpyAsync(accum, h->cb_acc, C * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (counters) {
+            std::vector<unsigned long long> c2(C * 2);
+            CK(cudaMemcpyAsync(c2.data(), h->cb_counts, C * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (uint64_t c = 0; c < C; ++c) {
+                counters[4 * c + 0] = c2[2 * c]; counters[4 * c + 1] = c2[2 * c + 1] - c2[2 * c];
+                counters[4 * c + 2] = 0; counters[4 * c + 3] = 0;
+            }
+        }
+    } else {
+        if (r && (st = download_transposed(h, h->S.r, r, N)) != JMM_OK) return st;
+        if (totals && (st = download_transposed(h, h->S.tot, totals, 9)) != JMM_OK) return st;
+        if (accum && (st = download_transposed(h, h->S.acc, accum, 12)) != JMM_OK) return st;
+        if (counters) {
+            std::vector<uint64_t> t(C * 4);
+            CK(cudaMemcpyAsync(t.data(), h->S.cnt, C * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (uint64_t c = 0; c < C; ++c)
+                for (int k = 0; k < 4; ++k) counters[4 * c + k] = t[k * C + c];
+        }
+    }
+    if (l) CK(cudaMemcpyAsync(l, h->S.l, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_zero_accum(jmm_handle *h) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    double *a = is_cb(h) ? h->cb_acc : h->S.acc;
+    CK(cudaMemsetAsync(a, 0, h->S.nchains * 12 * sizeof(double), h->stream));
+    return JMM_OK;
+}
+
+extern "C" uint64_t jmm_step_number(const jmm_handle *h) { return h ? (is_cb(h) ? h->halfsweeps : h->sn) : 0; }
+extern "C" uint64_t jmm_stream_cursor(const jmm_handle *h) { return h ? h->cursor : 0; }
+extern "C" uint64_t jmm_kernel_launches(const jmm_handle *h) { return h ? h->launches : 0; }
+
+extern "C" double jmm_last_kernel_ms(const jmm_handle *hc) {
+    jmm_handle *h = const_cast<jmm_handle *>(hc);
+    if (!h || !h->ev0 || !h->ev1) return -1.0;
+    cudaSetDevice(h->cfg.device);
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+    return (double) ms;
+}
+
+extern "C" jmm_status jmm_set_stream(jmm_handle *h, void *cuda_stream) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) CK(cudaStreamDestroy(h->stream));
+    h->stream = (cudaStream_t) cuda_stream;
+    h->own_stream = false;
+    return JMM_OK;
+}
+
+extern "C" void *jmm_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void jmm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" jmm_status jmm_echeck_stats(jmm_handle *h, uint64_t *checks, uint64_t *discrepancies) {
+    if (!h || is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_echeck_stats: many-chain handles only");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains;
+    std::vector<uint64_t> t(2 * C);
+    CK(cudaMemcpyAsync(t.data(), h->S.echeck, 2 * C * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    uint64_t a = 0, b = 0;
+    for (uint64_t c = 0; c < C; ++c) { a += t[c]; b += t[C + c]; }
+    if (checks) *checks = a;
+    if (discrepancies) *discrepancies = b;
+    return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// start / relax / adjust
+// ------------------------------------------------------------------------------------------------
+static jmm_status totals_parallel(jmm_handle *h, const double *r, uint64_t ps, uint64_t cs, double *out, uint64_t ks, uint64_t ocs);
+
+extern "C" jmm_status jmm_start(jmm_handle *h) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    if (is_cb(h)) {
+        // totals of the initial configuration (what the step-0 fad establishes, :907-946), then the
+        // first updateThermo (src/Main.cpp:96) as a zero-length "finish"
+        jmm_status st = totals_parallel(h, h->cb_r[h->cb_cur], 1, h->S.N, h->cb_tot, 1, 9);
+        if (st != JMM_OK) return st;
+        k_sweep_finish<<<(unsigned) h->S.nchains, 32, 0, h->stream>>>(nullptr, 0, 0, h->S.N, h->S.l, h->cb_tot, h->cb_acc, 1);
+        h->launches++;
+        CK(cudaGetLastError());
+        return JMM_OK;
+    }
+    CK(DISPATCH_POT_TABLE(h, launch_start, h, false));
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_relax_volume(jmm_handle *h) {
+    if (!h || is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_relax_volume: many-chain handles only");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(DISPATCH_POT_TABLE(h, launch_start, h, true));
+    return JMM_OK;
+}
+
+// maxDisAdjust :2100-2115 / maxDVAdjust :2120-2139 with the host's libm, like the reference
+extern "C" jmm_status jmm_adjust_step_sizes(jmm_handle *h, int32_t do_dis, int32_t do_vol) {
+    if (!h || is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_adjust_step_sizes: many-chain handles only");
+    if (!do_dis && !do_vol) return JMM_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains;
+    const double N = (double) h->S.N;
+    std::vector<uint64_t> cnt(4 * C), vA(C);
+    std::vector<double> ms(C), mv(C);
+    CK(cudaMemcpyAsync(cnt.data(), h->S.cnt, 4 * C * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(vA.data(), h->S.vAErr, C * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ms.data(), h->S.maxStep, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(mv.data(), h->S.maxdl, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    volatile double idealRatio = 0.5;
+    for (uint64_t c = 0; c < C; ++c) {
+        const uint64_t d0 = cnt[c], d1 = cnt[C + c], v0 = cnt[2 * C + c], v1 = cnt[3 * C + c];
+        if (do_dis) {
+            const double actualRatio = (double) d0 / (d0 + d1);
+            ms[c] = ms[c] * log(0.672924 * idealRatio + 0.0644284) / log(0.672924 * (actualRatio + 0.0644284));
+            if (ms[c] < 0.002) ms[c] = 0.002;
+            else if (ms[c] > 0.5) ms[c] = 0.5;
+        }
+        if (do_vol && (v0 + v1 - vA[c]) > 0) {
+            vA[c] = v0 + v1;
+            const double actualRatio = (double) v0 / (v0 + v1);
+            mv[c] = mv[c] * log(0.672924 * idealRatio + 0.0644284) / log(0.672924 * (actualRatio + 0.0644284));
+            if (mv[c] < 0.002 * N) mv[c] = 0.002 * N;
+            else if (mv[c] > 0.10 * N) mv[c] = 0.50 * N;
+        }
+    }
+    CK(cudaMemcpyAsync(h->S.maxStep, ms.data(), C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->S.maxdl, mv.data(), C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->S.vAErr, vA.data(), C * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// energy
+// ------------------------------------------------------------------------------------------------
+template <int POT>
+static cudaError_t launch_totals_partial(jmm_handle *h, const double *r, uint64_t ps, uint64_t cs, int nblocks, int threads) {
+    k_totals_partial<POT><<<(unsigned) (h->S.nchains * nblocks), threads, 0, h->stream>>>(
+        r, ps, cs, h->S.N, h->S.nbn, h->S.cutoff, h->S.l, nblocks, h->d_partial);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+static jmm_status ensure_partial(jmm_handle *h, size_t bytes) {
+    if (h->partial_bytes >= bytes) return JMM_OK;
+    if (h->d_partial) CK(cudaFree(h->d_partial));
+    h->d_partial = nullptr; h->partial_bytes = 0;
+    CK(cudaMalloc((void **) &h->d_partial, bytes));
+    h->partial_bytes = bytes;
+    return JMM_OK;
+}
+
+static jmm_status totals_parallel(jmm_handle *h, const double *r, uint64_t ps, uint64_t cs, double *out, uint64_t ks, uint64_t ocs) {
+    const uint64_t C = h->S.nchains, N = h->S.N;
+    const int threads = N >= 256 ? 256 : (int) std::max<uint64_t>(32, ((N + 31) / 32) * 32);
+    uint64_t want = (N + threads - 1) / threads;                     // blocks per chain
+    const uint64_t cap = std::max<uint64_t>(1, (148ull * 8) / C);    // keep the grid near 8 CTAs per SM
+    const int nblocks = (int) std::max<uint64_t>(1, std::min(want, cap));
+    jmm_status st = ensure_partial(h, C * nblocks * 9 * sizeof(double));
+    if (st != JMM_OK) return st;
+    cudaError_t e;
+    switch (h->cfg.pot) {
+        case JMM_POT_LJ: e = launch_totals_partial<kPotLJ>(h, r, ps, cs, nblocks, threads); break;
+        case JMM_POT_LJCUT: e = launch_totals_partial<kPotLJcut>(h, r, ps, cs, nblocks, threads); break;
+        default: e = launch_totals_partial<kPotHarmonic>(h, r, ps, cs, nblocks, threads); break;
+    }
+    CK(e);
+    k_totals_finish<<<nblk(C * 9, 128), 128, 0, h->stream>>>(h->d_partial, nblocks, C, out, ks, ocs);
+    h->launches++;
+    CK(cudaGetLastError());
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_energy(jmm_handle *h, double *totals, int32_t exact_order) {
+    if (!h || !totals) return fail(JMM_ERR_INVALID, "jmm_energy: null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains;
+    jmm_status st = ensure_stage(h, 2 * C * 9 * sizeof(double));
+    if (st != JMM_OK) return st;
+    double *d_out = h->d_stage + C * 9;          // [9][C] (many-chain) or [C][9] (checkerboard)
+    h->timed = false; tick(h);
+    if (is_cb(h)) {
+        if (exact_order) return fail(JMM_ERR_INVALID, "exact_order is a many-chain (one thread per chain) path");
+        st = totals_parallel(h, h->cb_r[h->cb_cur], 1, h->S.N, d_out, 1, 9);
+        if (st != JMM_OK) return st;
+        tock(h);
+        CK(cudaMemcpyAsync(totals, d_out, C * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return JMM_OK;
+    }
+    if (exact_order) {
+        switch (h->cfg.pot) {
+            case JMM_POT_LJ: k_chains_totals_exact<kPotLJ><<<nblk(C, 32), 32, 0, h->stream>>>(h->S, d_out); break;
+            case JMM_POT_LJCUT: k_chains_totals_exact<kPotLJcut><<<nblk(C, 32), 32, 0, h->stream>>>(h->S, d_out); break;
+            default: k_chains_totals_exact<kPotHarmonic><<<nblk(C, 32), 32, 0, h->stream>>>(h->S, d_out); break;
+        }
+        h->launches++;
+        CK(cudaGetLastError());
+    } else {
+        st = totals_parallel(h, h->S.r, C, 1, d_out, C, 1);
+        if (st != JMM_OK) return st;
+    }
+    tock(h);
+    k_transpose_out<<<nblk(C * 9, 256), 256, 0, h->stream>>>(d_out, h->d_stage, C, 9);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(totals, h->d_stage, C * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step
+// ------------------------------------------------------------------------------------------------
+extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *rng_stream, uint64_t n_words, uint8_t *accept_log) {
+    if (!h || is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_step: many-chain handles only (use jmm_sweep)");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains;
+    if (h->cfg.rng_kind == JMM_RNG_RECORDED) {
+        if (rng_stream) {                        // (re)load a stream; NULL keeps consuming the loaded one
+            if (h->stream_cap < n_words) {
+                if (h->d_stream) CK(cudaFree(h->d_stream));
+                h->d_stream = nullptr; h->stream_cap = 0;
+                CK(cudaMalloc((void **) &h->d_stream, std::max<uint64_t>(n_words, 1) * sizeof(uint32_t)));
+                h->stream_cap = n_words;
+            }
+            CK(cudaMemcpyAsync(h->d_stream, rng_stream, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(uint64_t), h->stream));
+            h->cursor = 0;
+        } else n_words = h->stream_cap;
+        if (!h->d_stream) return fail(JMM_ERR_INVALID, "JMM_RNG_RECORDED needs rng_stream");
+    }
+    if (accept_log && nsteps) {
+        const size_t need = (size_t) nsteps * C;
+        if (h->log_bytes < need) {
+            if (h->d_log) CK(cudaFree(h->d_log));
+            h->d_log = nullptr; h->log_bytes = 0;
+            CK(cudaMalloc((void **) &h->d_log, need));
+            h->log_bytes = need;
+        }
+    }
+    StepArgs a{};
+    a.eci = h->cfg.eci; a.mdai = h->cfg.mdai; a.mvai = h->cfg.mvai;
+    a.adapt_device = h->cfg.adapt == JMM_ADAPT_DEVICE;
+    volatile double idealRatio = 0.5;
+    a.log_ideal = log(0.672924 * idealRatio + 0.0644284);
+    a.stream = h->d_stream; a.n_words = n_words; a.cursor = h->d_cursor; a.err = h->d_err;
+    a.pos_in_smem = h->pos_in_smem;
+    const bool relax_on = h->S.relax > 0 && h->S.ensemble == kEnsNPT;
+
+    h->timed = false;
+    uint64_t remaining = nsteps, done = 0;
+    while (remaining) {
+        uint64_t n = remaining;
+        if (!a.adapt_device) {                   // split at the reference's host-side events, src/Main.cpp:145-176
+            if (a.mdai) n = std::min(n, a.mdai - h->sn % a.mdai);
+            if (a.mvai) n = std::min(n, a.mvai - h->sn % a.mvai);
+            if (relax_on && h->sn < 1000000ull) n = std::min(n, 10000 - h->sn % 10000);
+        }
+        a.sn0 = h->sn; a.nsteps = n;
+        a.accept_log = accept_log ? h->d_log + done * C : nullptr;
+        tick(h);
+        CK(DISPATCH_POT_TABLE(h, launch_step_table, h, a));
+        tock(h);
+        h->sn += n; remaining -= n; done += n;
+        if (!a.adapt_device) {
+            const bool dis = a.mdai && h->sn % a.mdai == 0, vol = a.mvai && h->sn % a.mvai == 0;
+            if (dis || vol) {
+                jmm_status st = jmm_adjust_step_sizes(h, dis, vol);
+                if (st != JMM_OK) return st;
+            }
+            if (relax_on && h->sn % 10000 == 0 && h->sn < 1000000ull) {
+                jmm_status st = jmm_relax_volume(h);
+                if (st != JMM_OK) return st;
+            }
+        }
+    }
+    if (accept_log && nsteps) {
+        CK(cudaMemcpyAsync(accept_log, h->d_log, (size_t) nsteps * C, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (h->cfg.rng_kind == JMM_RNG_RECORDED) {
+        int err = 0;
+        CK(cudaMemcpyAsync(&h->cursor, h->d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (err) return fail(JMM_ERR_STREAM, "recorded random stream exhausted");
+    }
+    return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// checkerboard sweeps
+// ------------------------------------------------------------------------------------------------
+struct SweepShape { int tile, halo, nsub, threads, G; size_t smem; };
+
+static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
+    SweepShape s{};
+    const int nbn = h->cfg.nbn, ncol = nbn + 1;
+    const uint64_t N = h->S.N;
+    s.G = nbn >= 16 ? 32 : 1;
+    // shared-memory budget: window (tile + 2*halo) doubles; aim at ~2 sweeps per launch, <= 25 % halo overhead
+    const int budget = 200 * 1024 / 8;                      // doubles
+    int nsub = (int) std::min<uint64_t>(want_sub, (uint64_t) 2 * ncol);
+    int tile, halo;
+    for (;;) {
+        halo = nsub * nbn;
+        halo += halo & 1;
+        tile = budget - 2 * halo - 1024;
+        if (tile >= 8 * halo || nsub == 1) break;
+        nsub = std::max(1, nsub / 2);
+    }
+    tile = std::max(tile, 2 * ncol);
+    // enough tiles to fill the machine: at least ~148 CTAs over all chains when N allows
+    const uint64_t min_tiles = std::max<uint64_t>(1, (148 + h->S.nchains - 1) / h->S.nchains);
+    uint64_t t_fill = (N + min_tiles - 1) / min_tiles;
+    t_fill += t_fill & 1;
+    tile = (int) std::min<uint64_t>((uint64_t) tile, std::max<uint64_t>(t_fill, (uint64_t) 4 * halo));
+    tile = (int) std::min<uint64_t>((uint64_t) tile, N + (N & 1));
+    tile &= ~1;
+    if (tile < 2) tile = 2;
+    s.tile = tile; s.halo = halo; s.nsub = nsub;
+    const int per_sub = (tile + ncol - 1) / ncol;           // trials per half-sweep per tile
+    int threads = s.G == 1 ? per_sub : per_sub * 32;
+    threads = std::min(1024, std::max(64, ((threads + 31) / 32) * 32));
+    s.threads = threads;
+    s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) nsub * 4 + 16;
+    return s;
+}
+
+template <int POT>
+static cudaError_t launch_sweep(jmm_handle *h, const SweepShape &s, const SweepDev &W, uint64_t step0, int nsub, unsigned ntiles) {
+    dim3 grid(ntiles, (unsigned) h->S.nchains);
+    cudaError_t e;
+    if (s.G == 1) {
+        e = cudaFuncSetAttribute(k_sweep<POT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
+        if (e != cudaSuccess) return e;
+        k_sweep<POT, 1><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, h->d_partial, h->cb_counts);
+    } else {
+        e = cudaFuncSetAttribute(k_sweep<POT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
+        if (e != cudaSuccess) return e;
+        k_sweep<POT, 32><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, h->d_partial, h->cb_counts);
+    }
+    h->launches++;
+    return cudaGetLastError();
+}
+
+extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *trials_out) {
+    if (!h || !is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_sweep: JMM_MODE_CHECKERBOARD handles only");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains, N = h->S.N;
+    std::vector<unsigned long long> c0(2 * C), c1(2 * C);
+    if (trials_out) {
+        CK(cudaMemcpyAsync(c0.data(), h->cb_counts, 2 * C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->timed = false;
+    uint64_t remaining = n_halfsweeps;
+    while (remaining) {
+        const SweepShape s = sweep_shape(h, remaining);
+        const int nsub = (int) std::min<uint64_t>(remaining, (uint64_t) s.nsub);
+        const unsigned ntiles = (unsigned) ((N + s.tile - 1) / s.tile);
+        jmm_status st = ensure_partial(h, C * (size_t) nsub * ntiles * 9 * sizeof(double));
+        if (st != JMM_OK) return st;
+        SweepDev W{};
+        W.nchains = C; W.N = N; W.nbn = h->cfg.nbn; W.ncol = h->cfg.nbn + 1; W.cutoff = h->S.cutoff;
+        W.r_in = h->cb_r[h->cb_cur]; W.r_out = h->cb_r[h->cb_cur ^ 1];
+        W.l = h->S.l; W.T = h->S.T; W.maxStep = h->S.maxStep; W.seed = h->cfg.seed; W.chain_id0 = h->cfg.chain_id0;
+        tick(h);
+        cudaError_t e;
+        switch (h->cfg.pot) {
+            case JMM_POT_LJ: e = launch_sweep<kPotLJ>(h, s, W, h->halfsweeps, nsub, ntiles); break;
+            case JMM_POT_LJCUT: e = launch_sweep<kPotLJcut>(h, s, W, h->halfsweeps, nsub, ntiles); break;
+            default: e = launch_sweep<kPotHarmonic>(h, s, W, h->halfsweeps, nsub, ntiles); break;
+        }
+        CK(e);
+        k_sweep_finish<<<(unsigned) C, 32, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, N, h->S.l, h->cb_tot, h->cb_acc, 0);
+        h->launches++;
+        CK(cudaGetLastError());
+        tock(h);
+        h->cb_cur ^= 1;
+        h->halfsweeps += nsub;
+        remaining -= nsub;
+    }
+    if (trials_out) {
+        CK(cudaMemcpyAsync(c1.data(), h->cb_counts, 2 * C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        uint64_t t = 0;
+        for (uint64_t c = 0; c < C; ++c) t += c1[2 * c + 1] - c0[2 * c + 1];
+        *trials_out = t;
+    }
+    return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// misc
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *jmm_last_error(void) { return g_err.c_str(); }
+extern "C" const char *jmm_version(void) { return "jmmonedmc_b200 0.1 (sm_100a)"; }
+
+__global__ void k_rng_selftest(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                               uint64_t seed, uint32_t *out, uint32_t *taus_out, uint32_t n) {
+    const Philox4 b = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    for (int i = 0; i < 4; ++i) out[i] = b.w[i];
+    uint32_t s1, s2, s3;
+    taus2_seed(seed, s1, s2, s3);
+    for (uint32_t i = 0; i < n; ++i) taus_out[i] = taus2_next(s1, s2, s3);
+}
+
+extern "C" jmm_status jmm_rng_selftest(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], uint64_t seed,
+                                       uint32_t *taus_out, uint32_t n, int32_t device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(JMM_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    CK(cudaSetDevice(device));
+    uint32_t *d = nullptr;
+    CK(cudaMalloc((void **) &d, (4 + (size_t) n) * sizeof(uint32_t)));
+    k_rng_selftest<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], seed, d, d + 4, n);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) { cudaFree(d); return fail(JMM_ERR_CUDA, cudaGetErrorString(le)); }
+    std::vector<uint32_t> hbuf(4 + (size_t) n);
+    e = cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(JMM_ERR_CUDA, cudaGetErrorString(e));
+    memcpy(out, hbuf.data(), 4 * sizeof(uint32_t));
+    if (n) memcpy(taus_out, hbuf.data() + 4, (size_t) n * sizeof(uint32_t));
+    return JMM_OK;
+}

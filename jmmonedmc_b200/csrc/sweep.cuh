@@ -1,0 +1,297 @@
+// Long-chain kernels (configs C3/C5): colour-decomposed ("checkerboard") displacement sweeps and the
+// parallel configuration-totals reduction.
+//
+// No reference counterpart: the reference makes one qad2 trial per Step (src/jmmMCState.cpp:1758-1811)
+// and keeps O(N^2) pair tables (:308-328,442-456), so N = 2^20 cannot even be allocated there.  What IS
+// the reference's is each individual trial: md, wall test, partner set |i-nm| <= NBN, the (acc-old)+new
+// sums and the Metropolis rule are exactly qad2 (:1182-1377) with distances taken from positions.
+//
+// Decomposition.  With NBN = k two particles interact iff |i-j| <= k (:1217,1312), so the particles of
+// one colour (i mod (k+1)) are mutually independent: their trials commute and are made concurrently.
+// One "half-sweep" = draw a colour uniformly (Philox), try every particle of that colour once.
+//
+// Tiling.  A thread block owns TILE consecutive particles and stages them plus HALO = nsub*NBN particles
+// on either side in shared memory with one TMA bulk copy (cp.async.bulk, 1-D).  Because every random
+// number is a pure function of (seed, chain, half-sweep, particle), neighbouring blocks recompute each
+// other's halo trials bit-identically, so a block can run nsub half-sweeps from shared memory with no
+// inter-block communication: after half-sweep t the outer (t+1)*NBN halo particles are stale and are no
+// longer used.  HBM traffic per launch: (TILE+2*HALO)*8 B read + TILE*8 B written per tile, for
+// TILE*nsub/(NBN+1) trials.  Positions are double-buffered in HBM (r_in -> r_out) so halos read by a
+// neighbour are never overwritten mid-launch.
+#pragma once
+#include <math.h>
+#include "pot.cuh"
+
+namespace jmm {
+
+struct SweepDev {
+    uint64_t nchains, N;
+    int nbn, ncol;
+    double cutoff;
+    const double *r_in;   // [nchains][N]
+    double *r_out;        // [nchains][N]
+    const double *l, *T, *maxStep;     // [nchains]
+    uint64_t seed, chain_id0;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ int colour_of(uint64_t seed, uint32_t chain, uint64_t step, int ncol) {
+    const Philox4 b = philox4x32_10((uint32_t) step, (uint32_t)(step >> 32), 0xFFFFFFFFu, kTagColour | chain,
+                                    (uint32_t) seed, (uint32_t)(seed >> 32));
+    return (int) (((uint64_t) b.w[0] * (uint64_t) ncol) >> 32);
+}
+
+// G lanes cooperate on one particle's trial.  G = 1: reference summation order; G = 32: one warp per
+// particle, lane-strided partners + xor butterfly, for wide neighbour sets (only 1 and 32 are
+// instantiated: a group must be a whole warp for the full-mask shuffles below).
+template <int POT, int G>
+__global__ void __launch_bounds__(1024) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
+                                                 double *partial /*[nchains][nsub][ntiles][9]*/,
+                                                 unsigned long long *counts /*[nchains][2] accepted, trials*/) {
+    constexpr int NC = PotTraits<POT>::NC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nwarps = blockDim.x >> 5;
+    double *w = reinterpret_cast<double *>(smem_raw);                 // window of positions
+    const int64_t N = (int64_t) S.N;
+    const int chain = blockIdx.y;
+    const int64_t tile_lo = (int64_t) blockIdx.x * tile;
+    const int64_t tile_hi = min(tile_lo + tile, N);
+    const int64_t g0 = max((int64_t) 0, tile_lo - halo);              // window = [g0, g1)
+    const int64_t g1 = min(N, tile_hi + halo);
+    const int wlen = (int) (g1 - g0);
+    const int wcap = tile + 2 * halo;
+    double *red = w + wcap;                                           // [2][nwarps][9]
+    int *colours = reinterpret_cast<int *>(red + 2 * nwarps * 9);     // [nsub]
+    __shared__ __align__(8) unsigned long long mbar;
+
+    const double *src = S.r_in + (uint64_t) chain * S.N + g0;
+    // ---- stage the window: one TMA bulk copy for the 16-byte-aligned body, plain loads for the rest
+    const int body = ((((uintptr_t) src) & 15) == 0) ? (wlen & ~1) : 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && body > 0) {
+        const uint32_t bytes = (uint32_t) body * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(w)), "l"(src), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+    }
+    for (int i = body + threadIdx.x; i < wlen; i += blockDim.x) w[i] = src[i];
+    for (int t = threadIdx.x; t < nsub; t += blockDim.x)
+        colours[t] = colour_of(S.seed, (uint32_t)(S.chain_id0 + chain), step0 + t, S.ncol);
+    if (body > 0) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+        }
+    }
+    __syncthreads();
+
+    const double lbox = S.l[chain], T = S.T[chain], maxStep = S.maxStep[chain], cutoff = S.cutoff;
+    const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32);
+    const uint32_t tag = kTagParticle | (uint32_t)(S.chain_id0 + chain);
+    const int nbn = S.nbn, ncol = S.ncol;
+    const int group = threadIdx.x / G, lane = threadIdx.x % G, ngroups = blockDim.x / G;
+    const int warp = threadIdx.x >> 5;
+    unsigned long long n_acc = 0, n_try = 0;
+
+    for (int t = 0; t < nsub; ++t) {
+        const int col = colours[t];
+        // particles whose whole neighbourhood is still valid in this window
+        const int64_t ulo = (g0 == 0) ? 0 : g0 + (int64_t)(t + 1) * nbn;
+        const int64_t uhi = (g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn;
+        const int64_t first = ulo + (((int64_t) col - ulo % ncol) + ncol) % ncol;
+        double dacc[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) dacc[k] = 0;
+        for (int64_t g = first + (int64_t) group * ncol; g < uhi; g += (int64_t) ngroups * ncol) {
+            const Philox4 b = philox4x32_10((uint32_t)(step0 + t), (uint32_t)((step0 + t) >> 32), (uint32_t) g, tag, k0, k1);
+            const double rn = u01(b.w[0]), ran = u01(b.w[1]);
+            const int x = (int) (g - g0);
+            const double rnm = w[x];
+            const double md = (rn - 0.5) * 2 * maxStep;                               // qad2 :1182
+            const double rT = rnm + md;                                               // :1183
+            const bool owned = (g >= tile_lo) && (g < tile_hi);
+            if (owned && lane == 0) ++n_try;
+            if (fabs(rT) > lbox / 2.0) continue;                                      // :1188 (group-uniform)
+            const int lo = (int) max((int64_t) 0, g - nbn) - (int) g0, hi = (int) min(N - 1, g + nbn) - (int) g0;
+            double d[NC];
+            if constexpr (G == 1) {
+                double dsum[NC], dleft[NC], po[NC], pn[NC];
+#pragma unroll
+                for (int k = 0; k < NC; ++k) { dsum[k] = 0; dleft[k] = 0; }
+                for (int p = lo; p <= hi; ++p) {
+                    if (p == x) {
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) { dleft[k] = dsum[k]; dsum[k] = 0; }
+                        continue;
+                    }
+                    const bool left = p < x;
+                    const double rp = w[p];
+                    phi<POT, true>(left ? rnm - rp : rp - rnm, cutoff, lbox, po);
+                    phi<POT, true>(left ? rT - rp : rp - rT, cutoff, lbox, pn);
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) dsum[k] = dsum[k] - po[k] + pn[k];   // :1244, :1339
+                }
+#pragma unroll
+                for (int k = 0; k < NC; ++k) d[k] = dleft[k] + dsum[k];               // :1354
+            } else {
+                double po[NC], pn[NC];
+#pragma unroll
+                for (int k = 0; k < NC; ++k) d[k] = 0;
+                for (int p = lo + lane; p <= hi; p += G) {
+                    if (p == x) continue;
+                    const bool left = p < x;
+                    const double rp = w[p];
+                    phi<POT, true>(left ? rnm - rp : rp - rnm, cutoff, lbox, po);
+                    phi<POT, true>(left ? rT - rp : rp - rT, cutoff, lbox, pn);
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) d[k] = d[k] - po[k] + pn[k];
+                }
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], off, G);
+            }
+            bool accept = d[0] <= 0;
+            if (!accept) accept = exp(-d[0] / T) > ran;                               // :1367-1377
+            if (accept) {
+                if (G > 1) __syncwarp();
+                if (lane == 0) {
+                    w[x] = rT;
+                    if (owned) {
+                        ++n_acc;
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) dacc[k] += d[k];
+                    }
+                }
+            }
+        }
+        // block-wide sum of this half-sweep's deltas over the owned particles -> partial[chain][t][tile][:]
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) dacc[k] += __shfl_xor_sync(0xffffffffu, dacc[k], off);
+        }
+        double *rbuf = red + (t & 1) * nwarps * 9;
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int k = 0; k < NC; ++k) rbuf[warp * 9 + k] = dacc[k];
+        __syncthreads();                       // also orders this half-sweep's position writes before the next reads
+        if (threadIdx.x < 9) {
+            double s = 0;
+            if (threadIdx.x < NC)
+                for (int wv = 0; wv < nwarps; ++wv) s += rbuf[wv * 9 + threadIdx.x];
+            partial[(((uint64_t) chain * nsub + t) * gridDim.x + blockIdx.x) * 9 + threadIdx.x] = s;
+        }
+    }
+
+    // ---- write back the owned particles
+    double *dst = S.r_out + (uint64_t) chain * S.N;
+    for (int64_t g = tile_lo + threadIdx.x; g < tile_hi; g += blockDim.x) dst[g] = w[g - g0];
+    // counters
+    if (G > 1 && lane != 0) { n_acc = 0; n_try = 0; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_acc += __shfl_xor_sync(0xffffffffu, n_acc, off);
+        n_try += __shfl_xor_sync(0xffffffffu, n_try, off);
+    }
+    if ((threadIdx.x & 31) == 0 && (n_acc | n_try)) {
+        atomicAdd(&counts[2 * chain], n_acc);
+        atomicAdd(&counts[2 * chain + 1], n_try);
+    }
+}
+
+// After a k_sweep launch: fold the per-tile deltas into the running totals half-sweep by half-sweep
+// (fixed summation order -> reproducible) and sample the twelve sums once per half-sweep
+// (updateThermo :1941-1961 with l constant).
+__device__ __forceinline__ void cb_sample(double (&a)[12], const double *cur, double N, double lbox) {
+    const double rho = N / lbox, E = cur[0], Vir = cur[1], HV = cur[6];
+    a[0] += rho; a[1] += rho * rho; a[2] += lbox; a[3] += lbox * lbox;
+    a[4] += E; a[5] += E * E; a[6] += lbox * E; a[7] += Vir; a[8] += Vir * Vir; a[9] += E * Vir;
+    a[10] += HV; a[11] += HV * HV;
+}
+
+// presample != 0: one extra sample of the current totals first (the updateThermo of src/Main.cpp:96)
+__global__ void k_sweep_finish(const double *partial, int nsub, int ntiles, uint64_t N, const double *l,
+                               double *tot /*[nchains][9]*/, double *acc /*[nchains][12]*/, int presample) {
+    const int chain = blockIdx.x;
+    __shared__ double cur[9];
+    if (threadIdx.x < 9) cur[threadIdx.x] = tot[chain * 9 + threadIdx.x];
+    __syncthreads();
+    double a[12];
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 12; ++k) a[k] = acc[chain * 12 + k];
+    const double lbox = l[chain];
+    if (presample && threadIdx.x == 0) cb_sample(a, cur, (double) N, lbox);
+    for (int t = 0; t < nsub; ++t) {
+        if (threadIdx.x < 9) {
+            double s = 0;
+            const double *p = partial + (((uint64_t) chain * nsub + t) * ntiles) * 9 + threadIdx.x;
+            for (int b = 0; b < ntiles; ++b) s += p[(uint64_t) b * 9];
+            cur[threadIdx.x] += s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) cb_sample(a, cur, (double) N, lbox);
+        __syncthreads();
+    }
+    if (threadIdx.x < 9) tot[chain * 9 + threadIdx.x] = cur[threadIdx.x];
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 12; ++k) acc[chain * 12 + k] = a[k];
+}
+
+// Parallel configuration totals (SURVEY §3.3 loop): grid (nblocks, nchains), rows i strided over the
+// grid, warp-shuffle + shared-memory reduction, per-block partials summed in fixed order by k_totals_finish.
+// Works for both layouts through (ps, cs) = (particle stride, chain stride).
+template <int POT>
+__global__ void __launch_bounds__(256) k_totals_partial(const double *__restrict__ r, uint64_t ps, uint64_t cs, uint64_t N, int nbn,
+                                                        double cutoff, const double *__restrict__ l, int nblocks,
+                                                        double *partial /*[nchains][nblocks][9]*/) {
+    constexpr int NC = PotTraits<POT>::NC;
+    const uint64_t chain = blockIdx.x / nblocks;      // grid.x = nchains * nblocks (grid.y is capped at 65535)
+    const uint32_t blk = blockIdx.x % nblocks;
+    const double *rc = r + chain * cs;
+    const double lbox = l[chain];
+    double s[NC], p[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) s[k] = 0;
+    for (uint64_t i = (uint64_t) blk * blockDim.x + threadIdx.x; i + 1 < N; i += (uint64_t) nblocks * blockDim.x) {
+        const uint64_t jmax = (nbn < 0 || i + (uint64_t) nbn > N - 1) ? N - 1 : i + (uint64_t) nbn;
+        const double ri = rc[i * ps];
+        for (uint64_t j = i + 1; j <= jmax; ++j) {
+            phi<POT, true>(rc[j * ps] - ri, cutoff, lbox, p);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) s[k] += p[k];
+        }
+    }
+    __shared__ double red[8][9];
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) red[threadIdx.x >> 5][k] = s[k];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0;
+        if (threadIdx.x < NC)
+            for (int wv = 0; wv < (int) (blockDim.x >> 5); ++wv) v += red[wv][threadIdx.x];
+        partial[(chain * nblocks + blk) * 9 + threadIdx.x] = v;
+    }
+}
+
+__global__ void k_totals_finish(const double *partial, int nblocks, uint64_t nchains, double *out, uint64_t ks, uint64_t cs) {
+    const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nchains * 9) return;
+    const uint64_t chain = t / 9, k = t % 9;
+    double s = 0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(chain * nblocks + b) * 9 + k];
+    out[k * ks + chain * cs] = s;
+}
+
+}  // namespace jmm

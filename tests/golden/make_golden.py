@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the COMPILED REFERENCE.
+
+The reference ships no expected outputs, so the goldens are outputs of the reference
+itself: oracle/Makefile (`make ref`) compiles /root/reference/src unchanged except for the one-token
+phiij[6]->[9] fix, with the gsl_rng_taus2 shim, and this script runs that binary single-threaded
+(the only mode in which it is deterministic) on the reference's own decks.  Run it in the build
+container (it needs /root/reference); the GPU box only reads the committed outputs.
+
+    python tests/golden/make_golden.py [--full]     # --full also runs the 5 000 000-step smalltest
+"""
+import hashlib
+import json
+import re
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import oracle as O  # noqa: E402
+
+REF_TEST = Path("/root/reference/test")
+
+
+def deck_with(text, **kw):
+    for k, v in kw.items():
+        text = re.sub(rf"^{k}\s+.*$", f"{k:<10} {v}", text, flags=re.M)
+    return text
+
+
+def summarise(stdout: str) -> dict:
+    s = {}
+    m = re.search(r"\nE = (\S+)", stdout)
+    s["final_E_printed"] = m.group(1)
+    m = re.search(r"(\d+)/(\d+)\s+(\d+)/(\d+)\s*$", stdout.strip())
+    s["counters"] = [int(x) for x in m.groups()]
+    s["verified"] = stdout.count("Energy was just verified")
+    s["discrepancy"] = stdout.count("Energy discrepancy")
+    s["relax_calls"] = stdout.count("Relaxing the Volume")
+    s["not_understood"] = re.findall(r"Property command (\S+) not understood", stdout)
+    m = re.search(r"Relaxation converged\. Length,energy: (\S+),(\S+)", stdout)
+    if m:
+        s["first_relax"] = [m.group(1), m.group(2)]
+    s["maxStep_updates"] = re.findall(r"new maxStep: (\S+)", stdout)[-4:]
+    return s
+
+
+def last_frame(config_text: str):
+    lines = config_text.strip().splitlines()
+    n = int(lines[0])
+    frame = lines[-(n + 2):]
+    box = float(frame[1].split("Box length:")[1])
+    return box, [float(x.split()[3]) for x in frame[2:]]
+
+
+def run(name, deck, keep_rng=True, keep_files=True):
+    out = HERE / name
+    out.mkdir(exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        R = O.run_reference(deck, tmp, record_rng=True)
+        (out / "INPUT").write_text(deck)
+        s = summarise(R["stdout"])
+        thermo = Path(R["thermo"]).read_bytes()
+        config = Path(R["config"]).read_bytes()
+        s["thermo_md5"] = hashlib.md5(thermo).hexdigest()
+        s["config_md5"] = hashlib.md5(config).hexdigest()
+        s["rng_words"] = int(R["rng"].size)
+        s["rng_first8"] = [int(x) for x in R["rng"][:8]]
+        s["rng_md5"] = hashlib.md5(R["rng"].tobytes()).hexdigest()
+        box, pos = last_frame(config.decode())
+        s["last_frame_box"] = box
+        s["last_frame_r"] = pos
+        s["stdout_thermo_lines"] = re.findall(r"^\d+  \S+  \S+  \S+  \S+$", R["stdout"], flags=re.M)[:40]
+        if keep_files:
+            (out / "thermo.dat.mcs").write_bytes(thermo)
+            (out / "config.dat.mcs").write_bytes(config)
+        else:
+            (out / "thermo.tail.mcs").write_bytes(b"\n".join(thermo.splitlines()[-5:]) + b"\n")
+        if keep_rng:
+            R["rng"].tofile(out / "rng.u32")
+        (out / "summary.json").write_text(json.dumps(s, indent=1) + "\n")
+        print(name, s["final_E_printed"], s["counters"], "words", s["rng_words"])
+
+
+def main():
+    O.build()
+    small = (REF_TEST / "INPUT_smalltest").read_text()
+    run("smalltest_12", deck_with(small, NUMSTEPS=12, TPI=1, CPI=1))
+    run("smalltest_2000", deck_with(small, NUMSTEPS=2000, TPI=100, CPI=500))
+    run("smalltest_20000", deck_with(small, NUMSTEPS=20000), keep_rng=False)
+    run("inputstd", (REF_TEST / "INPUTstd").read_text())
+    big = (REF_TEST / "INPUT").read_text()
+    run("input_n2000_40", deck_with(big, NUMSTEPS=40, CPI=40, TPI=5), keep_rng=True)
+    if "--full" in sys.argv:
+        run("smalltest_full", small, keep_rng=False, keep_files=False)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/jmm_gpu.h), against the oracle.
+
+Bars: bit-exact for positions, accept/reject sequences, counters and (in the reference-order paths)
+totals and running sums; 1e-12 relative for sums whose order of addition differs (north_star).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import bits_equal, jmm_config_from_deck, oracle_accept_log, rel_err
+
+pytestmark = pytest.mark.gpu
+
+PHILOX_KAT = [  # Random123 kat_vectors, philox4x32-10
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def test_device_generators(J, O, gold):
+    for ctr, key, want in PHILOX_KAT:
+        got, _ = J.rng_selftest(ctr, key, 1, 0)
+        assert tuple(got) == want
+    _, words = J.rng_selftest((0,) * 4, (0, 0), 92847, 4096)
+    assert np.array_equal(words, gold("smalltest_2000")["rng"][:4096])      # the reference's own stream
+    _, w1 = J.rng_selftest((0,) * 4, (0, 0), 1, 10000)
+    assert int(w1[9999]) == 2733957125                                       # GSL rng/test.c known answer
+
+
+@pytest.mark.parametrize("pot,nbn,cutoff", [("LJ", -1, math.inf), ("LJ", 3, math.inf), ("LJcut", -1, 2.5),
+                                             ("LJcut", 4, 5.0), ("HARMONIC", 1, math.inf), ("HARMONIC", 2, 1.6)])
+@pytest.mark.parametrize("N,C", [(10, 7), (80, 33), (257, 3)])
+def test_configuration_totals(J, O, pot, nbn, cutoff, N, C):
+    rng = np.random.default_rng(N * 1000 + C + nbn)
+    from jmmonedmc_b200.capi import config
+    P = {"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT, "HARMONIC": J.POT_HARMONIC}[pot]
+    l = rng.uniform(1.0, 1.3, C) * N
+    # ordered, non-overlapping particles (LJ diverges at 0), jittered lattice
+    r = np.stack([((np.arange(N) + 0.5) / N - 0.5) * l[c] + rng.uniform(-0.2, 0.2, N) for c in range(C)])
+    with J.Handle(config(N=N, pot=P, nbn=nbn, cutoff=cutoff, nchains=C, T=1.0, P=1.0)) as h:
+        h.set_state(r=r, l=l)
+        exact = h.energy(exact_order=True)
+        fast = h.energy(exact_order=False)
+    want = np.stack([O.totals_of(r[c], nbn, O.POT[pot], cutoff, 1.0, 1, l[c]) for c in range(C)])
+    assert bits_equal(exact, want), "reference-order totals must be bit-exact"
+    scale = np.maximum(np.abs(want), 1e-300)
+    assert np.max(np.abs(fast - want) / scale) < 1e-12, "parallel totals within 1e-12 relative (north_star)"
+
+
+def _lockstep(J, O, gold, name, nsteps, rng_kind, chunk=None):
+    g = gold(name)
+    d = O.parse_deck(g["deck_text"])
+    words = g.get("rng")
+    if words is None or rng_kind == "taus2-as-recorded":
+        words = O.taus2_words(int(d["SEED"]), 3 * nsteps + 64)
+    # oracle: TABLE mode (bit-exact against the compiled reference, see test_oracle_vs_reference.py)
+    oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_TAUS2, mode=O.MODE_TABLE))
+    oc.start()
+    kind = J.RNG_TAUS2 if rng_kind == "taus2" else J.RNG_RECORDED
+    cfg = jmm_config_from_deck(J, d, rng_kind=kind, mode=J.MODE_TABLE, adapt=J.ADAPT_HOST)
+    with J.Handle(cfg) as h:
+        h.start()
+        s0 = h.get_state()
+        assert bits_equal(s0["r"][0], oc.r) and bits_equal(s0["totals"][0][:2], oc.totals[:2])
+        assert bits_equal(s0["l"], [oc.l]) and bits_equal(s0["accum"][0][:10], oc.accum[:10])
+        want_log = oracle_accept_log(oc, nsteps)
+        logs = []
+        if chunk is None:
+            logs.append(h.step(nsteps, rng_stream=words if kind == J.RNG_RECORDED else None, accept_log=True))
+        else:
+            done = 0
+            while done < nsteps:
+                n = min(chunk, nsteps - done)
+                logs.append(h.step(n, rng_stream=words if (kind == J.RNG_RECORDED and done == 0) else None, accept_log=True))
+                done += n
+        got_log = np.concatenate(logs)[:, 0]
+        s = h.get_state()
+        assert np.array_equal(got_log & 3, want_log), "accept/reject sequence differs from the reference's"
+        assert bits_equal(s["r"][0], oc.r), "final positions must be bit-identical"
+        assert bits_equal(s["l"], [oc.l])
+        assert np.array_equal(s["counters"][0], oc.counters)
+        nc = 2 if d["POT"] == "HARMONIC" else 9
+        assert bits_equal(s["totals"][0][:nc], oc.totals[:nc])
+        na = 10 if d["POT"] == "HARMONIC" else 12
+        assert bits_equal(s["accum"][0][:na], oc.accum[:na])
+        ms, mv = h.get_step_sizes()
+        assert bits_equal([ms[0], mv[0]], list(oc.step_sizes))
+        assert h.echeck_stats() == oc.echecks
+        if kind == J.RNG_RECORDED and g.get("rng") is not None and nsteps == int(d["NUMSTEPS"]):
+            assert h.stream_cursor == g["summary"]["rng_words"]
+        return s, g
+
+
+def test_lockstep_smalltest_recorded_stream(J, O, gold):
+    """north_star: fed the stream recorded from the compiled reference, reproduce INPUT_smalltest exactly."""
+    s, g = _lockstep(J, O, gold, "smalltest_2000", 2000, "recorded")
+    assert [int(x) for x in s["counters"][0]] == g["summary"]["counters"]
+    assert np.allclose(s["r"][0], g["summary"]["last_frame_r"], rtol=0, atol=5e-7)     # %.8G text of the reference
+    assert float("%.8G" % s["totals"][0][0]) == float(g["summary"]["final_E_printed"])
+
+
+def test_lockstep_smalltest_chunked_launches(J, O, gold):
+    _lockstep(J, O, gold, "smalltest_2000", 2000, "recorded", chunk=333)
+
+
+def test_lockstep_smalltest_20000_device_taus2(J, O, gold):
+    """Same deck, taus2 generated on the device; 20 000 steps = 20 adjustments, 2 periodic relaxations."""
+    s, g = _lockstep(J, O, gold, "smalltest_20000", 20000, "taus2")
+    assert [int(x) for x in s["counters"][0]] == g["summary"]["counters"]
+    assert float("%.8G" % s["totals"][0][0]) == float(g["summary"]["final_E_printed"])
+
+
+def test_lockstep_inputstd(J, O, gold):
+    s, g = _lockstep(J, O, gold, "inputstd", 10, "recorded")
+    assert [int(x) for x in s["counters"][0]] == g["summary"]["counters"]
+    assert float("%.8G" % s["l"][0]) == g["summary"]["last_frame_box"] or abs(s["l"][0] - g["summary"]["last_frame_box"]) < 5e-6
+
+
+def test_lockstep_input_n2000(J, O, gold):
+    s, g = _lockstep(J, O, gold, "input_n2000_40", 40, "recorded")
+    assert [int(x) for x in s["counters"][0]] == g["summary"]["counters"]
+    assert float("%.8G" % s["totals"][0][0]) == float(g["summary"]["final_E_printed"])
+
+
+def test_recorded_stream_exhaustion_is_an_error(J, O, gold):
+    g = gold("smalltest_2000")
+    d = O.parse_deck(g["deck_text"])
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_RECORDED, mode=J.MODE_TABLE, adapt=J.ADAPT_HOST)
+    with J.Handle(cfg) as h:
+        h.start()
+        with pytest.raises(J.JmmError) as e:
+            h.step(100, rng_stream=g["rng"][:50])
+        assert e.value.status == -4
+
+
+DECKS = {
+    "std": dict(N=10, POT="HARMONIC", NBN=1, CUTOFF=math.inf, ENSEMBLE="NPT", P=0.7, T=0.4, MAXSTEP=0.1, MAXDV=1.0,
+                ENGCHECK=1, DADJ=100, VADJ=100, SEED=125, RELAX=0),
+    "small": dict(N=10, POT="LJ", NBN=-1, CUTOFF=math.inf, ENSEMBLE="NPT", P=1.0, T=0.9, MAXSTEP=0.1, MAXDV=0.1,
+                  ENGCHECK=1000, DADJ=1000, VADJ=1000, SEED=92847, RELAX=1),
+    "ljcut_nbn": dict(N=24, POT="LJcut", NBN=3, CUTOFF=2.5, ENSEMBLE="NPT", P=0.5, T=0.7, MAXSTEP=0.15, MAXDV=0.4,
+                      ENGCHECK=50, DADJ=200, VADJ=300, SEED=7, RELAX=1),
+    "nlt": dict(N=16, POT="LJ", NBN=2, CUTOFF=math.inf, ENSEMBLE="NLT", L=20.0, T=0.8, MAXSTEP=0.2, MAXDV=0.1,
+                ENGCHECK=10, DADJ=0, VADJ=0, SEED=3, RELAX=0),
+}
+
+
+@pytest.mark.parametrize("name", list(DECKS))
+@pytest.mark.parametrize("mode", ["recompute", "table"])
+def test_philox_many_chains_bit_exact(J, O, name, mode):
+    """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
+    every chain must equal the oracle bit for bit, including after adjustments and relaxations."""
+    d = DECKS[name]
+    C, nsteps, id0 = 37, 1500, 1000
+    jm = J.MODE_RECOMPUTE if mode == "recompute" else J.MODE_TABLE
+    om = O.MODE_RECOMPUTE if mode == "recompute" else O.MODE_TABLE
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=jm, adapt=J.ADAPT_HOST, nchains=C, chain_id0=id0)
+    with J.Handle(cfg) as h:
+        h.start()
+        log = h.step(nsteps, accept_log=True)
+        s = h.get_state()
+        ms, mv = h.get_step_sizes()
+    nc = 2 if d["POT"] == "HARMONIC" else 9
+    na = 10 if d["POT"] == "HARMONIC" else 12
+    for c in range(C):
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=om, chain_id=id0 + c))
+        oc.start()
+        want_log = oracle_accept_log(oc, nsteps)
+        assert np.array_equal(log[:, c] & 3, want_log), f"chain {c}: accept sequence"
+        assert bits_equal(s["r"][c], oc.r), f"chain {c}: positions"
+        assert bits_equal(s["l"][c:c + 1], [oc.l])
+        assert np.array_equal(s["counters"][c], oc.counters)
+        assert bits_equal(s["totals"][c][:nc], oc.totals[:nc]), f"chain {c}: totals"
+        assert bits_equal(s["accum"][c][:na], oc.accum[:na]), f"chain {c}: running sums"
+        assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
+
+
+def test_device_adaptation_matches_until_first_adjust_then_statistically(J, O):
+    d = dict(DECKS["std"])
+    C = 64
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE, nchains=C)
+    with J.Handle(cfg) as h:
+        h.start()
+        h.step(99)                                   # DADJ = 100: no adjustment yet
+        s = h.get_state()
+        for c in (0, 17, 63):
+            oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=c))
+            oc.start(); oc.run(99)
+            assert bits_equal(s["r"][c], oc.r) and np.array_equal(s["counters"][c], oc.counters)
+        h.step(20000 - 99)
+        ms, mv = h.get_step_sizes()
+        s = h.get_state()
+    ref = []
+    for c in range(8):
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=c))
+        oc.start(); oc.run(20000)
+        ref.append(oc.step_sizes)
+    ref = np.array(ref)
+    # CUDA log vs glibc log differ by <= 1 ulp; the adapted step sizes stay statistically the same
+    assert abs(np.mean(ms) - np.mean(ref[:, 0])) < 0.25 * np.mean(ref[:, 0])
+    assert np.all(s["counters"].sum(axis=1) == 20001)
+    assert h is not None
+
+
+def test_energy_bookkeeping_stays_consistent(J, O):
+    """Size-independent property at the bench size: after many steps the incrementally maintained
+    totals equal a fresh recompute from the positions (the invariant ECheck guards, :1998)."""
+    d = dict(DECKS["std"])
+    C = 4096
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE, nchains=C)
+    with J.Handle(cfg) as h:
+        h.start()
+        h.step(5000)
+        s = h.get_state()
+        fresh = h.energy(exact_order=True)
+        checks, disc = h.echeck_stats()
+    assert checks == C * 5000 and disc == 0
+    assert np.all(s["counters"].sum(axis=1) == 5001)                      # step 0 counts as a displacement (:968)
+    assert np.max(np.abs(s["totals"][:, 0] - fresh[:, 0])) < 1e-9
+    assert np.max(np.abs(s["totals"][:, 1] - fresh[:, 1])) < 1e-9
+    assert np.all(np.diff(s["r"], axis=1) > 0), "particles never reorder (HARMONIC returns 1e11 for d<=0)"
+    assert np.all(np.abs(s["r"]) <= s["l"][:, None] / 2)                   # hard walls at +-l/2 (:1188)
+    acc = s["accum"]
+    assert np.allclose(acc[:, 2] / 5001, s["l"], rtol=0.5)                 # <L> is of the order of L
+
+
+@pytest.mark.parametrize("pot,nbn,cutoff,N,C", [("LJcut", 4, 5.0, 20000, 2), ("LJ", 2, math.inf, 5001, 1),
+                                                 ("HARMONIC", 1, math.inf, 8192, 3), ("LJ", 24, math.inf, 6000, 2)])
+def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C):
+    from jmmonedmc_b200.capi import config
+    P = {"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT, "HARMONIC": J.POT_HARMONIC}[pot]
+    seed, id0, T, ms, nhs = 92847, 5, 0.9, 0.12, 3 * (nbn + 1) + 1
+    L = N * 1.12
+    cfg = config(N=N, pot=P, nbn=nbn, cutoff=cutoff, ensemble=J.ENS_NLT, L=L, T=T, maxStep=ms, seed=seed,
+                 nchains=C, chain_id0=id0, mode=J.MODE_CHECKERBOARD)
+    with J.Handle(cfg) as h:
+        h.start()
+        s0 = h.get_state()
+        trials = h.sweep(nhs)
+        s = h.get_state()
+        fresh = h.energy()
+    ncol = nbn + 1
+    for c in range(C):
+        r = ((np.arange(N) + 0.5) / N - 0.5) * L
+        assert bits_equal(s0["r"][c], r)
+        t0 = O.totals_of(r, nbn, O.POT[pot], cutoff, 1.0, 1, L)
+        assert rel_err(s0["totals"][c], np.where(t0 == 0, 1e-300, t0)) < 1e-12 or np.allclose(s0["totals"][c], t0, rtol=1e-12, atol=1e-9)
+        tot, nacc, ntry = t0.copy(), 0, 0
+        for t in range(nhs):
+            col = O.colour_of_step(seed, id0 + c, t, ncol)
+            a, dt = O.colour_halfsweep(r, L, nbn, O.POT[pot], cutoff, T, ms, seed, id0 + c, t, ncol, col)
+            nacc += a; ntry += len(range(col, N, ncol)); tot += dt
+        assert bits_equal(s["r"][c], r), f"chain {c}: positions after {nhs} half-sweeps"
+        assert int(s["counters"][c][0]) == nacc and int(s["counters"][c].sum()) == ntry
+        assert np.allclose(s["totals"][c], tot, rtol=1e-11, atol=1e-8 * N)
+        assert np.allclose(fresh[c], O.totals_of(r, nbn, O.POT[pot], cutoff, 1.0, 1, L), rtol=1e-11, atol=1e-8 * N)
+    assert trials == sum(int(x) for x in s["counters"].sum(axis=1))
