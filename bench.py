@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — trial moves/s of the jmmOneDMC hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4|c5]
+
+Workload at N=1 (and per GPU at N>1, weak scaling): BASELINE.json configs[1] = the test/INPUTstd deck
+(N=10, HARMONIC, NBN 1, NPT, P=0.7, T=0.4, MAXSTEP 0.1, MAXDV 1.0, ENGCHECK 1, DADJ/VADJ 100) replicated
+as 4096 independent chains per B200, Philox stream keyed by global chain id.
+One bench "step" = one jmm_step() launch advancing every chain by MC_PER_STEP Monte-Carlo steps.
+
+  value     trial moves/s, all ranks, state resident in HBM, CUDA-event timed (max over ranks)
+  e2e       the same through the C ABI with HOST buffers: jmm_set_state (H2D) + jmm_step + jmm_get_state
+            (D2H) inside the timed region
+  roofline  the dominant kernel (k_chains_step) against the fp64 pipe — the binding roof of this
+            layout (bytes/trial -> 0) — with the HBM view beside it
+  cpu_baseline  the reference's own CPU program (oracle/_ref, compiled from /root/reference) on the
+            host cores, one single-threaded process per core (its OpenMP path is racy)
+
+--impl reference times that CPU program alone on the same config and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+C2 = dict(N=10, P=0.7, T=0.4, pot="HARMONIC", nbn=1, maxStep=0.1, maxdl=1.0, eci=1, mdai=100, mvai=100, seed=125,
+          nchains=4096)
+MC_PER_STEP = 20000
+METRIC = "MC trial moves/sec"
+UNIT = "trial moves/s"
+WORKLOAD = "C2: test/INPUTstd deck (N=10, HARMONIC, NBN 1, NPT, ENGCHECK 1, DADJ/VADJ 100) x 4096 chains per GPU"
+
+# algorithmic work per trial, SURVEY.md §8(d): displacement 10*p+37 flop with p in {1,2} (mean 1.8 over the
+# 10 particles), volume trial (fav) 15*9 = 135 flop at 1/11 of the trials, ECheck every step 4*9 = 36 flop
+FLOP_PER_TRIAL = (10.0 / 11.0) * (10 * 1.8 + 37) + (1.0 / 11.0) * 135 + 36
+BYTES_PER_CHAIN_PER_LAUNCH = 2 * (8 * C2["N"] + 256)          # §8(d): state load + store
+
+
+def deck_text(numsteps: int, seed: int) -> str:
+    """The C2 deck as an INPUT file for the reference binary: print intervals pushed out and the
+    (out-of-scope) histograms reduced to one bin so they do not burden the reference."""
+    big = 10 ** 12
+    return (f"N          10\nP          0.7\nT          0.4\nNUMSTEPS   {numsteps}\nPOT        HARMONIC\nNBN        1\n"
+            f"MAXSTEP    0.1\nMAXDV      1.0\nCPI        {big}\nTPI        {big}\nRBW        0.01\nRHONB      1\n"
+            f"RHOPI      {big}\nGSW        100\nGNS        1\nGBW        0.01\nGNB        1\nGPI        {big}\n"
+            f"SEED       {seed}\nENGCHECK   1\nDADJ       100\nVADJ       100\n")
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_sample(numsteps: int, nproc: int) -> dict:
+    """nproc independent single-threaded copies of the compiled reference, one deck each."""
+    from oracle import oracle as O
+    if not O.REF_BIN.exists():
+        O.build()
+    if not O.REF_BIN.exists():
+        return run_port_sample(numsteps, nproc)
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = []
+        env = dict(os.environ, OMP_NUM_THREADS="1")
+        env.pop("JMM_RNG_LOG", None)
+        for p in range(nproc):
+            d = Path(tmp) / f"p{p}"
+            d.mkdir()
+            (d / "INPUT").write_text(deck_text(numsteps, 125 + p))
+        t0 = time.perf_counter()
+        for p in range(nproc):
+            procs.append(subprocess.Popen([str(O.REF_BIN)], cwd=Path(tmp) / f"p{p}", env=env,
+                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        rcs = [p.wait() for p in procs]
+        dt = time.perf_counter() - t0
+    if any(rcs):
+        raise RuntimeError(f"reference binary failed: {rcs}")
+    return {"seconds": dt, "trials": numsteps * nproc, "kind": "reference", "cores": nproc,
+            "sample": f"{nproc} independent single-thread processes of oracle/_ref/jmmOneDMC_ref (reference Main.cpp "
+                      f"-O3, OMP_NUM_THREADS=1) x {numsteps} steps of the C2 deck, stdout to /dev/null, set-up included"}
+
+
+def run_port_sample(numsteps: int, nproc: int) -> dict:
+    """Fallback when the compiled reference did not travel: the C restatement, one process per core."""
+    code = ("import sys; sys.path.insert(0, %r)\nfrom oracle import oracle as O\n"
+            "d=dict(N=10,POT='HARMONIC',NBN=1,CUTOFF=float('inf'),ENSEMBLE='NPT',P=0.7,T=0.4,MAXSTEP=0.1,MAXDV=1.0,"
+            "ENGCHECK=1,DADJ=100,VADJ=100,SEED=int(sys.argv[1]),RELAX=0)\n"
+            "c=O.Chain(O.config_from_deck(d,mode=O.MODE_TABLE)); c.start(); c.run(int(sys.argv[2]))\n") % str(ROOT)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(125 + p), str(numsteps)]) for p in range(nproc)]
+    rcs = [p.wait() for p in procs]
+    dt = time.perf_counter() - t0
+    if any(rcs):
+        raise RuntimeError("oracle port failed")
+    return {"seconds": dt, "trials": numsteps * nproc, "kind": "port", "cores": nproc,
+            "sample": f"{nproc} processes of the C restatement (oracle/jmm_oracle.c, table mode) x {numsteps} steps, "
+                      "interpreter start-up included"}
+
+
+def reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_step = 400_000                      # ~4 s of CPU work per process per bench step
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        run_reference_sample(50_000, cores)
+    t, trials, last = 0.0, 0, None
+    for _ in range(args.steps):
+        last = run_reference_sample(per_step, cores)
+        t += last["seconds"]; trials += last["trials"]
+    v = trials / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chains_per_step": cores, "mc_steps_per_chain_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 8 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def gpu_arm(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import jmmonedmc_b200 as J
+    from jmmonedmc_b200.capi import config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA path is the only implementation (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    J.build()
+
+    C = C2["nchains"]
+    cfg = config(N=C2["N"], pot=J.POT_HARMONIC, nbn=C2["nbn"], ensemble=J.ENS_NPT, P=C2["P"], T=C2["T"],
+                 maxStep=C2["maxStep"], maxdl=C2["maxdl"], eci=C2["eci"], mdai=C2["mdai"], mvai=C2["mvai"], seed=C2["seed"],
+                 nchains=C, chain_id0=rank * C, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE,
+                 device=local)
+    h = J.Handle(cfg)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)          # the library launches on torch's stream so torch events time it
+    h.start()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        h.step(MC_PER_STEP)
+    launches0 = h.kernel_launches
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1.0)                      # L2 flush between timed iterations, outside the event pair
+        a.record(stream)
+        h.step(MC_PER_STEP)
+        b.record(stream)
+        kernel_ms.append(None)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = h.kernel_launches - launches0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    trials_per_rank = C * MC_PER_STEP * args.steps
+    value = world * trials_per_rank / (dev_ms * 1e-3)
+
+    # dominant kernel alone: library-side CUDA events around k_chains_step (same stream)
+    h.step(MC_PER_STEP)
+    k_ms = h.last_kernel_ms
+    trials_per_launch = C * MC_PER_STEP
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region
+    s = h.get_state()
+    r_host, l_host = s["r"], s["l"]
+    h2d = r_host.nbytes + l_host.nbytes
+    d2h = r_host.nbytes + l_host.nbytes + s["totals"].nbytes + s["accum"].nbytes + s["counters"].nbytes
+    for _ in range(2):
+        h.set_state(r=r_host, l=l_host); h.step(MC_PER_STEP); s = h.get_state(); r_host, l_host = s["r"], s["l"]
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.set_state(r=r_host, l=l_host)
+        h.step(MC_PER_STEP)
+        s = h.get_state()
+        r_host, l_host = s["r"], s["l"]
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * trials_per_rank / float(te.item())
+
+    # ---- final summary reduction: one NCCL allgather of the per-chain records
+    rec = torch.from_numpy(np.concatenate([s["accum"], s["totals"][:, :2], s["l"][:, None],
+                                           s["counters"].astype(np.float64)], axis=1)).cuda()
+    if world > 1:
+        allrec = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(allrec, rec)
+        rec = torch.cat(allrec)
+    nchains_total = int(rec.shape[0])
+    disc = h.echeck_stats()[1]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        fp64_peak = J.lib().jmm_fp64_peak_tflops(local)
+        k_s = k_ms * 1e-3
+        achieved_tf = trials_per_launch * FLOP_PER_TRIAL / k_s / 1e12
+        achieved_gbs = C * BYTES_PER_CHAIN_PER_LAUNCH / k_s / 1e9
+        cpu = None
+        try:
+            smp = run_reference_sample(400_000, host_cores())
+            cpu = {"value": smp["trials"] / smp["seconds"], "unit": UNIT, "cores": smp["cores"], "kind": smp["kind"],
+                   "sample": smp["sample"]}
+        except Exception as e:                      # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chains_per_gpu": C, "chains_total": nchains_total,
+                       "mc_steps_per_chain_per_step": MC_PER_STEP, "rng": "philox4x32-10", "adapt": "device",
+                       "l2": "flushed between timed iterations (256 MiB fill)", "echeck_discrepancies": disc},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+            "roofline": {"bound": "fp64", "kernel": "k_chains_step<HARMONIC,recompute,philox>",
+                         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None,
+                         "peak_source": "DFMA microbenchmark in libjmmgpu (jmm_fp64_peak_tflops), measured in this run; "
+                                        "MEASURED_PEAKS.json has no fp64 entry",
+                         "flop_per_trial": FLOP_PER_TRIAL, "kernel_ms": k_ms, "traffic": None,
+                         "note": "serial Markov chains: latency-bound, see DESIGN.md §roofline",
+                         "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
+                                 "bytes_per_launch": C * BYTES_PER_CHAIN_PER_LAUNCH}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,10 @@ jmm_status jmm_set_stream(jmm_handle *h, void *cuda_stream);
 void      *jmm_host_alloc(uint64_t bytes);
 void       jmm_host_free(void *p);
 
+/* fp64 pipe microbenchmark for the roofline denominator (MEASURED_PEAKS.json has no fp64 entry):
+ * independent DFMA chains on every SM; returns TFLOP/s counting one FMA as 2 flop, <0 on error */
+double     jmm_fp64_peak_tflops(int32_t device);
+
 const char *jmm_last_error(void);
 const char *jmm_version(void);
 /* device-side self-test of the generators: fills out[0..3] with Philox4x32-10(ctr,key) and

@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
         "jmm_set_stream": (C.c_int32, [H, C.c_void_p]),
         "jmm_host_alloc": (C.c_void_p, [C.c_uint64]),
         "jmm_host_free": (None, [C.c_void_p]),
+        "jmm_fp64_peak_tflops": (C.c_double, [C.c_int32]),
         "jmm_last_error": (C.c_char_p, []),
         "jmm_version": (C.c_char_p, []),
         "jmm_rng_selftest": (C.c_int32, [u32p, u32p, u32p, C.c_uint64, u32p, C.c_uint32, C.c_int32]),

@@ -864,6 +864,47 @@ __global__ void k_rng_selftest(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
     for (uint32_t i = 0; i < n; ++i) taus_out[i] = taus2_next(s1, s2, s3);
 }
 
+// 16 independent DFMA chains per thread, 2 x 148 x 4 CTAs of 256 threads: saturates the fp64 pipe
+__global__ void k_fp64_peak(double *out, int iters, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = a + i + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = __fma_rn(x[i], b, a);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 12345.678) out[0] = s;      // never true; keeps the chains alive
+}
+
+extern "C" double jmm_fp64_peak_tflops(int32_t device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { fail(JMM_ERR_CUDA, "no CUDA device"); return -1.0; }
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    double *d = nullptr;
+    if (cudaMalloc((void **) &d, 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_fp64_peak<<<blocks, threads>>>(d, iters, 1.0000001, 0.9999999);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 16.0 * (double) iters * (double) blocks * threads;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return best;
+}
+
 extern "C" jmm_status jmm_rng_selftest(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], uint64_t seed,
                                        uint32_t *taus_out, uint32_t n, int32_t device) {
     int ndev = 0;

@@ -224,7 +224,7 @@ def test_energy_bookkeeping_stays_consistent(J, O):
     assert np.all(np.diff(s["r"], axis=1) > 0), "particles never reorder (HARMONIC returns 1e11 for d<=0)"
     assert np.all(np.abs(s["r"]) <= s["l"][:, None] / 2)                   # hard walls at +-l/2 (:1188)
     acc = s["accum"]
-    assert np.allclose(acc[:, 2] / 5001, s["l"], rtol=0.5)                 # <L> is of the order of L
+    assert abs(np.mean(acc[:, 2] / 5001) - np.mean(s["l"])) < 0.2 * np.mean(s["l"])   # ensemble <L> ~ current L
 
 
 @pytest.mark.parametrize("pot,nbn,cutoff,N,C", [("LJcut", 4, 5.0, 20000, 2), ("LJ", 2, math.inf, 5001, 1),
