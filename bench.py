@@ -281,7 +281,7 @@ def gpu_arm(args) -> None:
         achieved_gbs = C * BYTES_PER_CHAIN_PER_LAUNCH / k_s / 1e9
         cpu = None
         try:
-            smp = run_reference_sample(400_000, host_cores())
+            smp = run_reference_sample(int(os.environ.get("JMM_BENCH_CPU_STEPS", "400000")), host_cores())
             cpu = {"value": smp["trials"] / smp["seconds"], "unit": UNIT, "cores": smp["cores"], "kind": smp["kind"],
                    "sample": smp["sample"]}
         except Exception as e:                      # the baseline is reported, never required

@@ -15,6 +15,7 @@
 #include "../../include/jmm_gpu.h"
 #include "chains.cuh"
 #include "sweep.cuh"
+#include "coop.cuh"
 
 using namespace jmm;
 
@@ -42,6 +43,9 @@ struct jmm_handle {
     // many-chain launch shape
     int block = 32, pos_in_smem = 1;
     size_t smem = 0;
+    int coop_g = 0;                 // lanes per chain of the cooperative kernel (0 = one chain per thread)
+    int coop_npad = 0;
+    size_t coop_smem = 0;
     // recorded stream
     uint32_t *d_stream = nullptr;
     uint64_t stream_cap = 0;
@@ -313,6 +317,20 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
         h->smem = (size_t) N * h->block * sizeof(double);
         h->pos_in_smem = h->smem <= 200 * 1024;
         if (!h->pos_in_smem) h->smem = 0;
+        // Few chains: let G lanes share a chain (coop.cuh) so that ~4096+ warps are in flight.
+        if (cfg->mode == JMM_MODE_RECOMPUTE && cfg->rng_kind == JMM_RNG_PHILOX) {
+            int g = 0;
+            if (C <= 4096) g = 32; else if (C <= 8192) g = 16; else if (C <= 16384) g = 8;
+            if (const char *e = getenv("JMM_COOP_G")) g = atoi(e);
+            if (g == 8 || g == 16 || g == 32) {
+                const int nc = (cfg->pot == JMM_POT_HARMONIC) ? 2 : 9;
+                const int scratch = kCoopChunk * 2 * nc;
+                int npad = (int) N;
+                npad += (17 - ((npad + scratch) % 16)) % 16;          // rows of different groups hit different banks
+                const size_t bytes = (size_t) (128 / g) * (npad + scratch) * sizeof(double);
+                if (bytes <= 200 * 1024) { h->coop_g = g; h->coop_npad = npad; h->coop_smem = bytes; }
+            }
+        }
     }
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
@@ -347,8 +365,33 @@ static cudaError_t launch_step_rng(jmm_handle *h, const StepArgs &a) {
     return cudaGetLastError();
 }
 
+template <int POT, int G>
+static cudaError_t launch_step_coop_g(jmm_handle *h, const StepArgs &a) {
+    auto kern = k_chains_step_coop<POT, G>;
+    if (h->coop_smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->coop_smem);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned per_block = 128 / G;
+    kern<<<nblk(h->S.nchains, per_block), 128, h->coop_smem, h->stream>>>(h->S, a, h->coop_npad);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <int POT>
+static cudaError_t launch_step_coop(jmm_handle *h, const StepArgs &a) {
+    switch (h->coop_g) {
+        case 8: return launch_step_coop_g<POT, 8>(h, a);
+        case 16: return launch_step_coop_g<POT, 16>(h, a);
+        default: return launch_step_coop_g<POT, 32>(h, a);
+    }
+}
+
 template <int POT, bool TABLE>
 static cudaError_t launch_step_table(jmm_handle *h, const StepArgs &a) {
+    if constexpr (!TABLE) {
+        if (h->coop_g) return launch_step_coop<POT>(h, a);
+    }
     switch (h->cfg.rng_kind) {
         case JMM_RNG_TAUS2: return launch_step_rng<POT, TABLE, kRngTaus2>(h, a);
         case JMM_RNG_PHILOX: return launch_step_rng<POT, TABLE, kRngPhilox>(h, a);
