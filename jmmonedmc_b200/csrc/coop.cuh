@@ -39,6 +39,7 @@ struct Coop {
     // lane identity
     uint32_t lane;                                // 0..G-1 inside the group
     uint32_t gmask;                               // lanes of this group inside the warp
+    bool chain_of_bonds;                          // NBN == 1 and N-1 <= G: one nearest-neighbour pair per lane
 
     __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
     __device__ __forceinline__ void set_l(double lnew) {
@@ -76,6 +77,19 @@ template <int POT, int G, int NCX, class F>
 __device__ __forceinline__ void coop_pair_sum(const Coop<POT, G> &c, F term, double (&out)[NCX]) {
 #pragma unroll
     for (int k = 0; k < NCX; ++k) out[k] = 0;
+    if (c.chain_of_bonds) {
+        // NBN == 1 and N-1 <= G: pair q is (q, q+1) and lane q owns it.  The ordered sum is a walk over
+        // the lanes with shuffles: no scratch, no barrier.
+        double t[NCX];
+#pragma unroll
+        for (int k = 0; k < NCX; ++k) t[k] = 0;
+        if (c.lane + 1 < c.N) term(c.lane, c.lane + 1, t);
+        for (uint32_t q = 0; q + 1 < c.N; ++q) {
+#pragma unroll
+            for (int k = 0; k < NCX; ++k) out[k] += __shfl_sync(c.gmask, t[k], q, G);
+        }
+        return;
+    }
     const uint32_t total = c.npairs_included();
     // per-lane cursor over pairs q = lane, lane+G, ... : (i, off) with j = i+1+off
     uint32_t i = 0, off = c.lane;
@@ -127,13 +141,17 @@ __device__ __forceinline__ double coop_full_energy(const Coop<POT, G> &c, double
 // ECheck's ETest (:1974-1993): only compared against 1e-4, so lane partial sums + butterfly
 template <int POT, int G>
 __device__ __forceinline__ double coop_energy_unordered(const Coop<POT, G> &c) {
-    const uint32_t total = c.npairs_included();
-    uint32_t i = 0, off = c.lane;
     double e = 0;
-    for (uint32_t q = c.lane; q < total; q += G) {
-        while (off >= c.rowlen(i)) { off -= c.rowlen(i); ++i; }
-        e += phi_energy<POT>(c.r[i + 1 + off] - c.r[i], c.cutoff);
-        off += G;
+    if (c.chain_of_bonds) {
+        if (c.lane + 1 < c.N) e = phi_energy<POT>(c.r[c.lane + 1] - c.r[c.lane], c.cutoff);
+    } else {
+        const uint32_t total = c.npairs_included();
+        uint32_t i = 0, off = c.lane;
+        for (uint32_t q = c.lane; q < total; q += G) {
+            while (off >= c.rowlen(i)) { off -= c.rowlen(i); ++i; }
+            e += phi_energy<POT>(c.r[i + 1 + off] - c.r[i], c.cutoff);
+            off += G;
+        }
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) e += __shfl_xor_sync(c.gmask, e, o, G);
@@ -222,7 +240,24 @@ __device__ __forceinline__ uint8_t coop_displacement(Coop<POT, G> &c, uint32_t n
     double dsum[NC], dleft[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) { dsum[k] = 0; dleft[k] = 0; }
-    if (c.nbn >= 0 && c.nbn <= 4) {
+    if (c.nbn == 1) {
+        // at most one partner on each side: straight-line, predicated
+        double po[NC], pn[NC];
+        if (nm > 0) {
+            const double rp = c.r[nm - 1];
+            phi_h<POT, true>(rnm - rp, c.cutoff, c.two_over_l, po);
+            phi_h<POT, true>(rT - rp, c.cutoff, c.two_over_l, pn);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) dleft[k] = 0.0 - po[k] + pn[k];
+        }
+        if (nm + 1 < N) {
+            const double rp = c.r[nm + 1];
+            phi_h<POT, true>(rp - rnm, c.cutoff, c.two_over_l, po);
+            phi_h<POT, true>(rp - rT, c.cutoff, c.two_over_l, pn);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) dsum[k] = 0.0 - po[k] + pn[k];
+        }
+    } else if (c.nbn >= 0 && c.nbn <= 4) {
         double po[NC], pn[NC];
         for (uint32_t p = lo; p <= hi; ++p) {
             if (p == nm) {
@@ -351,6 +386,7 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
     Coop<POT, G> c;
     c.lane = threadIdx.x % G;
     c.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    c.chain_of_bonds = (S.nbn == 1) && (S.N - 1 <= (uint64_t) G);
     const size_t per_group = (size_t) npad + (size_t) kCoopChunk * 2 * NC;
     c.r = smem + gib * per_group;
     c.sc = c.r + npad;
@@ -372,15 +408,25 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
     const uint32_t scale = 0xffffffffu / ntt;
     const bool scaling_volume = (POT == kPotLJ) && S.nbn < 0;
     uint64_t sn = a.sn0;
-    uint64_t eci_left = a.eci ? a.eci - sn % a.eci : ~0ull;
-    uint64_t mdai_left = (a.adapt_device && a.mdai) ? a.mdai - sn % a.mdai : ~0ull;
-    uint64_t mvai_left = (a.adapt_device && a.mvai) ? a.mvai - sn % a.mvai : ~0ull;
-    uint64_t relax_left = (a.adapt_device && S.relax > 0 && S.ensemble == kEnsNPT) ? 10000 - sn % 10000 : ~0ull;
+    // countdowns to the next multiple of each interval; a launch is far shorter than 2^32 steps and the
+    // host never asks for more than that per launch, so 32-bit counters saturated at 2^32-1 are exact
+    auto until = [&](uint64_t every) -> uint32_t {
+        if (!every) return 0xffffffffu;
+        const uint64_t left = every - sn % every;
+        return left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left;
+    };
+    uint32_t eci_left = until(a.eci);
+    uint32_t mdai_left = a.adapt_device ? until(a.mdai) : 0xffffffffu;
+    uint32_t mvai_left = a.adapt_device ? until(a.mvai) : 0xffffffffu;
+    uint32_t relax_left = (a.adapt_device && S.relax > 0 && S.ensemble == kEnsNPT) ? until(10000) : 0xffffffffu;
+    const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
+    const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
+    const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
 
     uint32_t my_nm = 0, my_w1 = 0, my_w2 = 0;                 // this lane's share of the Philox batch
     uint32_t batch_pos = G;                                   // G = empty
 
-    for (uint64_t s = 0; s < a.nsteps; ++s) {
+    for (uint32_t s = 0; s < (uint32_t) a.nsteps; ++s) {
         ++sn;
         if (batch_pos == G) {                                 // lane j draws the block of step sn + j
             const uint64_t mine = sn + c.lane;
@@ -403,16 +449,16 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
                 flags = scaling_volume ? coop_volume_scaling(c, rn, ran) : coop_volume_full(c, rn, ran);
             } else flags = coop_volume_full(c, rn, ran);
         }
-        if (--eci_left == 0) { coop_energy_check(c); eci_left = a.eci; }
+        if (--eci_left == 0) { coop_energy_check(c); eci_left = eci32; }
         coop_update_thermo(c);
-        if (a.accept_log && c.lane == 0) a.accept_log[s * C + chain] = flags;
+        if (a.accept_log && c.lane == 0) a.accept_log[(uint64_t) s * C + chain] = flags;
         if (a.adapt_device) {
             if (--mdai_left == 0) {
                 const double actualRatio = (double) c.cnt[0] / (double)(c.cnt[0] + c.cnt[1]);
                 c.maxStep = c.maxStep * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
                 if (c.maxStep < 0.002) c.maxStep = 0.002;
                 else if (c.maxStep > 0.5) c.maxStep = 0.5;
-                mdai_left = a.mdai;
+                mdai_left = mdai32;
             }
             if (--mvai_left == 0) {
                 if ((c.cnt[2] + c.cnt[3] - c.vAErr) > 0) {
@@ -422,7 +468,7 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
                     if (c.maxdl < 0.002 * (double) c.N) c.maxdl = 0.002 * (double) c.N;
                     else if (c.maxdl > 0.10 * (double) c.N) c.maxdl = 0.50 * (double) c.N;
                 }
-                mvai_left = a.mvai;
+                mvai_left = mvai32;
             }
             if (--relax_left == 0) { if (sn < 1000000ull) coop_relax_volume(c); relax_left = 10000; }
         }
