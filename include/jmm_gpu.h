@@ -52,7 +52,10 @@ enum { JMM_MODE_TABLE = 0,     /* incremental rij table = the reference's arithm
        JMM_MODE_CHECKERBOARD = 2 }; /* one long chain, colour-decomposed sweeps (jmm_sweep)      */
 /* who runs maxDisAdjust / maxDVAdjust (src/jmmMCState.cpp:2100-2139) */
 enum { JMM_ADAPT_HOST = 0,     /* host libm log(): bit-identical step sizes to the reference      */
-       JMM_ADAPT_DEVICE = 1 }; /* inside the kernel: no launch boundary every DADJ/VADJ steps     */
+       JMM_ADAPT_DEVICE = 1,   /* inside the kernel: no launch boundary every DADJ/VADJ steps     */
+       JMM_ADAPT_CALLER = 2 }; /* jmm_step never adjusts or relaxes: the caller drives the cadence
+                                  of src/Main.cpp:145-176 itself (jmm_adjust_step_sizes,
+                                  jmm_relax_volume) — what the jmmMCState.h-compatible shim does   */
 
 /* index of each total in a 9-vector: the order phi() writes them, src/pot.cpp:90-100 */
 enum { JMM_E = 0, JMM_VIR, JMM_E12, JMM_VIR12, JMM_E6, JMM_VIR6, JMM_HV, JMM_HV12, JMM_HV6, JMM_NTOT };
@@ -121,6 +124,9 @@ jmm_status jmm_get_step_sizes(jmm_handle *h, double *maxStep, double *maxdl);
 /* The prologue of main(): fad(mcs,&0,&0.5) "step 0" (src/Main.cpp:66-68, jmmMCState.cpp:853-1003),
  * relaxVolume if RELAX (src/Main.cpp:71-73) and the first updateThermo (src/Main.cpp:96). */
 jmm_status jmm_start(jmm_handle *h);
+/* the same three pieces individually, for callers that keep main()'s own call sequence:
+ * fad (src/Main.cpp:66-68), relaxVolume (:71-73), updateThermo (:96) */
+jmm_status jmm_start_parts(jmm_handle *h, int32_t do_fad, int32_t do_relax, int32_t do_thermo);
 
 /* Configuration totals from the current positions: the pair loop shared by fad :907-946,
  * fav :2196-2235, ECheck :1974-1993, moveVolume :2865-2904.  totals [nchains][9].

@@ -15,7 +15,7 @@ POT_LJ, POT_LJCUT, POT_HARMONIC = 0, 1, 2
 ENS_NPT, ENS_NLT = 0, 1
 RNG_TAUS2, RNG_PHILOX, RNG_RECORDED = 0, 1, 2
 MODE_TABLE, MODE_RECOMPUTE, MODE_CHECKERBOARD = 0, 1, 2
-ADAPT_HOST, ADAPT_DEVICE = 0, 1
+ADAPT_HOST, ADAPT_DEVICE, ADAPT_CALLER = 0, 1, 2
 LOG_ACCEPTED, LOG_VOLUME, LOG_WALL = 1, 2, 4
 
 
@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
         "jmm_set_step_sizes": (C.c_int32, [H, dp, dp]),
         "jmm_get_step_sizes": (C.c_int32, [H, dp, dp]),
         "jmm_start": (C.c_int32, [H]),
+        "jmm_start_parts": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_int32]),
         "jmm_energy": (C.c_int32, [H, dp, C.c_int32]),
         "jmm_step": (C.c_int32, [H, C.c_uint64, u32p, C.c_uint64, u8p]),
         "jmm_relax_volume": (C.c_int32, [H]),
@@ -184,6 +185,9 @@ class Handle:
 
     def start(self):
         _check(self.L.jmm_start(self.h))
+
+    def start_parts(self, fad=True, relax=True, thermo=True):
+        _check(self.L.jmm_start_parts(self.h, int(fad), int(relax), int(thermo)))
 
     def energy(self, exact_order=False):
         t = np.empty((self.C, 9))

@@ -440,23 +440,27 @@ __device__ __forceinline__ void store_chain(const Chain<POT> &ch, const ChainsDe
 // ---------------------------------------------------------------- kernels
 
 // Prologue of main(): fad step 0 (src/Main.cpp:66-68), relaxVolume if RELAX (:71-73), updateThermo (:96)
+constexpr int kStartFad = 1, kStartRelax = 2, kStartThermo = 4;
+
 template <int POT, bool TABLE>
-__global__ void k_chains_start(ChainsDev S, int pos_in_smem) {
+__global__ void k_chains_start(ChainsDev S, int pos_in_smem, int parts) {
     extern __shared__ double smem[];
     const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= S.nchains) return;
     Chain<POT> ch;
     load_chain(ch, S, c, pos_in_smem ? smem + threadIdx.x : nullptr, blockDim.x);
-    table_from_positions<POT, TABLE>(ch);          // fad sets rijTrial for every pair, :918
-    recompute_into_state<POT, TABLE>(ch);
-    ch.cnt[0]++;                                   // :968
-    if (S.relax > 0 && S.ensemble == kEnsNPT) relax_volume<POT, TABLE>(ch);
-    update_thermo(ch);
+    if (parts & kStartFad) {
+        table_from_positions<POT, TABLE>(ch);      // fad sets rijTrial for every pair, :918
+        recompute_into_state<POT, TABLE>(ch);
+        ch.cnt[0]++;                               // :968
+    }
+    if ((parts & kStartRelax) && S.relax > 0 && S.ensemble == kEnsNPT) relax_volume<POT, TABLE>(ch);
+    if (parts & kStartThermo) update_thermo(ch);
     store_chain(ch, S, c, pos_in_smem != 0);
 }
 
 template <int POT, bool TABLE>
-__global__ void k_chains_relax(ChainsDev S, int pos_in_smem) {
+__global__ void k_chains_relax(ChainsDev S, int pos_in_smem, int /*parts*/) {
     extern __shared__ double smem[];
     const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= S.nchains) return;

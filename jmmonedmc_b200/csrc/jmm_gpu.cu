@@ -197,6 +197,7 @@ static jmm_status validate(const jmm_config *c) {
         return fail(JMM_ERR_UNKNOWN_ENS, "FATAL ERROR: Unknown ensemble.");
     if (c->rng_kind < JMM_RNG_TAUS2 || c->rng_kind > JMM_RNG_RECORDED) return fail(JMM_ERR_INVALID, "bad rng_kind");
     if (c->mode < JMM_MODE_TABLE || c->mode > JMM_MODE_CHECKERBOARD) return fail(JMM_ERR_INVALID, "bad mode");
+    if (c->adapt < JMM_ADAPT_HOST || c->adapt > JMM_ADAPT_CALLER) return fail(JMM_ERR_INVALID, "bad adapt");
     if (c->rng_kind == JMM_RNG_RECORDED && c->nchains != 1)
         return fail(JMM_ERR_INVALID, "a recorded stream drives exactly one chain");
     if (c->mode == JMM_MODE_CHECKERBOARD) {
@@ -343,13 +344,13 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
 // kernel dispatch over (POT, TABLE, RNG)
 // ------------------------------------------------------------------------------------------------
 template <int POT, bool TABLE>
-static cudaError_t launch_start(jmm_handle *h, bool relax_only) {
+static cudaError_t launch_start(jmm_handle *h, bool relax_only, int parts = kStartFad | kStartRelax | kStartThermo) {
     auto kern = relax_only ? k_chains_relax<POT, TABLE> : k_chains_start<POT, TABLE>;
     if (h->smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<nblk(h->S.nchains, h->block), h->block, h->smem, h->stream>>>(h->S, h->pos_in_smem);
+    kern<<<nblk(h->S.nchains, h->block), h->block, h->smem, h->stream>>>(h->S, h->pos_in_smem, parts);
     h->launches++;
     return cudaGetLastError();
 }
@@ -586,6 +587,15 @@ extern "C" jmm_status jmm_start(jmm_handle *h) {
     return JMM_OK;
 }
 
+extern "C" jmm_status jmm_start_parts(jmm_handle *h, int32_t do_fad, int32_t do_relax, int32_t do_thermo) {
+    if (!h || is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_start_parts: many-chain handles only");
+    CK(cudaSetDevice(h->cfg.device));
+    const int parts = (do_fad ? kStartFad : 0) | (do_relax ? kStartRelax : 0) | (do_thermo ? kStartThermo : 0);
+    if (!parts) return JMM_OK;
+    CK(DISPATCH_POT_TABLE(h, launch_start, h, false, parts));
+    return JMM_OK;
+}
+
 extern "C" jmm_status jmm_relax_volume(jmm_handle *h) {
     if (!h || is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_relax_volume: many-chain handles only");
     CK(cudaSetDevice(h->cfg.device));
@@ -743,6 +753,7 @@ extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *r
     StepArgs a{};
     a.eci = h->cfg.eci; a.mdai = h->cfg.mdai; a.mvai = h->cfg.mvai;
     a.adapt_device = h->cfg.adapt == JMM_ADAPT_DEVICE;
+    const bool host_cadence = h->cfg.adapt == JMM_ADAPT_HOST;
     volatile double idealRatio = 0.5;
     a.log_ideal = log(0.672924 * idealRatio + 0.0644284);
     a.stream = h->d_stream; a.n_words = n_words; a.cursor = h->d_cursor; a.err = h->d_err;
@@ -753,7 +764,7 @@ extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *r
     uint64_t remaining = nsteps, done = 0;
     while (remaining) {
         uint64_t n = std::min<uint64_t>(remaining, 1ull << 30);      // kernels count steps in 32 bits
-        if (!a.adapt_device) {                   // split at the reference's host-side events, src/Main.cpp:145-176
+        if (host_cadence) {                      // split at the reference's host-side events, src/Main.cpp:145-176
             if (a.mdai) n = std::min(n, a.mdai - h->sn % a.mdai);
             if (a.mvai) n = std::min(n, a.mvai - h->sn % a.mvai);
             if (relax_on && h->sn < 1000000ull) n = std::min(n, 10000 - h->sn % 10000);
@@ -764,7 +775,7 @@ extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *r
         CK(DISPATCH_POT_TABLE(h, launch_step_table, h, a));
         tock(h);
         h->sn += n; remaining -= n; done += n;
-        if (!a.adapt_device) {
+        if (host_cadence) {
             const bool dis = a.mdai && h->sn % a.mdai == 0, vol = a.mvai && h->sn % a.mvai == 0;
             if (dis || vol) {
                 jmm_status st = jmm_adjust_step_sizes(h, dis, vol);

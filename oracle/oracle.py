@@ -18,6 +18,7 @@ LIB_PATH = HERE / "libjmm_oracle.so"
 REF_DIR = HERE / "_ref"
 REF_BIN = REF_DIR / "jmmOneDMC_ref"
 REF_SERIAL_BIN = REF_DIR / "jmmOneDMC_serial"
+COMPAT_BIN = REF_DIR / "jmmOneDMC_gpu"       # reference Main.cpp + readInput.cpp linked against libjmmgpu.so
 
 POT = {"LJ": 0, "LJcut": 1, "HARMONIC": 2}
 ENS = {"NPT": 0, "NLT": 1}
@@ -44,8 +45,13 @@ def build(force: bool = False) -> None:
     make = ["make", "-s", "-C", str(HERE)]
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < (HERE / "jmm_oracle.c").stat().st_mtime:
         subprocess.run(make + ["oracle"], check=True)
-    if Path("/root/reference/src").is_dir() and (force or not REF_BIN.exists()):
-        subprocess.run(make + ["ref"], check=True)
+    if Path("/root/reference/src").is_dir():
+        if force or not REF_BIN.exists():
+            subprocess.run(make + ["ref"], check=True)
+        gpu_lib = HERE.parent / "jmmonedmc_b200" / "libjmmgpu.so"
+        shim = HERE.parent / "jmmonedmc_b200" / "csrc" / "host" / "jmm_mcstate_compat.cpp"
+        if gpu_lib.exists() and (force or not COMPAT_BIN.exists() or COMPAT_BIN.stat().st_mtime < shim.stat().st_mtime):
+            subprocess.run(make + ["compat"], check=True)
 
 
 _lib = None
