@@ -78,8 +78,19 @@ def test_create_validates_and_never_falls_back(J):
         assert e.value.status == -2 and "no CPU fallback" in str(e.value)
 
 
-def test_product_never_imports_the_oracle():
-    for p in list((ROOT / "jmmonedmc_b200").rglob("*.py")) + list((ROOT / "jmmonedmc_b200" / "csrc").rglob("*.*")):
-        if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".h", ".hpp"):
+def test_product_never_imports_the_oracle(J):
+    """The oracle is a checker: nothing under jmmonedmc_b200/ may import, include, link or call it."""
+    import re
+    for p in (ROOT / "jmmonedmc_b200").rglob("*"):
+        if p.suffix == ".py":
             text = p.read_text()
-            assert "oracle" not in text.replace("see oracle header", ""), p
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), p
+            assert "libjmm_oracle" not in text and "jmo_" not in text, p
+        elif p.suffix in (".cu", ".cuh", ".cpp", ".h", ".hpp"):
+            text = p.read_text()
+            assert not re.search(r"#\s*include\s*[<\"][^>\"]*(oracle|jmm_oracle)", text), p
+            assert "jmo_" not in text, p
+    deps = subprocess.run(["ldd", str(J.lib_path())], capture_output=True, text=True).stdout
+    assert "oracle" not in deps
+    syms = subprocess.run(["nm", "-D", str(J.lib_path())], capture_output=True, text=True).stdout
+    assert "jmo_" not in syms
