@@ -47,6 +47,20 @@ WORKLOAD = "C2: test/INPUTstd deck (N=10, HARMONIC, NBN 1, NPT, ENGCHECK 1, DADJ
 FLOP_PER_TRIAL = (10.0 / 11.0) * (10 * 1.8 + 37) + (1.0 / 11.0) * 135 + 36
 BYTES_PER_CHAIN_PER_LAUNCH = 2 * (8 * C2["N"] + 256)          # §8(d): state load + store
 
+# The other BASELINE.json configurations, as secondary workloads (--workload c3|c4|c5); SURVEY.md §8(d) table.
+EXTRA = {
+    "c3": dict(desc="C3: one chain, N=1,048,576, LJcut 5.0, NBN 4, NLT (L=1.12N), T=0.9, checkerboard half-sweeps",
+               kind="sweep", N=1 << 20, nchains=1, pot="LJcut", nbn=4, cutoff=5.0, T=0.9, maxStep=0.12, seed=92847,
+               per_step=50, flop=33 * 8 + 37, bytes_per_trial=16.0),
+    "c4": dict(desc="C4: RunJobs-style sweep, 65,536 chains (256x256 P,T grid in [0.1,1]) x N=80, LJ, NBN -1, NPT, RELAX",
+               kind="chains", N=80, nchains=65536, pot="LJ", nbn=-1, cutoff=math.inf, maxStep=0.1, maxdl=2.0, eci=10000,
+               mdai=10 ** 6, mvai=10 ** 6, seed=92847, relax=1, per_step=250, flop=33 * 79 + 37,
+               bytes_per_trial=None),
+    "c5": dict(desc="C5: 8 chains x N=262,144, LJ, NBN 64 (128 partners), NLT (L=1.12N), T=0.9, checkerboard half-sweeps",
+               kind="sweep", N=1 << 18, nchains=8, pot="LJ", nbn=64, cutoff=math.inf, T=0.9, maxStep=0.12, seed=92847,
+               per_step=65, flop=33 * 128 + 37, bytes_per_trial=16.0),
+}
+
 
 def deck_text(numsteps: int, seed: int) -> str:
     """The C2 deck as an INPUT file for the reference binary: print intervals pushed out and the
@@ -258,12 +272,9 @@ def gpu_arm(args) -> None:
     e2e_value = world * trials_per_rank / float(te.item())
 
     # ---- final summary reduction: one NCCL allgather of the per-chain records
-    rec = torch.from_numpy(np.concatenate([s["accum"], s["totals"][:, :2], s["l"][:, None],
-                                           s["counters"].astype(np.float64)], axis=1)).cuda()
-    if world > 1:
-        allrec = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(allrec, rec)
-        rec = torch.cat(allrec)
+    from jmmonedmc_b200.sharding import allgather_summaries, summary_records
+    rec = summary_records(rank * C, C2["P"], C2["T"], h.step_number + 1, s["accum"], s["totals"], s["l"], s["counters"]).cuda()
+    rec = allgather_summaries(rec)                     # the only collective of the job (NCCL), SURVEY §8e
     nchains_total = int(rec.shape[0])
     disc = h.echeck_stats()[1]
 
@@ -315,15 +326,115 @@ def gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
+def extra_arm(args) -> None:
+    """Secondary workloads (one GPU per rank, weak scaling): same JSON shape, no e2e/cpu legs beyond a note."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import jmmonedmc_b200 as J
+    from jmmonedmc_b200.capi import config
+
+    w = EXTRA[args.workload]
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    J.build()
+    pot = {"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT, "HARMONIC": J.POT_HARMONIC}[w["pot"]]
+    C, N = w["nchains"], w["N"]
+    if w["kind"] == "sweep":
+        cfg = config(N=N, pot=pot, nbn=w["nbn"], cutoff=w["cutoff"], ensemble=J.ENS_NLT, L=1.12 * N, T=w["T"],
+                     maxStep=w["maxStep"], seed=w["seed"], nchains=C, chain_id0=rank * C, mode=J.MODE_CHECKERBOARD, device=local)
+    else:
+        cfg = config(N=N, pot=pot, nbn=w["nbn"], cutoff=w["cutoff"], ensemble=J.ENS_NPT, relax=w["relax"], P=0.5, T=0.5,
+                     maxStep=w["maxStep"], maxdl=w["maxdl"], eci=w["eci"], mdai=w["mdai"], mvai=w["mvai"], seed=w["seed"],
+                     nchains=C, chain_id0=rank * C, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE,
+                     device=local)
+    h = J.Handle(cfg)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    if w["kind"] == "chains":
+        g = np.linspace(0.1, 1.0, 256)
+        ids = rank * C + np.arange(C)
+        h.set_state(P=g[(ids // 256) % 256], T=g[ids % 256])
+    h.start()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def one():
+        return h.sweep(w["per_step"]) if w["kind"] == "sweep" else (h.step(w["per_step"]) or C * w["per_step"])
+
+    for _ in range(max(args.warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = h.kernel_launches
+    ev, trials = [], 0
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); n = one(); b.record(stream)
+        trials += n if isinstance(n, int) and n else C * w["per_step"]
+        ev.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms, float(trials)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, trials = float(tm[0]), float(ts[1])
+    launches = h.kernel_launches - l0
+    one(); k_ms = h.last_kernel_ms
+    st = h.get_state(r=False)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        fp64_peak = J.lib().jmm_fp64_peak_tflops(local)
+        value = trials / (ms * 1e-3)
+        per_gpu = value / world
+        tf = per_gpu * w["flop"] / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"],
+                                                "l2": "flushed between timed iterations (256 MiB fill)"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": tf / fp64_peak if fp64_peak > 0 else None, "flop_per_trial": w["flop"],
+                             "kernel_ms_last_call": k_ms, "traffic": None,
+                             "peak_source": "DFMA microbenchmark in libjmmgpu, this run",
+                             "hbm": None if not w["bytes_per_trial"] else {
+                                 "bound": "hbm", "achieved": per_gpu * w["bytes_per_trial"] / 1e9, "unit": "GB/s",
+                                 "peak": float(peaks.get("hbm_gbs", 6650.0)),
+                                 "frac": per_gpu * w["bytes_per_trial"] / 1e9 / float(peaks.get("hbm_gbs", 6650.0))}},
+                "acceptance": float(st["counters"][:, 0].sum() / max(1, st["counters"][:, :2].sum())),
+                "e2e": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload != "c2":
+        extra_arm(args)
     else:
         gpu_arm(args)
 

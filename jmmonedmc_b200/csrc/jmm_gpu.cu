@@ -834,7 +834,7 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     s.tile = tile; s.halo = halo; s.nsub = nsub;
     const int per_sub = (tile + ncol - 1) / ncol;           // trials per half-sweep per tile
     int threads = s.G == 1 ? per_sub : per_sub * 32;
-    threads = std::min(1024, std::max(64, ((threads + 31) / 32) * 32));
+    threads = std::min(512, std::max(64, ((threads + 31) / 32) * 32));
     s.threads = threads;
     s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) nsub * 4 + 16;
     return s;

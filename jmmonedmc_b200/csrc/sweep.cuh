@@ -46,7 +46,7 @@ __device__ __forceinline__ int colour_of(uint64_t seed, uint32_t chain, uint64_t
 // particle, lane-strided partners + xor butterfly, for wide neighbour sets (only 1 and 32 are
 // instantiated: a group must be a whole warp for the full-mask shuffles below).
 template <int POT, int G>
-__global__ void __launch_bounds__(1024) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
+__global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
                                                  double *partial /*[nchains][nsub][ntiles][9]*/,
                                                  unsigned long long *counts /*[nchains][2] accepted, trials*/) {
     constexpr int NC = PotTraits<POT>::NC;

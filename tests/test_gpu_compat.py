@@ -92,5 +92,5 @@ def test_batch_driver_state_point_sweep(gold, tmp_path):
     for t in T:
         assert sum(L[(0.5, t)]) / 2 > sum(L[(1.5, t)]) / 2
     thermo = (tmp_path / "thermo_chains.dat.mcs").read_text().splitlines()
-    assert len(thermo) == 1 + 24 * (1 + 4)
+    assert len(thermo) == 1 + 24 * (1 + 4000 // 100)            # TPI 100: step 0 + 40 block rows per chain
     assert "0 discrepancies" in out.stdout
