@@ -54,7 +54,9 @@ class Deck(C.Structure):
 
 
 def lib_path() -> Path:
-    return PKG / "libjmmgpu.so"
+    # JMM_LIBJMMGPU: load another build of the same library (kernel tuning experiments)
+    import os
+    return Path(os.environ["JMM_LIBJMMGPU"]) if os.environ.get("JMM_LIBJMMGPU") else PKG / "libjmmgpu.so"
 
 
 def declared_symbols() -> list[str]:

@@ -59,6 +59,7 @@ struct Chain {
     uint32_t N; int nbn;
     double cutoff;
     double l, P, T, maxStep, maxdl;
+    double invT;                  // 1/T for the acceptance bounds only (metropolis_accept)
     double tot[NC];
     double acc[kNAcc];
     uint64_t cnt[kNCnt];
@@ -210,8 +211,7 @@ template <> struct Rng<kRngPhilox> {
     }
     __device__ __forceinline__ uint32_t trial_type(uint32_t n, uint32_t scale) {
         uint32_t k = b.w[0] / scale;
-        if (k >= n) k = b.w[3] / scale;
-        if (k >= n) k = b.w[3] % n;
+        if (k >= n) { k = b.w[3] / scale; if (k >= n) k = mulhi32(b.w[3], n); }
         return k;
     }
     __device__ __forceinline__ double rn() { return u01(b.w[1]); }
@@ -296,11 +296,7 @@ __device__ __forceinline__ uint8_t displacement_trial(Chain<POT> &ch, uint32_t n
     for (int k = 0; k < NC; ++k) d[k] = dleft[k] + dsum[k];
 
     bool accept = d[0] <= 0;
-    if (!accept) {                                                                   // :1367-1377
-        const double ran = rng.ran();
-        const double bf = exp(-d[0] / ch.T);
-        accept = bf > ran;
-    }
+    if (!accept) accept = metropolis_accept(d[0], ch.T, ch.invT, rng.ran());      // :1367-1377 (ran drawn only here)
     if (!accept) { ch.cnt[1]++; return 0; }                                          // :1447
     ch.cnt[0]++;                                                                     // :1384-1394
 #pragma unroll
@@ -406,6 +402,7 @@ __device__ __forceinline__ void load_chain(Chain<POT> &ch, const ChainsDev &S, u
     constexpr int NC = PotTraits<POT>::NC;
     ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff;
     ch.l = S.l[c]; ch.P = S.P[c]; ch.T = S.T[c]; ch.maxStep = S.maxStep[c]; ch.maxdl = S.maxdl[c];
+    ch.invT = 1.0 / ch.T;
 #pragma unroll
     for (int k = 0; k < NC; ++k) ch.tot[k] = S.tot[k * S.nchains + c];
 #pragma unroll

@@ -14,6 +14,9 @@
 //     (src/jmmMCState.cpp:1998), so it alone uses a butterfly reduction.
 // Results are bit-identical to chains.cuh in RECOMPUTE mode and to the oracle's RECOMPUTE mode.
 //
+// Occupancy note (measured, C2, trial moves/s): __launch_bounds__(128) -> 128 registers, 4 CTAs/SM: 2.93e9;
+// forcing 6 or 8 CTAs/SM (80 / 64 registers, 250-480 B of spills): 2.16e9 / 1.77e9; (128,1): 1.75e9.
+//
 // Reference lines restated: see chains.cuh (same functions, same order of operations).
 #pragma once
 #include "chains.cuh"
@@ -32,6 +35,7 @@ struct Coop {
     double cutoff;
     double l, P, T, maxStep, maxdl;
     double half_l, rho, two_over_l;               // l/2.0, N/l, 2/l: recomputed whenever l changes
+    double invT;                                  // 1/T, only for the acceptance bounds (metropolis_accept)
     double tot[NC];
     double acc[kNAcc];
     uint64_t cnt[kNCnt];
@@ -305,9 +309,7 @@ __device__ __forceinline__ uint8_t coop_displacement(Coop<POT, G> &c, uint32_t n
     double d[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) d[k] = dleft[k] + dsum[k];
-    bool accept = d[0] <= 0;
-    if (!accept) accept = exp(-d[0] / c.T) > ran;
-    if (!accept) { c.cnt[1]++; return 0; }
+    if (!metropolis_accept(d[0], c.T, c.invT, ran)) { c.cnt[1]++; return 0; }
     c.cnt[0]++;
 #pragma unroll
     for (int k = 0; k < NC; ++k) c.tot[k] += d[k];
@@ -373,7 +375,7 @@ __device__ __forceinline__ void coop_energy_check(Coop<POT, G> &c) {            
 }
 
 // nsteps x Step() :1758-1811, G lanes per chain, Philox stream, positions from shared memory
-template <int POT, int G>
+template <int POT, int G, bool LOG>
 __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs a, int npad) {
     constexpr int NC = PotTraits<POT>::NC;
     extern __shared__ double smem[];
@@ -392,6 +394,7 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
     c.sc = c.r + npad;
     c.N = (uint32_t) S.N; c.nbn = S.nbn; c.cutoff = S.cutoff;
     c.P = S.P[chain]; c.T = S.T[chain]; c.maxStep = S.maxStep[chain]; c.maxdl = S.maxdl[chain];
+    c.invT = 1.0 / c.T;
     c.set_l(S.l[chain]);
 #pragma unroll
     for (int k = 0; k < NC; ++k) c.tot[k] = S.tot[k * C + chain];
@@ -432,8 +435,7 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
             const uint64_t mine = sn + c.lane;
             const Philox4 b = philox4x32_10((uint32_t) mine, (uint32_t)(mine >> 32), cid, kTagTrial, k0, k1);
             uint32_t k = b.w[0] / scale;                      // gsl_rng_uniform_int rule, see Rng<kRngPhilox>
-            if (k >= ntt) k = b.w[3] / scale;
-            if (k >= ntt) k = b.w[3] % ntt;
+            if (k >= ntt) { k = b.w[3] / scale; if (k >= ntt) k = mulhi32(b.w[3], ntt); }
             my_nm = k; my_w1 = b.w[1]; my_w2 = b.w[2];
             batch_pos = 0;
         }
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
         }
         if (--eci_left == 0) { coop_energy_check(c); eci_left = eci32; }
         coop_update_thermo(c);
-        if (a.accept_log && c.lane == 0) a.accept_log[(uint64_t) s * C + chain] = flags;
+        if (LOG && c.lane == 0) a.accept_log[(uint64_t) s * C + chain] = flags;
         if (a.adapt_device) {
             if (--mdai_left == 0) {
                 const double actualRatio = (double) c.cnt[0] / (double)(c.cnt[0] + c.cnt[1]);

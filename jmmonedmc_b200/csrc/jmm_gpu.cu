@@ -369,7 +369,7 @@ static cudaError_t launch_step_rng(jmm_handle *h, const StepArgs &a) {
 
 template <int POT, int G>
 static cudaError_t launch_step_coop_g(jmm_handle *h, const StepArgs &a) {
-    auto kern = k_chains_step_coop<POT, G>;
+    auto kern = a.accept_log ? k_chains_step_coop<POT, G, true> : k_chains_step_coop<POT, G, false>;
     if (h->coop_smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->coop_smem);
         if (e != cudaSuccess) return e;

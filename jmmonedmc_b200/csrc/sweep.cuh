@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
     __syncthreads();
 
     const double lbox = S.l[chain], T = S.T[chain], maxStep = S.maxStep[chain], cutoff = S.cutoff;
+    const double invT = 1.0 / T;
     const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32);
     const uint32_t tag = kTagParticle | (uint32_t)(S.chain_id0 + chain);
     const int nbn = S.nbn, ncol = S.ncol;
@@ -157,8 +158,7 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
 #pragma unroll
                     for (int k = 0; k < NC; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], off, G);
             }
-            bool accept = d[0] <= 0;
-            if (!accept) accept = exp(-d[0] / T) > ran;                               // :1367-1377
+            const bool accept = metropolis_accept(d[0], T, invT, ran);                // :1367-1377
             if (accept) {
                 if (G > 1) __syncwarp();
                 if (lane == 0) {

@@ -94,8 +94,7 @@ static uint64_t draw_trial_type(jmo_state *s) {
     if (s->cfg.rng_kind == JMO_RNG_PHILOX) {
         uint32_t scale = 0xffffffffu / (uint32_t) n;
         uint64_t k = s->phx[0] / scale;
-        if (k >= n) k = s->phx[3] / scale;
-        if (k >= n) k = s->phx[3] % n;
+        if (k >= n) { k = s->phx[3] / scale; if (k >= n) k = ((uint64_t) s->phx[3] * n) >> 32; }
         return k;
     }
     uint64_t scale = 0xffffffffUL / n, k;

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Condense an .ncu-rep into the numbers DESIGN.md / profiles/ quote: duration, occupancy, issue rate,
+fp64 pipe, DRAM traffic, stall reasons and the SASS opcode mix.  Usage: ncu_summary.py rep [units-per-launch]"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[-1]
+
+
+def main():
+    rep = sys.argv[1]
+    units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+    hdr, unit, val = raw(rep)
+    d = {h: (v, u) for h, u, v in zip(hdr, unit, val)}
+    def g(k):
+        return d.get(k, ("", ""))
+    print(f"# {rep}\nkernel: {g('Kernel Name')[0]}")
+    keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_shared_ld.sum"]
+    for k in keys:
+        v, u = g(k)
+        if v != "":
+            print(f"  {k:70s} {v} {u}")
+    for h in hdr:
+        if "issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+            try:
+                x = float(d[h][0].replace(",", ""))
+            except ValueError:
+                continue
+            if x > 2:
+                print(f"  stall {h[len('smsp__warp_issue_stalled_'):-len('_per_warp_active.pct')]:32s} {x:6.1f} %")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(src)))
+    h2 = next(r for r in rows if "Source" in r and "Instructions Executed" in r)
+    ia, ie = h2.index("Source"), h2.index("Instructions Executed")
+    ops, tot = collections.Counter(), 0
+    for r in rows[rows.index(h2) + 1:]:
+        try:
+            n = int(r[ie])
+        except (ValueError, IndexError):
+            continue
+        s = r[ia].strip().split()
+        op = (s[1] if s[0].startswith("@") else s[0]).split(".")[0]
+        ops[op] += n
+        tot += n
+    scale = units if units else 1.0
+    print(f"  warp instructions: {tot:.4g}" + (f"  = {tot / units:.1f} per unit" if units else ""))
+    print("  opcode mix: " + ", ".join(f"{op} {n / scale:.1f}" if units else f"{op} {100 * n / tot:.1f}%" for op, n in ops.most_common(22)))
+    fp64 = sum(n for op, n in ops.items() if op in ("DADD", "DMUL", "DFMA", "DSETP", "MUFU"))
+    print(f"  fp64-pipe instructions: {100 * fp64 / tot:.1f} % of all")
+
+
+if __name__ == "__main__":
+    main()
