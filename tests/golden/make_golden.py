@@ -94,6 +94,9 @@ def main():
     run("inputstd", (REF_TEST / "INPUTstd").read_text())
     big = (REF_TEST / "INPUT").read_text()
     run("input_n2000_40", deck_with(big, NUMSTEPS=40, CPI=40, TPI=5), keep_rng=True)
+    # block averages for the 2-sigma ensemble test (north_star): 40 blocks of 50 000 steps, no RELAX
+    blocks = deck_with(small.replace("RELAX\n", ""), NUMSTEPS=2000000, TPI=50000, CPI=2000000)
+    run("smalltest_blocks", blocks, keep_rng=False)
     if "--full" in sys.argv:
         run("smalltest_full", small, keep_rng=False, keep_files=False)
 
