@@ -85,6 +85,28 @@ def run(name, deck, keep_rng=True, keep_files=True):
         print(name, s["final_E_printed"], s["counters"], "words", s["rng_words"])
 
 
+def reference_ensemble(name, deck, nseeds=32, seed0=92847):
+    """`nseeds` independent runs of the COMPILED REFERENCE (seeds seed0+k), run in parallel; stores the
+    per-run block means (thermo rows) so that the ensemble error bar is a plain standard error over
+    independent chains (a single chain's 50k-step blocks are visibly autocorrelated)."""
+    from concurrent.futures import ThreadPoolExecutor
+    out = HERE / name
+    out.mkdir(exist_ok=True)
+
+    def one(k):
+        with tempfile.TemporaryDirectory() as tmp:
+            R = O.run_reference(deck_with(deck, SEED=seed0 + k), tmp)
+            rows = [[float(x) for x in l.split("\t")] for l in Path(R["thermo"]).read_text().splitlines()[1:]]
+            return {"seed": seed0 + k, "counters": summarise(R["stdout"])["counters"], "blocks": rows}
+
+    with ThreadPoolExecutor(8) as ex:
+        runs = list(ex.map(one, range(nseeds)))
+    (out / "INPUT").write_text(deck)
+    cols = ["Step", "Econf", "Econf2", "L", "L2", "LEconf", "rho", "rho2", "Virial", "Virial2", "EconfVir", "HV", "HV2"]
+    (out / "summary.json").write_text(json.dumps({"columns": cols, "runs": runs}) + "\n")
+    print(name, len(runs), "runs")
+
+
 def main():
     O.build()
     small = (REF_TEST / "INPUT_smalltest").read_text()
@@ -94,9 +116,9 @@ def main():
     run("inputstd", (REF_TEST / "INPUTstd").read_text())
     big = (REF_TEST / "INPUT").read_text()
     run("input_n2000_40", deck_with(big, NUMSTEPS=40, CPI=40, TPI=5), keep_rng=True)
-    # block averages for the 2-sigma ensemble test (north_star): 40 blocks of 50 000 steps, no RELAX
-    blocks = deck_with(small.replace("RELAX\n", ""), NUMSTEPS=2000000, TPI=50000, CPI=2000000)
-    run("smalltest_blocks", blocks, keep_rng=False)
+    # block averages for the 2-sigma ensemble test (north_star): 32 reference runs x 5 blocks of 200 000 steps, no RELAX
+    blocks = deck_with(small.replace("RELAX\n", ""), NUMSTEPS=1000000, TPI=200000, CPI=1000000)
+    reference_ensemble("smalltest_ensemble", blocks)
     if "--full" in sys.argv:
         run("smalltest_full", small, keep_rng=False, keep_files=False)
 

@@ -1,11 +1,16 @@
 """north_star, third criterion: production Philox runs must give ensemble averages (energy, length/density,
 acceptance) within 2 sigma of the block-averaged reference error bars.
 
-Reference side: tests/golden/smalltest_blocks = the COMPILED REFERENCE on test/INPUT_smalltest (RELAX line
-removed so that the deterministic relaxVolume calls of the first 10^6 steps do not bias the sample),
-2 000 000 steps, TPI 50 000: its thermo.dat.mcs rows ARE block averages.  The first 4 blocks are discarded.
+Reference side: tests/golden/smalltest_ensemble = 32 independent runs (seeds 92847+k) of the COMPILED
+REFERENCE on test/INPUT_smalltest (RELAX line removed so that the deterministic relaxVolume calls of the
+first 10^6 steps do not bias the sample), 1 000 000 steps each, TPI 200 000: its thermo.dat.mcs rows ARE block
+averages; the first block (200 000 steps) is discarded as equilibration.  Error bar = standard error over the
+32 independent runs (the 50k-step blocks of ONE chain are autocorrelated, which understates a single-chain
+error bar: a 2 000 000-step single chain sat 2.5 of its own sigmas from the 64-chain mean).
 GPU side: 512 independent chains, Philox stream, positions-only arithmetic, in-kernel step-size adaptation,
-300 000 steps each, first 100 000 discarded; error bar = standard error over chains."""
+500 000 steps each, first 200 000 discarded; error bar = standard error over chains."""
+import json
+
 import numpy as np
 import pytest
 
@@ -15,13 +20,14 @@ pytestmark = pytest.mark.gpu
 
 
 def test_production_ensemble_matches_reference_within_2_sigma(J, O, gold):
-    g = gold("smalltest_blocks")
-    rows = np.array([[float(x) for x in l.split("\t")] for l in (g["dir"] / "thermo.dat.mcs").read_text().splitlines()[1:]])
-    blocks = rows[5:]                                   # row 0 = step 0, rows 1-4 = equilibration
-    assert blocks.shape[0] == 36
-    ref = {"E": blocks[:, 1], "L": blocks[:, 3], "rho": blocks[:, 6]}
+    g = gold("smalltest_ensemble")
+    runs = g["summary"]["runs"]
+    cols = g["summary"]["columns"]
+    assert len(runs) == 32 and all(len(r["blocks"]) == 6 for r in runs)          # step 0 + 5 blocks
+    per_run = np.array([np.mean(r["blocks"][2:], axis=0) for r in runs])         # drop step-0 row and first block
+    ref = {"E": per_run[:, cols.index("Econf")], "L": per_run[:, cols.index("L")], "rho": per_run[:, cols.index("rho")]}
     d = O.parse_deck(g["deck_text"])
-    C, n_eq, n_run = 512, 100_000, 200_000
+    C, n_eq, n_run = 512, 200_000, 300_000
     cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE, nchains=C, seed=20261017)
     with J.Handle(cfg) as h:
         h.start()
@@ -41,14 +47,14 @@ def test_production_ensemble_matches_reference_within_2_sigma(J, O, gold):
         sigma = np.hypot(se_ref, se_gpu)
         report[k] = (m_ref, se_ref, m_gpu, se_gpu, (m_gpu - m_ref) / sigma)
         assert abs(m_gpu - m_ref) < 2 * sigma, f"{k}: reference {m_ref:.5f}+-{se_ref:.5f}, GPU {m_gpu:.5f}+-{se_gpu:.5f}"
-    # acceptance ratios: reference = whole-run counters (2e6 steps); GPU = counters of the sampled part
-    cr = np.array(g["summary"]["counters"], dtype=np.float64)
+    # acceptance ratios (whole-run counters of the reference runs; sampled part of the GPU chains)
+    cr = np.array([r["counters"] for r in runs], dtype=np.float64)
+    d_ref = cr[:, 0] / (cr[:, 0] + cr[:, 1]); v_ref = cr[:, 2] / (cr[:, 2] + cr[:, 3])
     dc = s["counters"].astype(np.float64) - c0
     d_gpu = dc[:, 0] / (dc[:, 0] + dc[:, 1]); v_gpu = dc[:, 2] / (dc[:, 2] + dc[:, 3])
-    d_ref, v_ref = cr[0] / (cr[0] + cr[1]), cr[2] / (cr[2] + cr[3])
-    # the Swendsen rule drives both to its fixed point; the reference value is one long chain (no error bar):
-    # allow 2 sigma of the GPU ensemble spread of a single chain plus 1 % absolute
-    assert abs(d_gpu.mean() - d_ref) < 2 * d_gpu.std(ddof=1) / np.sqrt(C) + 0.01
-    assert abs(v_gpu.mean() - v_ref) < 2 * v_gpu.std(ddof=1) / np.sqrt(C) + 0.02
-    print("ensemble check (ref mean, ref se, gpu mean, gpu se, z):", {k: tuple(round(float(x), 5) for x in v) for k, v in report.items()},
-          "acc d", round(float(d_gpu.mean()), 4), round(float(d_ref), 4), "v", round(float(v_gpu.mean()), 4), round(float(v_ref), 4))
+    for name, a, b in (("displacement", d_ref, d_gpu), ("volume", v_ref, v_gpu)):
+        sigma = np.hypot(a.std(ddof=1) / np.sqrt(a.size), b.std(ddof=1) / np.sqrt(b.size))
+        # the reference counters include its equilibration phase (first 20 % of the run): allow 0.5 % absolute for that
+        assert abs(a.mean() - b.mean()) < 2 * sigma + 0.005, f"{name} acceptance: reference {a.mean():.4f}, GPU {b.mean():.4f}"
+        report["acc_" + name] = (a.mean(), b.mean())
+    print("ensemble check (ref mean, ref se, gpu mean, gpu se, z):", {k: tuple(round(float(x), 5) for x in v) for k, v in report.items()})
