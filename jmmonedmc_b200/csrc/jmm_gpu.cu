@@ -578,7 +578,7 @@ extern "C" jmm_status jmm_start(jmm_handle *h) {
         // first updateThermo (src/Main.cpp:96) as a zero-length "finish"
         jmm_status st = totals_parallel(h, h->cb_r[h->cb_cur], 1, h->S.N, h->cb_tot, 1, 9);
         if (st != JMM_OK) return st;
-        k_sweep_finish<<<(unsigned) h->S.nchains, 32, 0, h->stream>>>(nullptr, 0, 0, h->S.N, h->S.l, h->cb_tot, h->cb_acc, 1);
+        k_sweep_finish<<<(unsigned) h->S.nchains, 288, 0, h->stream>>>(nullptr, 0, 0, h->S.N, h->S.l, h->cb_tot, h->cb_acc, 1);
         h->launches++;
         CK(cudaGetLastError());
         return JMM_OK;
@@ -809,27 +809,27 @@ struct SweepShape { int tile, halo, nsub, threads, G; size_t smem; };
 static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     SweepShape s{};
     const int nbn = h->cfg.nbn, ncol = nbn + 1;
-    const uint64_t N = h->S.N;
+    const uint64_t N = h->S.N, C = h->S.nchains;
     s.G = nbn >= 16 ? 32 : 1;
-    // shared-memory budget: window (tile + 2*halo) doubles; aim at ~2 sweeps per launch, <= 25 % halo overhead
-    const int budget = 200 * 1024 / 8;                      // doubles
-    int nsub = (int) std::min<uint64_t>(want_sub, (uint64_t) 2 * ncol);
-    int tile, halo;
+    const int budget = 200 * 1024 / 8 - 1024;               // doubles of shared memory for the window
+    // One CTA per SM and ONE wave: tiles per chain = m * floor(148 / nchains), the smallest m whose tile
+    // (plus halos) fits in shared memory.  152 CTAs on 148 SMs would cost a whole second wave.
+    const uint64_t base = std::max<uint64_t>(1, 148 / C);
+    int nsub = (int) std::min<uint64_t>(want_sub, 64);
+    int tile = 0, halo = 0;
     for (;;) {
         halo = nsub * nbn;
         halo += halo & 1;
-        tile = budget - 2 * halo - 1024;
+        uint64_t tiles = base;
+        for (;; tiles += base) {
+            uint64_t t = (N + tiles - 1) / tiles;
+            t += t & 1;
+            if ((int64_t) t + 2 * halo <= budget || t <= (uint64_t) 4 * ncol) { tile = (int) t; break; }
+        }
+        // keep the redundantly recomputed halo below ~25 % of the tile
         if (tile >= 8 * halo || nsub == 1) break;
         nsub = std::max(1, nsub / 2);
     }
-    tile = std::max(tile, 2 * ncol);
-    // enough tiles to fill the machine: at least ~148 CTAs over all chains when N allows
-    const uint64_t min_tiles = std::max<uint64_t>(1, (148 + h->S.nchains - 1) / h->S.nchains);
-    uint64_t t_fill = (N + min_tiles - 1) / min_tiles;
-    t_fill += t_fill & 1;
-    tile = (int) std::min<uint64_t>((uint64_t) tile, std::max<uint64_t>(t_fill, (uint64_t) 4 * halo));
-    tile = (int) std::min<uint64_t>((uint64_t) tile, N + (N & 1));
-    tile &= ~1;
     if (tile < 2) tile = 2;
     s.tile = tile; s.halo = halo; s.nsub = nsub;
     const int per_sub = (tile + ncol - 1) / ncol;           // trials per half-sweep per tile
@@ -886,7 +886,7 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
             default: e = launch_sweep<kPotHarmonic>(h, s, W, h->halfsweeps, nsub, ntiles); break;
         }
         CK(e);
-        k_sweep_finish<<<(unsigned) C, 32, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, N, h->S.l, h->cb_tot, h->cb_acc, 0);
+        k_sweep_finish<<<(unsigned) C, 288, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, N, h->S.l, h->cb_tot, h->cb_acc, 0);
         h->launches++;
         CK(cudaGetLastError());
         tock(h);

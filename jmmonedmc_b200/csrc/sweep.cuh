@@ -121,26 +121,35 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
             if (fabs(rT) > lbox / 2.0) continue;                                      // :1188 (group-uniform)
             const int lo = (int) max((int64_t) 0, g - nbn) - (int) g0, hi = (int) min(N - 1, g + nbn) - (int) g0;
             double d[NC];
+            bool accept;
             if constexpr (G == 1) {
+                // every lane walks nbn left partners (ascending index) then nbn right partners: uniform trip
+                // counts, slots outside the chain are skipped; left and right sums apart (:1277, :1354)
                 double dsum[NC], dleft[NC], po[NC], pn[NC];
 #pragma unroll
                 for (int k = 0; k < NC; ++k) { dsum[k] = 0; dleft[k] = 0; }
-                for (int p = lo; p <= hi; ++p) {
-                    if (p == x) {
-#pragma unroll
-                        for (int k = 0; k < NC; ++k) { dleft[k] = dsum[k]; dsum[k] = 0; }
-                        continue;
-                    }
-                    const bool left = p < x;
+                for (int p = x - nbn; p < x; ++p) {
+                    if (p < lo) continue;
                     const double rp = w[p];
-                    phi<POT, true>(left ? rnm - rp : rp - rnm, cutoff, lbox, po);
-                    phi<POT, true>(left ? rT - rp : rp - rT, cutoff, lbox, pn);
+                    phi<POT, true>(rnm - rp, cutoff, lbox, po);
+                    phi<POT, true>(rT - rp, cutoff, lbox, pn);
 #pragma unroll
-                    for (int k = 0; k < NC; ++k) dsum[k] = dsum[k] - po[k] + pn[k];   // :1244, :1339
+                    for (int k = 0; k < NC; ++k) dleft[k] = dleft[k] - po[k] + pn[k];     // :1244
+                }
+                for (int p = x + 1; p <= x + nbn; ++p) {
+                    if (p > hi) break;
+                    const double rp = w[p];
+                    phi<POT, true>(rp - rnm, cutoff, lbox, po);
+                    phi<POT, true>(rp - rT, cutoff, lbox, pn);
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) dsum[k] = dsum[k] - po[k] + pn[k];       // :1339
                 }
 #pragma unroll
-                for (int k = 0; k < NC; ++k) d[k] = dleft[k] + dsum[k];               // :1354
+                for (int k = 0; k < NC; ++k) d[k] = dleft[k] + dsum[k];                   // :1354
+                accept = metropolis_accept(d[0], T, invT, ran);                           // :1367-1377
             } else {
+                // one warp per particle: lane-strided partners; only dE is combined across the lanes (the
+                // decision needs it), the other components stay lane-local until the block-wide sum below
                 double po[NC], pn[NC];
 #pragma unroll
                 for (int k = 0; k < NC; ++k) d[k] = 0;
@@ -153,21 +162,17 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
 #pragma unroll
                     for (int k = 0; k < NC; ++k) d[k] = d[k] - po[k] + pn[k];
                 }
+                double dE = d[0];
 #pragma unroll
-                for (int off = G / 2; off > 0; off >>= 1)
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], off, G);
+                for (int off = G / 2; off > 0; off >>= 1) dE += __shfl_xor_sync(0xffffffffu, dE, off, G);
+                accept = metropolis_accept(dE, T, invT, ran);
             }
-            const bool accept = metropolis_accept(d[0], T, invT, ran);                // :1367-1377
             if (accept) {
                 if (G > 1) __syncwarp();
-                if (lane == 0) {
-                    w[x] = rT;
-                    if (owned) {
-                        ++n_acc;
+                if (lane == 0) { w[x] = rT; if (owned) ++n_acc; }
+                if (owned) {
 #pragma unroll
-                        for (int k = 0; k < NC; ++k) dacc[k] += d[k];
-                    }
+                    for (int k = 0; k < NC; ++k) dacc[k] += d[k];
                 }
             }
         }
@@ -216,32 +221,48 @@ __device__ __forceinline__ void cb_sample(double (&a)[12], const double *cur, do
     a[10] += HV; a[11] += HV * HV;
 }
 
-// presample != 0: one extra sample of the current totals first (the updateThermo of src/Main.cpp:96)
-__global__ void k_sweep_finish(const double *partial, int nsub, int ntiles, uint64_t N, const double *l,
-                               double *tot /*[nchains][9]*/, double *acc /*[nchains][12]*/, int presample) {
+// presample != 0: one extra sample of the current totals first (the updateThermo of src/Main.cpp:96).
+// Launched with 9 warps per chain: warp k owns component k; its lanes add the tiles strided and
+// combine with a fixed butterfly, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(288) k_sweep_finish(const double *partial, int nsub, int ntiles, uint64_t N, const double *l,
+                                                      double *tot /*[nchains][9]*/, double *acc /*[nchains][12]*/, int presample) {
     const int chain = blockIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ double cur[9];
-    if (threadIdx.x < 9) cur[threadIdx.x] = tot[chain * 9 + threadIdx.x];
+    __shared__ double series[3][64];                     // E, Vir, HV after each half-sweep, 64 at a time
+    if (lane == 0) cur[k] = tot[chain * 9 + k];
     __syncthreads();
     double a[12];
-    if (threadIdx.x == 0)
-        for (int k = 0; k < 12; ++k) a[k] = acc[chain * 12 + k];
     const double lbox = l[chain];
-    if (presample && threadIdx.x == 0) cb_sample(a, cur, (double) N, lbox);
-    for (int t = 0; t < nsub; ++t) {
-        if (threadIdx.x < 9) {
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 12; ++q) a[q] = acc[chain * 12 + q];
+        if (presample) cb_sample(a, cur, (double) N, lbox);
+    }
+    double mine = cur[k];                                 // running total of component k (same in all lanes)
+    for (int t0 = 0; t0 < nsub; t0 += 64) {
+        const int t1 = min(nsub, t0 + 64);
+        for (int t = t0; t < t1; ++t) {
+            const double *p = partial + (((uint64_t) chain * nsub + t) * ntiles) * 9 + k;
             double s = 0;
-            const double *p = partial + (((uint64_t) chain * nsub + t) * ntiles) * 9 + threadIdx.x;
-            for (int b = 0; b < ntiles; ++b) s += p[(uint64_t) b * 9];
-            cur[threadIdx.x] += s;
+            for (int b = lane; b < ntiles; b += 32) s += p[(uint64_t) b * 9];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            mine += s;
+            if (lane == 0 && (k == 0 || k == 1 || k == 6)) series[k == 0 ? 0 : (k == 1 ? 1 : 2)][t - t0] = mine;
         }
         __syncthreads();
-        if (threadIdx.x == 0) cb_sample(a, cur, (double) N, lbox);
+        if (threadIdx.x == 0) {
+            double c3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int t = t0; t < t1; ++t) {
+                c3[0] = series[0][t - t0]; c3[1] = series[1][t - t0]; c3[6] = series[2][t - t0];
+                cb_sample(a, c3, (double) N, lbox);
+            }
+        }
         __syncthreads();
     }
-    if (threadIdx.x < 9) tot[chain * 9 + threadIdx.x] = cur[threadIdx.x];
+    if (lane == 0) tot[chain * 9 + k] = mine;
     if (threadIdx.x == 0)
-        for (int k = 0; k < 12; ++k) acc[chain * 12 + k] = a[k];
+        for (int q = 0; q < 12; ++q) acc[chain * 12 + q] = a[q];
 }
 
 // Parallel configuration totals (SURVEY §3.3 loop): grid (nblocks, nchains), rows i strided over the
