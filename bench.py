@@ -352,7 +352,7 @@ def extra_arm(args) -> None:
         cfg = config(N=N, pot=pot, nbn=w["nbn"], cutoff=w["cutoff"], ensemble=J.ENS_NPT, relax=w["relax"], P=0.5, T=0.5,
                      maxStep=w["maxStep"], maxdl=w["maxdl"], eci=w["eci"], mdai=w["mdai"], mvai=w["mvai"], seed=w["seed"],
                      nchains=C, chain_id0=rank * C, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE,
-                     device=local)
+                     device=local, arith=J.ARITH_FAST if args.arith == "fast" else J.ARITH_REFERENCE)
     h = J.Handle(cfg)
     stream = torch.cuda.current_stream()
     h.set_stream(stream.cuda_stream)
@@ -404,7 +404,7 @@ def extra_arm(args) -> None:
         tf = per_gpu * w["flop"] / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"],
+                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": args.arith if w["kind"] == "chains" else "reference",
                                                 "l2": "flushed between timed iterations (256 MiB fill)"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -430,6 +430,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--arith", default="reference", choices=["reference", "fast"], help="c4 only: JMM_ARITH_*")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

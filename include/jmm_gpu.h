@@ -57,6 +57,11 @@ enum { JMM_ADAPT_HOST = 0,     /* host libm log(): bit-identical step sizes to t
                                   of src/Main.cpp:145-176 itself (jmm_adjust_step_sizes,
                                   jmm_relax_volume) — what the jmmMCState.h-compatible shim does   */
 
+/* arithmetic of the production displacement trial (JMM_MODE_RECOMPUTE, Philox, one chain per thread) */
+enum { JMM_ARITH_REFERENCE = 0, /* every pair term and sum as in src/pot.cpp / qad2: bit-identical     */
+       JMM_ARITH_FAST = 1 };    /* LJ/LJcut: one division per partner, r^-6/r^-12 differences only;
+                                   totals equal to <= 1e-12 relative, same decisions (see prod.cuh)   */
+
 /* index of each total in a 9-vector: the order phi() writes them, src/pot.cpp:90-100 */
 enum { JMM_E = 0, JMM_VIR, JMM_E12, JMM_VIR12, JMM_E6, JMM_VIR6, JMM_HV, JMM_HV12, JMM_HV6, JMM_NTOT };
 /* index of each running sum in a 12-vector: updateThermo, src/jmmMCState.cpp:1941-1961 */
@@ -88,6 +93,8 @@ typedef struct jmm_config {
     int32_t  mode;         /* JMM_MODE_*                                                         */
     int32_t  adapt;        /* JMM_ADAPT_*                                                        */
     int32_t  device;       /* CUDA device ordinal                                                */
+    int32_t  arith;        /* JMM_ARITH_*                                                        */
+    int32_t  reserved;     /* 0                                                                  */
 } jmm_config;
 
 /* The print/cadence keywords of the INPUT deck that the hot path itself does not consume

@@ -16,6 +16,7 @@
 #include "chains.cuh"
 #include "sweep.cuh"
 #include "coop.cuh"
+#include "prod.cuh"
 
 using namespace jmm;
 
@@ -198,6 +199,9 @@ static jmm_status validate(const jmm_config *c) {
     if (c->rng_kind < JMM_RNG_TAUS2 || c->rng_kind > JMM_RNG_RECORDED) return fail(JMM_ERR_INVALID, "bad rng_kind");
     if (c->mode < JMM_MODE_TABLE || c->mode > JMM_MODE_CHECKERBOARD) return fail(JMM_ERR_INVALID, "bad mode");
     if (c->adapt < JMM_ADAPT_HOST || c->adapt > JMM_ADAPT_CALLER) return fail(JMM_ERR_INVALID, "bad adapt");
+    if (c->arith != JMM_ARITH_REFERENCE && c->arith != JMM_ARITH_FAST) return fail(JMM_ERR_INVALID, "bad arith");
+    if (c->arith == JMM_ARITH_FAST && (c->pot == JMM_POT_HARMONIC || c->mode != JMM_MODE_RECOMPUTE || c->rng_kind != JMM_RNG_PHILOX))
+        return fail(JMM_ERR_INVALID, "JMM_ARITH_FAST is for LJ/LJcut in JMM_MODE_RECOMPUTE with the Philox stream");
     if (c->rng_kind == JMM_RNG_RECORDED && c->nchains != 1)
         return fail(JMM_ERR_INVALID, "a recorded stream drives exactly one chain");
     if (c->mode == JMM_MODE_CHECKERBOARD) {
@@ -389,10 +393,28 @@ static cudaError_t launch_step_coop(jmm_handle *h, const StepArgs &a) {
     }
 }
 
+template <int POT, int ARITH>
+static cudaError_t launch_step_prod(jmm_handle *h, const StepArgs &a) {
+    auto kern = a.accept_log ? k_chains_step_prod<POT, ARITH, true> : k_chains_step_prod<POT, ARITH, false>;
+    if (h->smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<nblk(h->S.nchains, kTile), kTile, h->smem, h->stream>>>(h->S, a);
+    h->launches++;
+    return cudaGetLastError();
+}
+
 template <int POT, bool TABLE>
 static cudaError_t launch_step_table(jmm_handle *h, const StepArgs &a) {
     if constexpr (!TABLE) {
         if (h->coop_g) return launch_step_coop<POT>(h, a);
+        if (h->cfg.rng_kind == JMM_RNG_PHILOX && h->pos_in_smem && h->block == kTile && !getenv("JMM_NO_PROD")) {
+            if constexpr (POT != kPotHarmonic) {
+                if (h->cfg.arith == JMM_ARITH_FAST) return launch_step_prod<POT, kArithFast>(h, a);
+            }
+            return launch_step_prod<POT, kArithReference>(h, a);
+        }
     }
     switch (h->cfg.rng_kind) {
         case JMM_RNG_TAUS2: return launch_step_rng<POT, TABLE, kRngTaus2>(h, a);

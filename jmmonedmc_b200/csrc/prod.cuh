@@ -1,0 +1,177 @@
+// Production many-chain kernel for PLENTIFUL chains (configs C4-like: >= ~16k chains): one chain per
+// thread, positions in an [N][32] shared-memory tile addressed with compile-time strides, Philox stream,
+// positions-only arithmetic.  Same trial moves as chains.cuh (qad2 :1160-1464 etc.), but the partner loop
+// is written for issue efficiency, because this regime is bound by the fp64 pipe, not by latency:
+//   * shared-memory loads with a constant 256-byte stride instead of generic 64-bit address arithmetic
+//     (the generic kernel spent 48 IMAD per partner on it, profiles/r01_c4_k_chains_step.txt);
+//   * JMM_ARITH_REFERENCE: every pair term and every sum exactly as the reference/oracle (bit-identical);
+//   * JMM_ARITH_FAST (LJ, LJcut): per partner ONE division serves the old and the new term
+//     (1/(A*B) with A = d_old^6, B = d_new^6), only the r^-6 and r^-12 differences are accumulated, and the
+//     nine deltas are derived from them by the exact ratios of src/pot.cpp:56-66
+//     (Vir12 = 12 E12, Vir6 = 6 E6, HV12 = 144 E12, HV6 = 36 E6).  ~30 fp64 instructions per partner
+//     instead of ~76.  Totals differ from the reference-order sums by rounding only (<= 1e-12 relative);
+//     an accept/reject decision can differ only if exp(-dE/T) and ran agree to ~1e-15.
+#pragma once
+#include "chains.cuh"
+
+namespace jmm {
+
+constexpr int kArithReference = 0, kArithFast = 1;
+constexpr int kTile = 32;                        // chains per block = stride between particles in the tile
+
+template <int POT>
+__device__ __forceinline__ uint8_t prod_displacement_ref(Chain<POT> &ch, const double *rs /*shared tile column*/,
+                                                         double *rs_w, uint32_t nm, double rn, double ran) {
+    constexpr int NC = PotTraits<POT>::NC;
+    const double md = (rn - 0.5) * 2 * ch.maxStep;
+    const double rnm = rs[nm * kTile];
+    const double rT = rnm + md;
+    if (fabs(rT) > ch.l / 2.0) { ch.cnt[1]++; return kLogWall; }
+    const uint32_t N = ch.N;
+    const uint32_t lo = (ch.nbn < 0 || (uint32_t) ch.nbn > nm) ? 0u : nm - (uint32_t) ch.nbn;
+    const uint32_t hi = (ch.nbn < 0 || nm + (uint32_t) ch.nbn > N - 1) ? N - 1 : nm + (uint32_t) ch.nbn;
+    double dsum[NC], dleft[NC], po[NC], pn[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { dsum[k] = 0; dleft[k] = 0; }
+    const double *rp = rs + lo * kTile;
+    for (uint32_t p = lo; p <= hi; ++p, rp += kTile) {
+        if (p == nm) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) { dleft[k] = dsum[k]; dsum[k] = 0; }
+            continue;
+        }
+        const bool left = p < nm;
+        const double r = *rp;
+        phi<POT, true>(left ? rnm - r : r - rnm, ch.cutoff, ch.l, po);
+        phi<POT, true>(left ? rT - r : r - rT, ch.cutoff, ch.l, pn);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) dsum[k] = dsum[k] - po[k] + pn[k];
+    }
+    double d[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) d[k] = dleft[k] + dsum[k];
+    if (!metropolis_accept(d[0], ch.T, ch.invT, ran)) { ch.cnt[1]++; return 0; }
+    ch.cnt[0]++;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) ch.tot[k] += d[k];
+    rs_w[nm * kTile] = rT;
+    return kLogAccepted;
+}
+
+// LJ / LJcut only
+template <int POT>
+__device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, const double *rs, double *rs_w,
+                                                          uint32_t nm, double rn, double ran) {
+    static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
+    const double md = (rn - 0.5) * 2 * ch.maxStep;
+    const double rnm = rs[nm * kTile];
+    const double rT = rnm + md;
+    if (fabs(rT) > ch.l / 2.0) { ch.cnt[1]++; return kLogWall; }
+    const uint32_t N = ch.N;
+    const uint32_t lo = (ch.nbn < 0 || (uint32_t) ch.nbn > nm) ? 0u : nm - (uint32_t) ch.nbn;
+    const uint32_t hi = (ch.nbn < 0 || nm + (uint32_t) ch.nbn > N - 1) ? N - 1 : nm + (uint32_t) ch.nbn;
+    double s6 = 0, s12 = 0;
+    const double *rp = rs + lo * kTile;
+    // branch-free body (the moved particle itself is given old = new = 1, which contributes exactly 0),
+    // so the unrolled iterations interleave and hide the division latency
+#pragma unroll 4
+    for (uint32_t p = lo; p <= hi; ++p, rp += kTile) {
+        const double r = *rp;
+        const bool self = (p == nm);
+        // |d| is what matters for the even powers; the sign only enters LJcut's d <= cutoff test (src/pot.cpp:53)
+        double a = (p < nm) ? rnm - r : r - rnm;              // old distance
+        double b = (p < nm) ? rT - r : r - rT;                // new distance
+        a = self ? 1.0 : a;
+        b = self ? 1.0 : b;
+        const double a3 = a * a * a, b3 = b * b * b;
+        const double A = a3 * a3, B = b3 * b3;
+        const double inv = 1.0 / (A * B);
+        double o6 = B * inv, n6 = A * inv;                   // a^-6, b^-6
+        if constexpr (POT == kPotLJcut) {
+            o6 = (a <= ch.cutoff) ? o6 : 0.0;
+            n6 = (b <= ch.cutoff) ? n6 : 0.0;
+        }
+        s6 += n6 - o6;
+        s12 += n6 * n6 - o6 * o6;
+    }
+    const double dE12 = 4 * s12, dE6 = 4 * s6;
+    const double dE = dE12 - dE6;
+    if (!metropolis_accept(dE, ch.T, ch.invT, ran)) { ch.cnt[1]++; return 0; }
+    ch.cnt[0]++;
+    const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
+    ch.tot[0] += dE;  ch.tot[2] += dE12; ch.tot[4] += dE6;
+    ch.tot[1] += dV12 - dV6; ch.tot[3] += dV12; ch.tot[5] += dV6;
+    ch.tot[6] += dH12 - dH6; ch.tot[7] += dH12; ch.tot[8] += dH6;
+    rs_w[nm * kTile] = rT;
+    return kLogAccepted;
+}
+
+template <int POT, int ARITH, bool LOG>
+__global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArgs a) {
+    extern __shared__ double smem[];
+    const uint64_t c = (uint64_t) blockIdx.x * kTile + threadIdx.x;
+    if (c >= S.nchains) return;
+    Chain<POT> ch;
+    load_chain(ch, S, c, smem + threadIdx.x, kTile);          // ch.r -> shared tile (rare paths use it generically)
+    const double *rs = smem + threadIdx.x;                    // same column, known to be shared memory
+    double *rs_w = smem + threadIdx.x;
+
+    Rng<kRngPhilox> rng;
+    rng.k0 = (uint32_t) S.seed; rng.k1 = (uint32_t)(S.seed >> 32); rng.chain = (uint32_t)(S.chain_id0 + c);
+    const uint32_t ntt = (uint32_t) S.numTrialTypes;
+    const uint32_t scale = 0xffffffffu / ntt;
+    const bool scaling_volume = (POT == kPotLJ) && S.nbn < 0;
+    uint64_t sn = a.sn0;
+    auto until = [&](uint64_t every) -> uint32_t {
+        if (!every) return 0xffffffffu;
+        const uint64_t left = every - sn % every;
+        return left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left;
+    };
+    uint32_t eci_left = until(a.eci);
+    uint32_t mdai_left = a.adapt_device ? until(a.mdai) : 0xffffffffu;
+    uint32_t mvai_left = a.adapt_device ? until(a.mvai) : 0xffffffffu;
+    uint32_t relax_left = (a.adapt_device && S.relax > 0 && S.ensemble == kEnsNPT) ? until(10000) : 0xffffffffu;
+    const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
+    const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
+    const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
+    double l_seen = ch.l, rho = (double) ch.N / ch.l;         // N/l only changes with l
+
+    for (uint32_t s = 0; s < (uint32_t) a.nsteps; ++s) {
+        ++sn;
+        rng.begin(sn);
+        const uint32_t nm = rng.trial_type(ntt, scale);
+        const double rn = rng.rn();
+        uint8_t flags;
+        if (nm < ch.N) {
+            if constexpr (ARITH == kArithFast) flags = prod_displacement_fast<POT>(ch, rs, rs_w, nm, rn, rng.ran());
+            else flags = prod_displacement_ref<POT>(ch, rs, rs_w, nm, rn, rng.ran());
+        } else {
+            if constexpr (POT == kPotLJ) {
+                flags = scaling_volume ? volume_trial_scaling<POT, false>(ch, rn, rng) : volume_trial_full<POT, false>(ch, rn, rng);
+            } else flags = volume_trial_full<POT, false>(ch, rn, rng);
+        }
+        if (--eci_left == 0) { energy_check<POT, false>(ch); eci_left = eci32; }
+        if (ch.l != l_seen) { l_seen = ch.l; rho = (double) ch.N / ch.l; }
+        {   // updateThermo :1941-1961 with the cached N/l
+            const double E = ch.tot[0], Vir = ch.tot[1];
+            ch.acc[0] = ch.acc[0] + rho;        ch.acc[1] = ch.acc[1] + rho * rho;
+            ch.acc[2] = ch.acc[2] + ch.l;       ch.acc[3] = ch.acc[3] + ch.l * ch.l;
+            ch.acc[4] = ch.acc[4] + E;          ch.acc[5] = ch.acc[5] + E * E;
+            ch.acc[6] = ch.acc[6] + ch.l * E;   ch.acc[7] = ch.acc[7] + Vir;
+            ch.acc[8] = ch.acc[8] + Vir * Vir;  ch.acc[9] = ch.acc[9] + E * Vir;
+            if constexpr (PotTraits<POT>::NC > 6) {
+                const double HV = ch.tot[6];
+                ch.acc[10] = ch.acc[10] + HV;   ch.acc[11] = ch.acc[11] + HV * HV;
+            }
+        }
+        if (LOG) a.accept_log[(uint64_t) s * S.nchains + c] = flags;
+        if (a.adapt_device) {
+            if (--mdai_left == 0) { adjust_max_step(ch, a.log_ideal); mdai_left = mdai32; }
+            if (--mvai_left == 0) { adjust_max_dl(ch, a.log_ideal); mvai_left = mvai32; }
+            if (--relax_left == 0) { if (sn < 1000000ull) relax_volume<POT, false>(ch); relax_left = 10000; }
+        }
+    }
+    store_chain(ch, S, c, true);
+}
+
+}  // namespace jmm

@@ -149,13 +149,27 @@ DECKS = {
 }
 
 
+ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gpu.cu: launch_step_table)
+    "coop": {"JMM_COOP_G": "16"},                       # coop.cuh, 16 lanes per chain
+    "coop32": {"JMM_COOP_G": "32"},
+    "coop8": {"JMM_COOP_G": "8"},
+    "prod": {"JMM_COOP_G": "0"},                        # prod.cuh, one chain per thread, shared tile
+    "generic": {"JMM_COOP_G": "0", "JMM_NO_PROD": "1"}, # chains.cuh
+}
+
+
 @pytest.mark.parametrize("name", list(DECKS))
-@pytest.mark.parametrize("mode", ["recompute", "table"])
-def test_philox_many_chains_bit_exact(J, O, name, mode):
+@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-generic"])
+def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
     """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
-    every chain must equal the oracle bit for bit, including after adjustments and relaxations."""
+    every chain must equal the oracle bit for bit, including after adjustments and relaxations —
+    whichever kernel (cooperative, per-thread production, generic) serves the handle."""
     d = DECKS[name]
     C, nsteps, id0 = 37, 1500, 1000
+    if "-" in mode:
+        mode, engine = mode.split("-")
+        for k, v in ENGINES[engine].items():
+            monkeypatch.setenv(k, v)
     jm = J.MODE_RECOMPUTE if mode == "recompute" else J.MODE_TABLE
     om = O.MODE_RECOMPUTE if mode == "recompute" else O.MODE_TABLE
     cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=jm, adapt=J.ADAPT_HOST, nchains=C, chain_id0=id0)
@@ -177,6 +191,37 @@ def test_philox_many_chains_bit_exact(J, O, name, mode):
         assert bits_equal(s["totals"][c][:nc], oc.totals[:nc]), f"chain {c}: totals"
         assert bits_equal(s["accum"][c][:na], oc.accum[:na]), f"chain {c}: running sums"
         assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
+
+
+@pytest.mark.parametrize("name", ["small", "ljcut_nbn", "nlt"])
+def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, monkeypatch):
+    """JMM_ARITH_FAST (prod.cuh): one division per partner, r^-6/r^-12 differences only.  Positions and the
+    accept/reject sequence must equal the oracle's exactly; the nine totals and twelve sums agree to 1e-12."""
+    monkeypatch.setenv("JMM_COOP_G", "0")
+    d = DECKS[name]
+    C, nsteps, id0 = 40, 1500, 7
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C, chain_id0=id0,
+                               arith=J.ARITH_FAST)
+    with J.Handle(cfg) as h:
+        h.start()
+        log = h.step(nsteps, accept_log=True)
+        s = h.get_state()
+        fresh = h.energy(exact_order=True)
+    for c in range(C):
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=id0 + c))
+        oc.start()
+        want_log = oracle_accept_log(oc, nsteps)
+        assert np.array_equal(log[:, c] & 3, want_log), f"chain {c}: accept sequence"
+        assert bits_equal(s["r"][c], oc.r), f"chain {c}: positions"
+        assert bits_equal(s["l"][c:c + 1], [oc.l]) and np.array_equal(s["counters"][c], oc.counters)
+        assert totals_close(s["totals"][c], oc.totals, 1e-12), f"chain {c}: totals"
+        # against a fresh recompute only the energies are comparable: qavLJ leaves HV untouched and adds the
+        # ideal term to Vir (src/jmmMCState.cpp:1675-1686), in the reference as here
+        for k in (0, 2, 4):
+            assert abs(s["totals"][c][k] - fresh[c][k]) <= 1e-11 * (abs(fresh[c][2]) + abs(fresh[c][4]))
+        assert np.allclose(s["accum"][c], oc.accum, rtol=1e-11, atol=1e-9)
+    with pytest.raises(J.JmmError):
+        J.Handle(jmm_config_from_deck(J, DECKS["std"], arith=J.ARITH_FAST))          # HARMONIC has no fast arithmetic
 
 
 def test_device_adaptation_matches_until_first_adjust_then_statistically(J, O):
