@@ -396,23 +396,32 @@ __device__ __forceinline__ void adjust_max_dl(Chain<POT> &ch, double log_ideal) 
 
 // ---------------------------------------------------------------- state load / store
 
-template <int POT>
+// CG: read through L2 (ld.global.cg) — needed when another SM may have written the state earlier in the
+// same launch (prod.cuh, time-sliced kernel); L1 is not coherent between SMs.
+template <bool CG, class T>
+__device__ __forceinline__ T ld_state(const T *p) {
+    if constexpr (CG) return __ldcg(p); else return *p;
+}
+
+template <int POT, bool CG = false>
 __device__ __forceinline__ void load_chain(Chain<POT> &ch, const ChainsDev &S, uint64_t c, double *smem_col,
                                            uint32_t smem_stride) {
     constexpr int NC = PotTraits<POT>::NC;
     ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff;
-    ch.l = S.l[c]; ch.P = S.P[c]; ch.T = S.T[c]; ch.maxStep = S.maxStep[c]; ch.maxdl = S.maxdl[c];
+    ch.l = ld_state<CG>(S.l + c); ch.P = ld_state<CG>(S.P + c); ch.T = ld_state<CG>(S.T + c);
+    ch.maxStep = ld_state<CG>(S.maxStep + c); ch.maxdl = ld_state<CG>(S.maxdl + c);
     ch.invT = 1.0 / ch.T;
 #pragma unroll
-    for (int k = 0; k < NC; ++k) ch.tot[k] = S.tot[k * S.nchains + c];
+    for (int k = 0; k < NC; ++k) ch.tot[k] = ld_state<CG>(S.tot + k * S.nchains + c);
 #pragma unroll
-    for (int k = 0; k < kNAcc; ++k) ch.acc[k] = S.acc[k * S.nchains + c];
+    for (int k = 0; k < kNAcc; ++k) ch.acc[k] = ld_state<CG>(S.acc + k * S.nchains + c);
 #pragma unroll
-    for (int k = 0; k < kNCnt; ++k) ch.cnt[k] = S.cnt[k * S.nchains + c];
-    ch.vAErr = S.vAErr[c]; ch.echecks = S.echeck[c]; ch.discrepancies = S.echeck[S.nchains + c];
+    for (int k = 0; k < kNCnt; ++k) ch.cnt[k] = ld_state<CG>(S.cnt + k * S.nchains + c);
+    ch.vAErr = ld_state<CG>(S.vAErr + c); ch.echecks = ld_state<CG>(S.echeck + c);
+    ch.discrepancies = ld_state<CG>(S.echeck + S.nchains + c);
     ch.rij = S.rij ? S.rij + c : nullptr; ch.ts = S.nchains;
     if (smem_col) {
-        for (uint32_t i = 0; i < ch.N; ++i) smem_col[i * smem_stride] = S.r[i * S.nchains + c];
+        for (uint32_t i = 0; i < ch.N; ++i) smem_col[i * smem_stride] = ld_state<CG>(S.r + i * S.nchains + c);
         ch.r = smem_col; ch.rs = smem_stride;
     } else { ch.r = S.r + c; ch.rs = S.nchains; }
 }

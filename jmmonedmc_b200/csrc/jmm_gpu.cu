@@ -53,6 +53,9 @@ struct jmm_handle {
     uint64_t *d_cursor = nullptr;
     int *d_err = nullptr;
     uint64_t cursor = 0;
+    // time-sliced production launches: work counter + per-tile progress words
+    unsigned int *d_work = nullptr;
+    size_t work_words = 0;
     // scratch
     double *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -226,6 +229,7 @@ extern "C" jmm_status jmm_destroy(jmm_handle *h) {
     if (h->d_log) cudaFree(h->d_log);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_stream) cudaFree(h->d_stream);
+    if (h->d_work) cudaFree(h->d_work);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -396,11 +400,38 @@ static cudaError_t launch_step_coop(jmm_handle *h, const StepArgs &a) {
 template <int POT, int ARITH>
 static cudaError_t launch_step_prod(jmm_handle *h, const StepArgs &a) {
     auto kern = a.accept_log ? k_chains_step_prod<POT, ARITH, true> : k_chains_step_prod<POT, ARITH, false>;
+    auto sliced = a.accept_log ? k_chains_step_prod_sliced<POT, ARITH, true> : k_chains_step_prod_sliced<POT, ARITH, false>;
+    cudaError_t e;
     if (h->smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem);
-        if (e != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(sliced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem)) != cudaSuccess) return e;
     }
-    kern<<<nblk(h->S.nchains, kTile), kTile, h->smem, h->stream>>>(h->S, a);
+    const unsigned ntiles = nblk(h->S.nchains, kTile);
+    // how many CTAs of the sliced kernel are co-resident on this device
+    int per_sm = 0, nsm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sliced, kTile, h->smem)) != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const unsigned slots = (unsigned) std::max(1, per_sm * nsm);
+    const double waves = (double) ntiles / slots;
+    const bool slice = getenv("JMM_FORCE_SLICE") ||
+                       (!getenv("JMM_NO_SLICE") && ntiles > slots && (waves - floor(waves)) < 0.85 && a.nsteps >= 16);
+    if (!slice) {
+        kern<<<ntiles, kTile, h->smem, h->stream>>>(h->S, a);
+        h->launches++;
+        return cudaGetLastError();
+    }
+    // ~12+ chunks per launch bounds the imbalance to one chunk in twelve; at least 8 steps per chunk
+    uint32_t chunk = (uint32_t) std::max<uint64_t>(8, (a.nsteps + 11) / 12);
+    if (const char *ev = getenv("JMM_SLICE_CHUNK")) chunk = (uint32_t) std::max(1, atoi(ev));
+    const uint32_t nchunks = (uint32_t) ((a.nsteps + chunk - 1) / chunk);
+    if (h->work_words < (size_t) ntiles + 1) {
+        if (h->d_work) cudaFree(h->d_work);
+        h->d_work = nullptr; h->work_words = 0;
+        if ((e = cudaMalloc((void **) &h->d_work, ((size_t) ntiles + 1) * sizeof(unsigned int))) != cudaSuccess) return e;
+        h->work_words = (size_t) ntiles + 1;
+    }
+    if ((e = cudaMemsetAsync(h->d_work, 0, ((size_t) ntiles + 1) * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
+    sliced<<<std::min(slots, ntiles * nchunks), kTile, h->smem, h->stream>>>(h->S, a, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
     h->launches++;
     return cudaGetLastError();
 }

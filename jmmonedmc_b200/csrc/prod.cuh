@@ -106,13 +106,14 @@ __device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, const 
     return kLogAccepted;
 }
 
-template <int POT, int ARITH, bool LOG>
-__global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArgs a) {
-    extern __shared__ double smem[];
-    const uint64_t c = (uint64_t) blockIdx.x * kTile + threadIdx.x;
-    if (c >= S.nchains) return;
+// One tile (32 chains) advanced by `count` steps starting after step sn0 (log rows from log_row0).
+// COHERENT: chain state is read with ld.global.cg (L2) because another SM may just have written it
+// (persistent time-sliced launch below).
+template <int POT, int ARITH, bool LOG, bool COHERENT>
+__device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs &a, uint64_t c, double *smem,
+                                              uint64_t sn0, uint32_t count, uint64_t log_row0) {
     Chain<POT> ch;
-    load_chain(ch, S, c, smem + threadIdx.x, kTile);          // ch.r -> shared tile (rare paths use it generically)
+    load_chain<POT, COHERENT>(ch, S, c, smem + threadIdx.x, kTile);   // ch.r -> shared tile (rare paths use it generically)
     const double *rs = smem + threadIdx.x;                    // same column, known to be shared memory
     double *rs_w = smem + threadIdx.x;
 
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArg
     const uint32_t ntt = (uint32_t) S.numTrialTypes;
     const uint32_t scale = 0xffffffffu / ntt;
     const bool scaling_volume = (POT == kPotLJ) && S.nbn < 0;
-    uint64_t sn = a.sn0;
+    uint64_t sn = sn0;
     auto until = [&](uint64_t every) -> uint32_t {
         if (!every) return 0xffffffffu;
         const uint64_t left = every - sn % every;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArg
     const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
     double l_seen = ch.l, rho = (double) ch.N / ch.l;         // N/l only changes with l
 
-    for (uint32_t s = 0; s < (uint32_t) a.nsteps; ++s) {
+    for (uint32_t s = 0; s < count; ++s) {
         ++sn;
         rng.begin(sn);
         const uint32_t nm = rng.trial_type(ntt, scale);
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArg
                 ch.acc[10] = ch.acc[10] + HV;   ch.acc[11] = ch.acc[11] + HV * HV;
             }
         }
-        if (LOG) a.accept_log[(uint64_t) s * S.nchains + c] = flags;
+        if (LOG) a.accept_log[(log_row0 + s) * S.nchains + c] = flags;
         if (a.adapt_device) {
             if (--mdai_left == 0) { adjust_max_step(ch, a.log_ideal); mdai_left = mdai32; }
             if (--mvai_left == 0) { adjust_max_dl(ch, a.log_ideal); mvai_left = mvai32; }
@@ -172,6 +173,48 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArg
         }
     }
     store_chain(ch, S, c, true);
+}
+
+template <int POT, int ARITH, bool LOG>
+__global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArgs a) {
+    extern __shared__ double smem[];
+    const uint64_t c = (uint64_t) blockIdx.x * kTile + threadIdx.x;
+    if (c >= S.nchains) return;
+    prod_run_tile<POT, ARITH, LOG, false>(S, a, c, smem, a.sn0, (uint32_t) a.nsteps, 0);
+}
+
+// Persistent, time-sliced variant for launches that would otherwise need a fractional number of waves
+// (65 536 chains = 2048 tiles on 1480 resident CTAs = 1.38 waves: the last 0.38 wave leaves most SMs idle).
+// The grid is exactly the number of co-resident CTAs.  Work items are (chunk, tile) pairs, chunk-major, handed
+// out by an atomic counter; a tile's chunk k+1 waits for its chunk k through a per-tile progress word
+// (release/acquire).  Every earlier item is held by a running CTA, so the wait always ends.  Chain state goes
+// through L2 between chunks (8N+256 B per chain per chunk: negligible next to `chunk` steps of work).
+template <int POT, int ARITH, bool LOG>
+__global__ void __launch_bounds__(kTile) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, uint32_t chunk, uint32_t ntiles,
+                                                                   uint32_t nchunks, unsigned int *work, unsigned int *progress) {
+    extern __shared__ double smem[];
+    for (;;) {
+        unsigned int item = 0;
+        if (threadIdx.x == 0) item = atomicAdd(work, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= ntiles * nchunks) return;
+        const uint32_t tile = item % ntiles, k = item / ntiles;
+        if (threadIdx.x == 0) {
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
+                if (seen < k) __nanosleep(200);
+            } while (seen < k);
+        }
+        __syncwarp();
+        const uint64_t c = (uint64_t) tile * kTile + threadIdx.x;
+        const uint32_t s0 = k * chunk;
+        const uint32_t count = min(chunk, (uint32_t) a.nsteps - s0);
+        if (c < S.nchains) prod_run_tile<POT, ARITH, LOG, true>(S, a, c, smem, a.sn0 + s0, count, s0);
+        __threadfence();
+        __syncwarp();
+        if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(progress + tile), "r"(k + 1) : "memory");
+    }
 }
 
 }  // namespace jmm

@@ -154,12 +154,13 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
     "coop32": {"JMM_COOP_G": "32"},
     "coop8": {"JMM_COOP_G": "8"},
     "prod": {"JMM_COOP_G": "0"},                        # prod.cuh, one chain per thread, shared tile
+    "sliced": {"JMM_COOP_G": "0", "JMM_FORCE_SLICE": "1", "JMM_SLICE_CHUNK": "7"},   # prod.cuh, persistent time-sliced launch
     "generic": {"JMM_COOP_G": "0", "JMM_NO_PROD": "1"}, # chains.cuh
 }
 
 
 @pytest.mark.parametrize("name", list(DECKS))
-@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-generic"])
+@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
 def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
     """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
     every chain must equal the oracle bit for bit, including after adjustments and relaxations —
