@@ -347,7 +347,8 @@ def extra_arm(args) -> None:
     C, N = w["nchains"], w["N"]
     if w["kind"] == "sweep":
         cfg = config(N=N, pot=pot, nbn=w["nbn"], cutoff=w["cutoff"], ensemble=J.ENS_NLT, L=1.12 * N, T=w["T"],
-                     maxStep=w["maxStep"], seed=w["seed"], nchains=C, chain_id0=rank * C, mode=J.MODE_CHECKERBOARD, device=local)
+                     maxStep=w["maxStep"], seed=w["seed"], nchains=C, chain_id0=rank * C, mode=J.MODE_CHECKERBOARD, device=local,
+                     arith=J.ARITH_FAST if args.arith == "fast" else J.ARITH_REFERENCE)
     else:
         cfg = config(N=N, pot=pot, nbn=w["nbn"], cutoff=w["cutoff"], ensemble=J.ENS_NPT, relax=w["relax"], P=0.5, T=0.5,
                      maxStep=w["maxStep"], maxdl=w["maxdl"], eci=w["eci"], mdai=w["mdai"], mvai=w["mvai"], seed=w["seed"],
@@ -404,7 +405,7 @@ def extra_arm(args) -> None:
         tf = per_gpu * w["flop"] / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": args.arith if w["kind"] == "chains" else "reference",
+                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": args.arith,
                                                 "l2": "flushed between timed iterations (256 MiB fill)"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",

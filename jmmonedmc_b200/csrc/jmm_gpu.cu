@@ -203,8 +203,8 @@ static jmm_status validate(const jmm_config *c) {
     if (c->mode < JMM_MODE_TABLE || c->mode > JMM_MODE_CHECKERBOARD) return fail(JMM_ERR_INVALID, "bad mode");
     if (c->adapt < JMM_ADAPT_HOST || c->adapt > JMM_ADAPT_CALLER) return fail(JMM_ERR_INVALID, "bad adapt");
     if (c->arith != JMM_ARITH_REFERENCE && c->arith != JMM_ARITH_FAST) return fail(JMM_ERR_INVALID, "bad arith");
-    if (c->arith == JMM_ARITH_FAST && (c->pot == JMM_POT_HARMONIC || c->mode != JMM_MODE_RECOMPUTE || c->rng_kind != JMM_RNG_PHILOX))
-        return fail(JMM_ERR_INVALID, "JMM_ARITH_FAST is for LJ/LJcut in JMM_MODE_RECOMPUTE with the Philox stream");
+    if (c->arith == JMM_ARITH_FAST && (c->pot == JMM_POT_HARMONIC || c->mode == JMM_MODE_TABLE || c->rng_kind != JMM_RNG_PHILOX))
+        return fail(JMM_ERR_INVALID, "JMM_ARITH_FAST is for LJ/LJcut with the Philox stream (RECOMPUTE or CHECKERBOARD mode)");
     if (c->rng_kind == JMM_RNG_RECORDED && c->nchains != 1)
         return fail(JMM_ERR_INVALID, "a recorded stream drives exactly one chain");
     if (c->mode == JMM_MODE_CHECKERBOARD) {
@@ -893,21 +893,21 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     return s;
 }
 
-template <int POT>
-static cudaError_t launch_sweep(jmm_handle *h, const SweepShape &s, const SweepDev &W, uint64_t step0, int nsub, unsigned ntiles) {
+template <int POT, int G, int ARITH>
+static cudaError_t launch_sweep_inst(jmm_handle *h, const SweepShape &s, const SweepDev &W, uint64_t step0, int nsub, unsigned ntiles) {
     dim3 grid(ntiles, (unsigned) h->S.nchains);
-    cudaError_t e;
-    if (s.G == 1) {
-        e = cudaFuncSetAttribute(k_sweep<POT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
-        if (e != cudaSuccess) return e;
-        k_sweep<POT, 1><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, h->d_partial, h->cb_counts);
-    } else {
-        e = cudaFuncSetAttribute(k_sweep<POT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
-        if (e != cudaSuccess) return e;
-        k_sweep<POT, 32><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, h->d_partial, h->cb_counts);
-    }
+    cudaError_t e = cudaFuncSetAttribute(k_sweep<POT, G, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
+    if (e != cudaSuccess) return e;
+    k_sweep<POT, G, ARITH><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, h->d_partial, h->cb_counts);
     h->launches++;
     return cudaGetLastError();
+}
+
+template <int POT>
+static cudaError_t launch_sweep(jmm_handle *h, const SweepShape &s, const SweepDev &W, uint64_t step0, int nsub, unsigned ntiles) {
+    const bool fast = h->cfg.arith == JMM_ARITH_FAST && POT != kPotHarmonic;
+    if (s.G == 1) return fast ? launch_sweep_inst<POT, 1, 1>(h, s, W, step0, nsub, ntiles) : launch_sweep_inst<POT, 1, 0>(h, s, W, step0, nsub, ntiles);
+    return fast ? launch_sweep_inst<POT, 32, 1>(h, s, W, step0, nsub, ntiles) : launch_sweep_inst<POT, 32, 0>(h, s, W, step0, nsub, ntiles);
 }
 
 extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *trials_out) {

@@ -45,7 +45,7 @@ __device__ __forceinline__ int colour_of(uint64_t seed, uint32_t chain, uint64_t
 // G lanes cooperate on one particle's trial.  G = 1: reference summation order; G = 32: one warp per
 // particle, lane-strided partners + xor butterfly, for wide neighbour sets (only 1 and 32 are
 // instantiated: a group must be a whole warp for the full-mask shuffles below).
-template <int POT, int G>
+template <int POT, int G, int ARITH>
 __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
                                                  double *partial /*[nchains][nsub][ntiles][9]*/,
                                                  unsigned long long *counts /*[nchains][2] accepted, trials*/) {
@@ -122,7 +122,44 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
             const int lo = (int) max((int64_t) 0, g - nbn) - (int) g0, hi = (int) min(N - 1, g + nbn) - (int) g0;
             double d[NC];
             bool accept;
-            if constexpr (G == 1) {
+            if constexpr (ARITH == 1 && POT != kPotHarmonic) {
+                // JMM_ARITH_FAST (see prod.cuh): one division per partner, only the r^-6 / r^-12 differences
+                double s6 = 0, s12 = 0;
+                const int pstart = (G == 1) ? x - nbn : lo + lane;
+                const int pend = (G == 1) ? x + nbn : hi;
+#pragma unroll 4
+                for (int p = pstart; p <= pend; p += G) {
+                    const bool valid = (p >= lo) && (p <= hi) && (p != x);
+                    const double rp = w[min(max(p, lo), hi)];
+                    double a = (p < x) ? rnm - rp : rp - rnm;
+                    double b = (p < x) ? rT - rp : rp - rT;
+                    a = valid ? a : 1.0;
+                    b = valid ? b : 1.0;
+                    const double a3 = a * a * a, b3 = b * b * b;
+                    const double A = a3 * a3, B = b3 * b3;
+                    const double inv = 1.0 / (A * B);
+                    double o6 = B * inv, n6 = A * inv;
+                    if constexpr (POT == kPotLJcut) {
+                        o6 = (a <= cutoff) ? o6 : 0.0;
+                        n6 = (b <= cutoff) ? n6 : 0.0;
+                    }
+                    s6 += n6 - o6;
+                    s12 += n6 * n6 - o6 * o6;
+                }
+                double t6 = s6, t12 = s12;                       // lane-local shares (G == 32) or the whole sums (G == 1)
+                if constexpr (G > 1) {
+#pragma unroll
+                    for (int off = G / 2; off > 0; off >>= 1) {
+                        s6 += __shfl_xor_sync(0xffffffffu, s6, off, G);
+                        s12 += __shfl_xor_sync(0xffffffffu, s12, off, G);
+                    }
+                }
+                accept = metropolis_accept(4 * s12 - 4 * s6, T, invT, ran);
+                const double e12 = 4 * t12, e6 = 4 * t6;
+                d[0] = e12 - e6; d[2] = e12; d[4] = e6;
+                d[3] = 12 * e12; d[5] = 6 * e6; d[1] = d[3] - d[5];
+                d[7] = 144 * e12; d[8] = 36 * e6; d[6] = d[7] - d[8];
+            } else if constexpr (G == 1) {
                 // every lane walks nbn left partners (ascending index) then nbn right partners: uniform trip
                 // counts, slots outside the chain are skipped; left and right sums apart (:1277, :1354)
                 double dsum[NC], dleft[NC], po[NC], pn[NC];

@@ -274,15 +274,19 @@ def test_energy_bookkeeping_stays_consistent(J, O):
     assert abs(np.mean(acc[:, 2] / 5001) - np.mean(s["l"])) < 0.2 * np.mean(s["l"])   # ensemble <L> ~ current L
 
 
+@pytest.mark.parametrize("arith", ["reference", "fast"])
 @pytest.mark.parametrize("pot,nbn,cutoff,N,C", [("LJcut", 4, 5.0, 20000, 2), ("LJ", 2, math.inf, 5001, 1),
                                                  ("HARMONIC", 1, math.inf, 8192, 3), ("LJ", 24, math.inf, 6000, 2)])
-def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C):
+def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C, arith):
     from jmmonedmc_b200.capi import config
+    if arith == "fast" and pot == "HARMONIC":
+        pytest.skip("fast arithmetic is an LJ-family path")
     P = {"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT, "HARMONIC": J.POT_HARMONIC}[pot]
     seed, id0, T, ms, nhs = 92847, 5, 0.9, 0.12, 3 * (nbn + 1) + 1
     L = N * 1.12
     cfg = config(N=N, pot=P, nbn=nbn, cutoff=cutoff, ensemble=J.ENS_NLT, L=L, T=T, maxStep=ms, seed=seed,
-                 nchains=C, chain_id0=id0, mode=J.MODE_CHECKERBOARD)
+                 nchains=C, chain_id0=id0, mode=J.MODE_CHECKERBOARD,
+                 arith=J.ARITH_FAST if arith == "fast" else J.ARITH_REFERENCE)
     with J.Handle(cfg) as h:
         h.start()
         s0 = h.get_state()
