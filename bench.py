@@ -51,14 +51,14 @@ BYTES_PER_CHAIN_PER_LAUNCH = 2 * (8 * C2["N"] + 256)          # §8(d): state lo
 EXTRA = {
     "c3": dict(desc="C3: one chain, N=1,048,576, LJcut 5.0, NBN 4, NLT (L=1.12N), T=0.9, checkerboard half-sweeps",
                kind="sweep", N=1 << 20, nchains=1, pot="LJcut", nbn=4, cutoff=5.0, T=0.9, maxStep=0.12, seed=92847,
-               per_step=50, flop=33 * 8 + 37, bytes_per_trial=16.0),
+               per_step=64, flop=33 * 8 + 37, bytes_per_trial=16.0),
     "c4": dict(desc="C4: RunJobs-style sweep, 65,536 chains (256x256 P,T grid in [0.1,1]) x N=80, LJ, NBN -1, NPT, RELAX",
                kind="chains", N=80, nchains=65536, pot="LJ", nbn=-1, cutoff=math.inf, maxStep=0.1, maxdl=2.0, eci=10000,
                mdai=10 ** 6, mvai=10 ** 6, seed=92847, relax=1, per_step=250, flop=33 * 79 + 37,
                bytes_per_trial=None),
     "c5": dict(desc="C5: 8 chains x N=262,144, LJ, NBN 64 (128 partners), NLT (L=1.12N), T=0.9, checkerboard half-sweeps",
                kind="sweep", N=1 << 18, nchains=8, pot="LJ", nbn=64, cutoff=math.inf, T=0.9, maxStep=0.12, seed=92847,
-               per_step=65, flop=33 * 128 + 37, bytes_per_trial=16.0),
+               per_step=64, flop=33 * 128 + 37, bytes_per_trial=16.0),
 }
 
 

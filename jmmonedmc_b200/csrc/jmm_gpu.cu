@@ -864,10 +864,12 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     const int nbn = h->cfg.nbn, ncol = nbn + 1;
     const uint64_t N = h->S.N, C = h->S.nchains;
     s.G = nbn >= 16 ? 32 : 1;
-    const int budget = 200 * 1024 / 8 - 1024;               // doubles of shared memory for the window
-    // One CTA per SM and ONE wave: tiles per chain = m * floor(148 / nchains), the smallest m whose tile
+    // fast-arithmetic kernels fit two CTAs per SM (<= 64 registers): more warps to hide the division latency
+    const bool two_per_sm = h->cfg.arith == JMM_ARITH_FAST && h->cfg.pot != JMM_POT_HARMONIC;
+    const int budget = (two_per_sm ? 100 : 200) * 1024 / 8 - 1024;   // doubles of shared memory for the window
+    // k CTAs per SM and ONE wave: tiles per chain = m * floor(148 k / nchains), the smallest m whose tile
     // (plus halos) fits in shared memory.  152 CTAs on 148 SMs would cost a whole second wave.
-    const uint64_t base = std::max<uint64_t>(1, 148 / C);
+    const uint64_t base = std::max<uint64_t>(1, (two_per_sm ? 296 : 148) / C);
     int nsub = (int) std::min<uint64_t>(want_sub, 64);
     int tile = 0, halo = 0;
     for (;;) {
@@ -889,7 +891,7 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     int threads = s.G == 1 ? per_sub : per_sub * 32;
     threads = std::min(512, std::max(64, ((threads + 31) / 32) * 32));
     s.threads = threads;
-    s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) nsub * 4 + 16;
+    s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) nsub * 8 + 16;
     return s;
 }
 
@@ -914,11 +916,7 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
     if (!h || !is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_sweep: JMM_MODE_CHECKERBOARD handles only");
     CK(cudaSetDevice(h->cfg.device));
     const uint64_t C = h->S.nchains, N = h->S.N;
-    std::vector<unsigned long long> c0(2 * C), c1(2 * C);
-    if (trials_out) {
-        CK(cudaMemcpyAsync(c0.data(), h->cb_counts, 2 * C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    }
+    uint64_t trials = 0;
     h->timed = false;
     uint64_t remaining = n_halfsweeps;
     while (remaining) {
@@ -931,6 +929,17 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
         W.nchains = C; W.N = N; W.nbn = h->cfg.nbn; W.ncol = h->cfg.nbn + 1; W.cutoff = h->S.cutoff;
         W.r_in = h->cb_r[h->cb_cur]; W.r_out = h->cb_r[h->cb_cur ^ 1];
         W.l = h->S.l; W.T = h->S.T; W.maxStep = h->S.maxStep; W.seed = h->cfg.seed; W.chain_id0 = h->cfg.chain_id0;
+        // trials of this launch, counted on the host (the colour of a half-sweep is a pure function of
+        // (seed, chain, half-sweep)): no device round trip, launches stay asynchronous
+        for (uint64_t c = 0; c < C; ++c)
+            for (int t = 0; t < nsub; ++t) {
+                const uint64_t step = h->halfsweeps + t;
+                const Philox4 b = philox4x32_10((uint32_t) step, (uint32_t)(step >> 32), 0xFFFFFFFFu,
+                                                kTagColour | (uint32_t)(h->cfg.chain_id0 + c), (uint32_t) h->cfg.seed,
+                                                (uint32_t)(h->cfg.seed >> 32));
+                const uint64_t col = ((uint64_t) b.w[0] * (uint64_t) W.ncol) >> 32;
+                if (col < N) trials += (N - col + W.ncol - 1) / W.ncol;
+            }
         tick(h);
         cudaError_t e;
         switch (h->cfg.pot) {
@@ -947,13 +956,7 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
         h->halfsweeps += nsub;
         remaining -= nsub;
     }
-    if (trials_out) {
-        CK(cudaMemcpyAsync(c1.data(), h->cb_counts, 2 * C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        uint64_t t = 0;
-        for (uint64_t c = 0; c < C; ++c) t += c1[2 * c + 1] - c0[2 * c + 1];
-        *trials_out = t;
-    }
+    if (trials_out) *trials_out = trials;
     return JMM_OK;
 }
 

@@ -65,17 +65,24 @@ __device__ __forceinline__ double phi_energy(double d, double cutoff) {
 // Metropolis rule of qad2, src/jmmMCState.cpp:1367-1377: accept iff dE <= 0 || exp(-dE/T) > ran.
 // exp() and the division are ~70 instructions, and ran is uniform, so the decision is almost always
 // settled by the Taylor bounds  P3(x) <= exp(-x) <= P4(x)  (valid for every x >= 0):
-//   ran < P3(x) - 1e-9  -> accept,   ran > P4(x) + 1e-9 -> reject,   otherwise evaluate exactly.
+//   ran < P3(x) - 1e-9  -> accept,   ran > P4(x) + 1e-9 -> reject,   otherwise evaluate exactly
+// (for x > 1.5 the reciprocal of the degree-4 partial sum of e^x bounds exp(-x) from above instead).
 // The 1e-9 margins dwarf the rounding of x = dE*(1/T) and of the polynomials (~1e-15), so the result is
 // always the one exp(-dE/T) > ran would give: decisions stay bit-identical to the reference-order code.
 __device__ __forceinline__ bool metropolis_accept(double dE, double T, double invT, double ran) {
     if (dE <= 0) return true;
     const double x = dE * invT;
-    const double x2 = x * x;
-    const double p3 = 1.0 - x + x2 * (0.5 - x * (1.0 / 6.0));
-    if (ran < p3 - 1e-9) return true;
-    const double p4 = p3 + x2 * x2 * (1.0 / 24.0);
-    if (ran > p4 + 1e-9) return false;
+    if (x <= 1.5) {
+        const double x2 = x * x;
+        const double p3 = 1.0 - x + x2 * (0.5 - x * (1.0 / 6.0));
+        if (ran < p3 - 1e-9) return true;
+        const double p4 = p3 + x2 * x2 * (1.0 / 24.0);
+        if (ran > p4 + 1e-9) return false;
+    } else {
+        // large x: e^x >= 1 + x + x^2/2 + x^3/6 + x^4/24, so exp(-x) <= 1/(that): almost every draw is rejected here
+        const double q = 1.0 + x * (1.0 + x * (0.5 + x * ((1.0 / 6.0) + x * (1.0 / 24.0))));
+        if (ran * q > 1.0 + 1e-9 * q) return false;
+    }
     return exp(-dE / T) > ran;
 }
 

@@ -46,7 +46,7 @@ __device__ __forceinline__ int colour_of(uint64_t seed, uint32_t chain, uint64_t
 // particle, lane-strided partners + xor butterfly, for wide neighbour sets (only 1 and 32 are
 // instantiated: a group must be a whole warp for the full-mask shuffles below).
 template <int POT, int G, int ARITH>
-__global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
+__global__ void __launch_bounds__(512, (ARITH == 1 && POT != kPotHarmonic) ? 2 : 1) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
                                                  double *partial /*[nchains][nsub][ntiles][9]*/,
                                                  unsigned long long *counts /*[nchains][2] accepted, trials*/) {
     constexpr int NC = PotTraits<POT>::NC;
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
     const int wcap = tile + 2 * halo;
     double *red = w + wcap;                                           // [2][nwarps][9]
     int *colours = reinterpret_cast<int *>(red + 2 * nwarps * 9);     // [nsub]
+    int *firsts = colours + nsub;                                     // [nsub] window index of the first particle to try
     __shared__ __align__(8) unsigned long long mbar;
 
     const double *src = S.r_in + (uint64_t) chain * S.N + g0;
@@ -80,8 +81,13 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
                      ::"r"(smem_u32(w)), "l"(src), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
     }
     for (int i = body + threadIdx.x; i < wlen; i += blockDim.x) w[i] = src[i];
-    for (int t = threadIdx.x; t < nsub; t += blockDim.x)
-        colours[t] = colour_of(S.seed, (uint32_t)(S.chain_id0 + chain), step0 + t, S.ncol);
+    for (int t = threadIdx.x; t < nsub; t += blockDim.x) {
+        const int col = colour_of(S.seed, (uint32_t)(S.chain_id0 + chain), step0 + t, S.ncol);
+        colours[t] = col;
+        // first particle of that colour whose whole neighbourhood is still valid in this window at half-sweep t
+        const int64_t ulo = (g0 == 0) ? 0 : g0 + (int64_t)(t + 1) * S.nbn;
+        firsts[t] = (int) (ulo + (((int64_t) col - ulo % S.ncol) + S.ncol) % S.ncol - g0);
+    }
     if (body > 0) {
         uint32_t done = 0;
         while (!done) {
@@ -101,17 +107,22 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
     unsigned long long n_acc = 0, n_try = 0;
 
     for (int t = 0; t < nsub; ++t) {
-        const int col = colours[t];
         // particles whose whole neighbourhood is still valid in this window
-        const int64_t ulo = (g0 == 0) ? 0 : g0 + (int64_t)(t + 1) * nbn;
         const int64_t uhi = (g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn;
-        const int64_t first = ulo + (((int64_t) col - ulo % ncol) + ncol) % ncol;
-        double dacc[NC];
+        const int64_t first = g0 + firsts[t];
+        constexpr bool kFast = (ARITH == 1 && POT != kPotHarmonic);
+        constexpr int NA = kFast ? 2 : NC;                // fast arithmetic carries only the r^-12 and r^-6 sums
+        double dacc[NA];
 #pragma unroll
-        for (int k = 0; k < NC; ++k) dacc[k] = 0;
+        for (int k = 0; k < NA; ++k) dacc[k] = 0;
         for (int64_t g = first + (int64_t) group * ncol; g < uhi; g += (int64_t) ngroups * ncol) {
-            const Philox4 b = philox4x32_10((uint32_t)(step0 + t), (uint32_t)((step0 + t) >> 32), (uint32_t) g, tag, k0, k1);
-            const double rn = u01(b.w[0]), ran = u01(b.w[1]);
+            uint32_t w0, w1;
+            if (G == 1 || lane == 0) {
+                const Philox4 b = philox4x32_10((uint32_t)(step0 + t), (uint32_t)((step0 + t) >> 32), (uint32_t) g, tag, k0, k1);
+                w0 = b.w[0]; w1 = b.w[1];
+            }
+            if constexpr (G > 1) { w0 = __shfl_sync(0xffffffffu, w0, 0); w1 = __shfl_sync(0xffffffffu, w1, 0); }
+            const double rn = u01(w0), ran = u01(w1);
             const int x = (int) (g - g0);
             const double rnm = w[x];
             const double md = (rn - 0.5) * 2 * maxStep;                               // qad2 :1182
@@ -120,9 +131,9 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
             if (owned && lane == 0) ++n_try;
             if (fabs(rT) > lbox / 2.0) continue;                                      // :1188 (group-uniform)
             const int lo = (int) max((int64_t) 0, g - nbn) - (int) g0, hi = (int) min(N - 1, g + nbn) - (int) g0;
-            double d[NC];
+            double d[NA];
             bool accept;
-            if constexpr (ARITH == 1 && POT != kPotHarmonic) {
+            if constexpr (kFast) {
                 // JMM_ARITH_FAST (see prod.cuh): one division per partner, only the r^-6 / r^-12 differences
                 double s6 = 0, s12 = 0;
                 const int pstart = (G == 1) ? x - nbn : lo + lane;
@@ -155,10 +166,7 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
                     }
                 }
                 accept = metropolis_accept(4 * s12 - 4 * s6, T, invT, ran);
-                const double e12 = 4 * t12, e6 = 4 * t6;
-                d[0] = e12 - e6; d[2] = e12; d[4] = e6;
-                d[3] = 12 * e12; d[5] = 6 * e6; d[1] = d[3] - d[5];
-                d[7] = 144 * e12; d[8] = 36 * e6; d[6] = d[7] - d[8];
+                d[0] = t12; d[1] = t6;
             } else if constexpr (G == 1) {
                 // every lane walks nbn left partners (ascending index) then nbn right partners: uniform trip
                 // counts, slots outside the chain are skipped; left and right sums apart (:1277, :1354)
@@ -209,25 +217,33 @@ __global__ void __launch_bounds__(512) k_sweep(SweepDev S, uint64_t step0, int n
                 if (lane == 0) { w[x] = rT; if (owned) ++n_acc; }
                 if (owned) {
 #pragma unroll
-                    for (int k = 0; k < NC; ++k) dacc[k] += d[k];
+                    for (int k = 0; k < NA; ++k) dacc[k] += d[k];
                 }
             }
         }
         // block-wide sum of this half-sweep's deltas over the owned particles -> partial[chain][t][tile][:]
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
+        for (int k = 0; k < NA; ++k) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) dacc[k] += __shfl_xor_sync(0xffffffffu, dacc[k], off);
         }
         double *rbuf = red + (t & 1) * nwarps * 9;
         if ((threadIdx.x & 31) == 0)
 #pragma unroll
-            for (int k = 0; k < NC; ++k) rbuf[warp * 9 + k] = dacc[k];
+            for (int k = 0; k < NA; ++k) rbuf[warp * 9 + k] = dacc[k];
         __syncthreads();                       // also orders this half-sweep's position writes before the next reads
         if (threadIdx.x < 9) {
             double s = 0;
-            if (threadIdx.x < NC)
+            if constexpr (kFast) {
+                // nine deltas from the two sums, by the exact ratios of src/pot.cpp:56-66
+                double s12 = 0, s6 = 0;
+                for (int wv = 0; wv < nwarps; ++wv) { s12 += rbuf[wv * 9]; s6 += rbuf[wv * 9 + 1]; }
+                const double e12 = 4 * s12, e6 = 4 * s6;
+                const double v[9] = {e12 - e6, 12 * e12 - 6 * e6, e12, 12 * e12, e6, 6 * e6, 144 * e12 - 36 * e6, 144 * e12, 36 * e6};
+                s = v[threadIdx.x];
+            } else if (threadIdx.x < NC) {
                 for (int wv = 0; wv < nwarps; ++wv) s += rbuf[wv * 9 + threadIdx.x];
+            }
             partial[(((uint64_t) chain * nsub + t) * gridDim.x + blockIdx.x) * 9 + threadIdx.x] = s;
         }
     }
