@@ -308,12 +308,16 @@ def gpu_arm(args) -> None:
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
-            "roofline": {"bound": "fp64", "kernel": "k_chains_step<HARMONIC,recompute,philox>",
+            "roofline": {"bound": "fp64", "kernel": "k_chains_step_coop<HARMONIC,G=16> (coop.cuh)",
                          "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None,
                          "peak_source": "DFMA microbenchmark in libjmmgpu (jmm_fp64_peak_tflops), measured in this run; "
                                         "MEASURED_PEAKS.json has no fp64 entry",
-                         "flop_per_trial": FLOP_PER_TRIAL, "kernel_ms": k_ms, "traffic": None,
+                         "flop_per_trial": FLOP_PER_TRIAL, "kernel_ms": k_ms,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed
+                         # ncu --set full capture (profiles/r01_c2_k_chains_step_coop.txt); the 2.75 MB of state
+                         # (algorithmic bytes) mostly stay in the 126 MB L2 between launches
+                         "traffic": 1252608,
                          "note": "serial Markov chains: latency-bound, see DESIGN.md §roofline",
                          "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
