@@ -17,6 +17,7 @@
 #include "sweep.cuh"
 #include "coop.cuh"
 #include "prod.cuh"
+#include "bond.cuh"
 
 using namespace jmm;
 
@@ -44,6 +45,7 @@ struct jmm_handle {
     // many-chain launch shape
     int block = 32, pos_in_smem = 1;
     size_t smem = 0;
+    int bond = 0;                   // bond.cuh serves this handle (HARMONIC, NBN 1, N <= 17, no RELAX)
     int coop_g = 0;                 // lanes per chain of the cooperative kernel (0 = one chain per thread)
     int coop_npad = 0;
     size_t coop_smem = 0;
@@ -340,6 +342,11 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
                 const size_t bytes = (size_t) (128 / g) * (npad + scratch) * sizeof(double);
                 if (bytes <= 200 * 1024) { h->coop_g = g; h->coop_npad = npad; h->coop_smem = bytes; }
             }
+            // nearest-neighbour bond chains (the INPUTstd shape): branch-free kernel, one chain per 16 lanes
+            const char *eb = getenv("JMM_BOND");
+            if (h->coop_g && cfg->pot == JMM_POT_HARMONIC && cfg->nbn == 1 && N - 1 <= 16 && !(h->cfg.relax > 0) &&
+                C <= 16384 && !(eb && atoi(eb) == 0))
+                h->bond = 1;
         }
     }
     CKH(cudaStreamSynchronize(h->stream));
@@ -388,8 +395,21 @@ static cudaError_t launch_step_coop_g(jmm_handle *h, const StepArgs &a) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
+    int npad = (int) h->S.N;
+    npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
+    auto kern = a.accept_log ? k_chains_step_bond<true> : k_chains_step_bond<false>;
+    const unsigned per_block = 128 / kB2G;
+    kern<<<nblk(h->S.nchains, per_block), 128, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
+    h->launches++;
+    return cudaGetLastError();
+}
+
 template <int POT>
 static cudaError_t launch_step_coop(jmm_handle *h, const StepArgs &a) {
+    if constexpr (POT == kPotHarmonic) {
+        if (h->bond) return launch_step_bond(h, a);
+    }
     switch (h->coop_g) {
         case 8: return launch_step_coop_g<POT, 8>(h, a);
         case 16: return launch_step_coop_g<POT, 16>(h, a);

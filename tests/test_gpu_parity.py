@@ -150,7 +150,8 @@ DECKS = {
 
 
 ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gpu.cu: launch_step_table)
-    "coop": {"JMM_COOP_G": "16"},                       # coop.cuh, 16 lanes per chain
+    "coop": {"JMM_COOP_G": "16", "JMM_BOND": "0"},     # coop.cuh, 16 lanes per chain
+    "bond": {"JMM_COOP_G": "16", "JMM_BOND": "1"},      # bond.cuh (HARMONIC NBN 1 decks; others fall to coop.cuh)
     "coop32": {"JMM_COOP_G": "32"},
     "coop8": {"JMM_COOP_G": "8"},
     "prod": {"JMM_COOP_G": "0"},                        # prod.cuh, one chain per thread, shared tile
@@ -160,7 +161,7 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
 
 
 @pytest.mark.parametrize("name", list(DECKS))
-@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
+@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
 def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
     """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
     every chain must equal the oracle bit for bit, including after adjustments and relaxations —
