@@ -20,6 +20,12 @@ namespace jmm {
 constexpr int kB2G = 16;                                  // lanes per chain
 using B2Chain = Coop<kPotHarmonic, kB2G>;
 
+// the gsl_rng_uniform_int redraw (see Rng<kRngPhilox>): out of line so the common path carries no second division
+__device__ __noinline__ uint32_t b2_redraw(uint32_t w3, uint32_t scale, uint32_t ntt) {
+    const uint32_t k = w3 / scale;
+    return k < ntt ? k : mulhi32(w3, ntt);
+}
+
 struct B2Trial {
     double rT, dE, dV;
     uint32_t nm;
@@ -28,15 +34,25 @@ struct B2Trial {
 
 // phiHarmoniccut (src/pot.cpp:110-134) with selects instead of branches: same values, no control flow, so the
 // two chains' evaluations can be interleaved by the instruction scheduler
+// INF: the deck gave no cut-off (POT HARMONIC without a third token, src/readInput.cpp:125-130), so
+// "d < cutOff" holds for every finite d and its select is dropped.
+template <bool INF>
 __device__ __forceinline__ void b2_phi(double d, double cutoff, double two_over_l, double &e, double &v) {
     const double rijm = d - 1.0;
     const double e_in = rijm * rijm, v_in = two_over_l * d * rijm;
-    const bool pos = d > 0, in = d < cutoff;
-    e = pos ? (in ? e_in : 0.0) : 10E10;
-    v = pos ? (in ? v_in : 0.0) : 10E10;
+    const bool pos = d > 0;
+    if constexpr (INF) {
+        e = pos ? e_in : 10E10;
+        v = pos ? v_in : 10E10;
+    } else {
+        const bool in = d < cutoff;
+        e = pos ? (in ? e_in : 0.0) : 10E10;
+        v = pos ? (in ? v_in : 0.0) : 10E10;
+    }
 }
 
 // qad2 :1160-1464 for NBN == 1, branch-free: a missing neighbour (chain end) contributes an exact 0
+template <bool INF>
 __device__ __forceinline__ B2Trial b2_displacement(const B2Chain &c, uint32_t nm, double rn, double ran) {
     B2Trial t;
     t.nm = nm;
@@ -47,10 +63,10 @@ __device__ __forceinline__ B2Trial b2_displacement(const B2Chain &c, uint32_t nm
     const bool hasL = nm > 0, hasR = nm + 1 < c.N;
     const double rl = c.r[hasL ? nm - 1 : nm], rr = c.r[hasR ? nm + 1 : nm];
     double po[2], pn[2], qo[2], qn[2];
-    b2_phi(rnm - rl, c.cutoff, c.two_over_l, po[0], po[1]);
-    b2_phi(t.rT - rl, c.cutoff, c.two_over_l, pn[0], pn[1]);
-    b2_phi(rr - rnm, c.cutoff, c.two_over_l, qo[0], qo[1]);
-    b2_phi(rr - t.rT, c.cutoff, c.two_over_l, qn[0], qn[1]);
+    b2_phi<INF>(rnm - rl, c.cutoff, c.two_over_l, po[0], po[1]);
+    b2_phi<INF>(t.rT - rl, c.cutoff, c.two_over_l, pn[0], pn[1]);
+    b2_phi<INF>(rr - rnm, c.cutoff, c.two_over_l, qo[0], qo[1]);
+    b2_phi<INF>(rr - t.rT, c.cutoff, c.two_over_l, qn[0], qn[1]);
     const double l0 = hasL ? (0.0 - po[0] + pn[0]) : 0.0, l1 = hasL ? (0.0 - po[1] + pn[1]) : 0.0;   // :1244
     const double r0 = hasR ? (0.0 - qo[0] + qn[0]) : 0.0, r1 = hasR ? (0.0 - qo[1] + qn[1]) : 0.0;   // :1339
     t.dE = l0 + r0;                                                                                  // :1354
@@ -82,12 +98,13 @@ __device__ __forceinline__ uint8_t b2_commit(B2Chain &c, const B2Trial &t) {
     return t.wall ? kLogWall : (ok ? kLogAccepted : 0);
 }
 
+template <bool INF>
 __device__ __forceinline__ double b2_etest_partial(const B2Chain &c) {
     const bool has = c.lane + 1 < c.N;
     const uint32_t i = has ? c.lane : 0;                       // idle lanes read pair (0,1) and discard it
     const double d = c.r[i + 1] - c.r[i];
     const double rijm = d - 1.0;
-    const double e = (d > 0) ? ((d < c.cutoff) ? rijm * rijm : 0.0) : 10E10;
+    const double e = (d > 0) ? ((INF || d < c.cutoff) ? rijm * rijm : 0.0) : 10E10;
     return has ? e : 0.0;
 }
 
@@ -141,7 +158,7 @@ __device__ __forceinline__ void b2_adapt(B2Chain &c, const StepArgs &a, bool dis
     }
 }
 
-template <bool LOG>
+template <bool LOG, bool INF>
 __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs a, int npad) {
     extern __shared__ double smem[];
     const uint32_t gib = threadIdx.x / kB2G, lane = threadIdx.x % kB2G;
@@ -169,12 +186,14 @@ __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs 
     const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
     const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
 
+    uint32_t adapt_span = min(mdai_left, mvai_left), adapt_left = adapt_span;   // steps to the next adjustment of either kind
+
     uint32_t nmA_l = 0, w1A_l = 0, w2A_l = 0;   // this lane's share of the Philox batch
     uint32_t batch_pos = kB2G;
     auto draw = [&](uint32_t cid, uint64_t step, uint32_t &nm, uint32_t &w1, uint32_t &w2) {
         const Philox4 b = philox4x32_10((uint32_t) step, (uint32_t)(step >> 32), cid, kTagTrial, k0, k1);
         uint32_t k = b.w[0] / scale;
-        if (k >= ntt) { k = b.w[3] / scale; if (k >= ntt) k = mulhi32(b.w[3], ntt); }
+        if (k >= ntt) k = b2_redraw(b.w[3], scale, ntt);          // probability ~ ntt / 2^32
         nm = k; w1 = b.w[1]; w2 = b.w[2];
     };
 
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs 
 
         uint8_t fA;
         if (nmA < N) {
-            B2Trial tA = b2_displacement(A, nmA, rnA, ranA);
+            B2Trial tA = b2_displacement<INF>(A, nmA, rnA, ranA);
             if (!(tA.decided | tA.wall)) b2_resolve(A, tA, ranA);
             __syncwarp(gmask);                         // every lane has read the positions
             fA = b2_commit(A, tA);
@@ -199,8 +218,8 @@ __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs 
         } else {
             fA = coop_volume_full(A, rnA, ranA);       // fav :2161-2293
         }
-        if (--eci_left == 0) {                         // ECheck :1965-2095, both chains' butterflies interleaved
-            double eA = b2_etest_partial(A);
+        if (eci32 == 1 || --eci_left == 0) {           // ECheck :1965-2095
+            double eA = b2_etest_partial<INF>(A);
 #pragma unroll
             for (int o = kB2G / 2; o > 0; o >>= 1) eA += __shfl_xor_sync(gmask, eA, o, kB2G);
             A.echecks++;
@@ -209,11 +228,13 @@ __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs 
         }
         coop_update_thermo(A);
         if (LOG && lane == 0) a.accept_log[(uint64_t) s * C + chainA] = fA;
-        if (a.adapt_device) {
-            const bool dis = (--mdai_left == 0), vol = (--mvai_left == 0);
-            if (dis | vol) b2_adapt(A, a, dis, vol);
+        if (--adapt_left == 0) {                       // maxDisAdjust / maxDVAdjust steps (src/Main.cpp:145-165)
+            mdai_left -= adapt_span; mvai_left -= adapt_span;
+            const bool dis = mdai_left == 0, vol = mvai_left == 0;
+            b2_adapt(A, a, dis, vol);
             if (dis) mdai_left = mdai32;
             if (vol) mvai_left = mvai32;
+            adapt_span = adapt_left = min(mdai_left, mvai_left);
         }
     }
     __syncwarp(gmask);

@@ -398,7 +398,9 @@ static cudaError_t launch_step_coop_g(jmm_handle *h, const StepArgs &a) {
 static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
     int npad = (int) h->S.N;
     npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
-    auto kern = a.accept_log ? k_chains_step_bond<true> : k_chains_step_bond<false>;
+    const bool inf = std::isinf(h->S.cutoff);
+    auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
+                             : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
     const unsigned per_block = 128 / kB2G;
     kern<<<nblk(h->S.nchains, per_block), 128, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
     h->launches++;
