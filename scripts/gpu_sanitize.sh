@@ -1,0 +1,38 @@
+#!/bin/bash
+# compute-sanitizer on small configurations of every kernel family (memcheck + racecheck + initcheck)
+cat > /tmp/san.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, math
+import jmmonedmc_b200 as J
+from jmmonedmc_b200.capi import config
+def run(cfg, steps=60, sweep=False):
+    with J.Handle(cfg) as h:
+        h.start()
+        if sweep: h.sweep(steps)
+        else: h.step(steps, accept_log=True)
+        s = h.get_state(); h.energy()
+        if not sweep: h.energy(exact_order=True)
+    return s
+std = dict(N=10, pot=J.POT_HARMONIC, nbn=1, P=0.7, T=0.4, maxStep=0.1, maxdl=1.0, eci=1, mdai=20, mvai=20, seed=125)
+lj = dict(N=12, pot=J.POT_LJ, nbn=-1, P=1.0, T=0.9, maxStep=0.1, maxdl=0.1, eci=10, mdai=20, mvai=20, seed=9, relax=1)
+ljc = dict(N=24, pot=J.POT_LJCUT, nbn=3, cutoff=2.5, P=0.5, T=0.7, maxStep=0.15, maxdl=0.4, eci=5, mdai=20, mvai=30, seed=7, relax=1)
+which = os.environ.get("SAN_CASE", "all")
+cases = {
+ "bond": lambda: run(config(nchains=37, **std)),
+ "coop": lambda: (os.environ.__setitem__("JMM_BOND", "0"), run(config(nchains=37, **std)), run(config(nchains=9, **lj)), run(config(nchains=9, **ljc))),
+ "prod": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), run(config(nchains=70, **lj)), run(config(nchains=70, arith=J.ARITH_FAST, **ljc))),
+ "sliced": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), os.environ.__setitem__("JMM_FORCE_SLICE", "1"), os.environ.__setitem__("JMM_SLICE_CHUNK", "7"), run(config(nchains=70, **lj))),
+ "generic": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), os.environ.__setitem__("JMM_NO_PROD", "1"), run(config(nchains=40, **ljc)), run(config(nchains=3, mode=J.MODE_TABLE, rng_kind=J.RNG_TAUS2, adapt=J.ADAPT_HOST, **lj))),
+ "sweep": lambda: (run(config(N=3000, pot=J.POT_LJCUT, nbn=4, cutoff=5.0, ensemble=J.ENS_NLT, L=3360.0, T=0.9, maxStep=0.12, seed=3, nchains=2, mode=J.MODE_CHECKERBOARD), 11, True),
+                   run(config(N=3000, pot=J.POT_LJ, nbn=20, ensemble=J.ENS_NLT, L=3360.0, T=0.9, maxStep=0.12, seed=3, nchains=2, mode=J.MODE_CHECKERBOARD, arith=J.ARITH_FAST), 25, True)),
+}
+for k, f in cases.items():
+    if which in ("all", k): f(); print("case", k, "ok")
+PY
+for tool in memcheck racecheck; do
+  for c in bond coop prod sliced generic sweep; do
+    echo "== $tool $c"
+    SAN_CASE=$c timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|case|Error|error|hazard|Invalid" | head -8
+  done
+done
