@@ -40,6 +40,13 @@ struct jmo_state {
     uint32_t phx[4]; int phx_valid;   /* Philox block of the current step */
     /* thermo print bookkeeping, src/jmmMCState.cpp:53-54,537 */
     uint64_t sltp;
+    /* histograms, src/jmmMCState.cpp:58-63,128-132,180-192 */
+    int hist;
+    uint64_t rhonb, gnb, slrho, slg;
+    int gns;
+    double rbw, gsw, gbw;
+    int64_t *rhol, *rhoA, *gl, *gA;          /* gl/gA are [gns][gnb] */
+    double last_md; uint64_t last_nm;        /* qagrho reads mcs->md and mcs->nm */
 };
 
 /* ------------------------------------------------------------------ generators */
@@ -190,7 +197,10 @@ jmo_state *jmo_create(const jmo_config *cfg) {
     return s;
 }
 
-void jmo_destroy(jmo_state *s) { if (!s) return; free(s->r); free(s->rTrial); free(s->rij); free(s); }
+void jmo_destroy(jmo_state *s) {
+    if (!s) return;
+    free(s->r); free(s->rTrial); free(s->rij); free(s->rhol); free(s->rhoA); free(s->gl); free(s->gA); free(s);
+}
 void jmo_set_recorded(jmo_state *s, const uint32_t *w, uint64_t n) { s->rec = w; s->nrec = n; s->irec = 0; }
 uint64_t jmo_recorded_cursor(const jmo_state *s) { return s->irec; }
 
@@ -276,6 +286,78 @@ void jmo_update_thermo(jmo_state *s) {
     s->acc[JMO_A_HV2]  = s->acc[JMO_A_HV2]  + HV * HV;
 }
 
+/* ------------------------------------------------------------------ histograms */
+
+/* fgrho, src/jmmMCState.cpp:1069-1127.  Pair distances: the rij table when there is one (the reference reads
+ * mcs->rij[ind], :1103), else r[jj]-r[ii]. */
+static void hist_fgrho(jmo_state *s) {
+    for (uint64_t b = 0; b < s->rhonb; b++) s->rhol[b] = 0;
+    for (uint64_t i = 0; i < s->N; i++) {
+        long rb = (long) floor(s->r[i] / s->rbw + s->rhonb / 2.0);
+        if (rb >= 0 && rb < (long) s->rhonb) s->rhol[rb]++;
+    }
+    for (uint64_t q = 0; q < (uint64_t) s->gns * s->gnb; q++) s->gl[q] = 0;
+    for (uint64_t i = 0; i + 1 < s->N; i++)
+        for (uint64_t j = i + 1; j < s->N; j++) {
+            long gs1 = (long) floor(s->r[i] / s->gsw + s->gns / 2.0);
+            long gs2 = (long) floor(s->r[j] / s->gsw + s->gns / 2.0);
+            double d = s->rij ? s->rij[pair_index(s->N, i, j)] : s->r[j] - s->r[i];
+            long gb = (long) floor(d / s->gbw);
+            if (gb < (long) s->gnb && gb >= 0) {       /* the reference does not test gb >= 0 (UB for crossed particles) */
+                if (gs1 >= 0 && gs1 < (long) s->gns) s->gl[gs1 * s->gnb + gb]++;
+                if (gs2 >= 0 && gs2 < (long) s->gns) s->gl[gs2 * s->gnb + gb]++;
+            }
+        }
+}
+
+/* ugrho, :1131-1149 */
+static void hist_ugrho(jmo_state *s) {
+    for (uint64_t b = 0; b < s->rhonb; b++) s->rhoA[b] += s->rhol[b];
+    for (uint64_t q = 0; q < (uint64_t) s->gns * s->gnb; q++) s->gA[q] += s->gl[q];
+}
+
+/* qagrho, :2297-2384: incremental update after an accepted displacement of particle nm by md.
+ * The old position is re-derived as r[nm] - md (not the stored old value), as in the reference. */
+static void hist_qagrho(jmo_state *s, uint64_t nm, double md) {
+    const double rn = s->r[nm];
+    long rbn1 = (long) floor((rn - md) / s->rbw + s->rhonb / 2.0);
+    long rbn2 = (long) floor(rn / s->rbw + s->rhonb / 2.0);
+    if (rbn1 >= 0 && rbn1 < (long) s->rhonb) s->rhol[rbn1]--;
+    if (rbn2 >= 0 && rbn2 < (long) s->rhonb) s->rhol[rbn2]++;
+    long gs11 = (long) floor((rn - md) / s->gsw + s->gns / 2.0);
+    long gs12 = (long) floor(rn / s->gsw + s->gns / 2.0);
+    int in11 = gs11 >= 0 && gs11 < s->gns, in12 = gs12 >= 0 && gs12 < s->gns;
+    for (uint64_t i = 0; i < s->N; i++) {
+        if (i == nm) continue;
+        long gs2 = (long) floor(s->r[i] / s->gsw + s->gns / 2.0);
+        int in2 = gs2 >= 0 && gs2 < s->gns;
+        long gb1 = (long) (unsigned long) floor(fabs(rn - md - s->r[i]) / s->gbw);
+        long gb2 = (long) (unsigned long) floor(fabs(rn - s->r[i]) / s->gbw);
+        int b1 = gb1 >= 0 && gb1 < (long) s->gnb, b2 = gb2 >= 0 && gb2 < (long) s->gnb;
+        if (in11 && b1) s->gl[gs11 * s->gnb + gb1]--;
+        if (in12 && b2) s->gl[gs12 * s->gnb + gb2]++;
+        if (in2 && b1) s->gl[gs2 * s->gnb + gb1]--;
+        if (in2 && b2) s->gl[gs2 * s->gnb + gb2]++;
+    }
+}
+
+void jmo_enable_histograms(jmo_state *s, uint64_t rhonb, double rbw, int gns, uint64_t gnb, double gsw, double gbw) {
+    s->hist = 1; s->rhonb = rhonb; s->rbw = rbw; s->gns = gns; s->gnb = gnb; s->gsw = gsw; s->gbw = gbw;
+    s->slrho = (uint64_t) -1; s->slg = (uint64_t) -1;                              /* :538-539 */
+    s->rhol = (int64_t *) calloc(rhonb ? rhonb : 1, sizeof(int64_t));
+    s->rhoA = (int64_t *) calloc(rhonb ? rhonb : 1, sizeof(int64_t));
+    const uint64_t ng = (uint64_t) gns * gnb;
+    s->gl = (int64_t *) calloc(ng > 0 ? ng : 1, sizeof(int64_t));
+    s->gA = (int64_t *) calloc(ng > 0 ? ng : 1, sizeof(int64_t));
+    hist_fgrho(s);                                                                 /* setupMCS :773-776 */
+    hist_ugrho(s);
+}
+
+void jmo_take_histograms(jmo_state *s, int64_t *rhoA, int64_t *gA) {
+    if (rhoA) { memcpy(rhoA, s->rhoA, s->rhonb * sizeof(int64_t)); memset(s->rhoA, 0, s->rhonb * sizeof(int64_t)); }
+    if (gA) { memcpy(gA, s->gA, (uint64_t) s->gns * s->gnb * sizeof(int64_t)); memset(s->gA, 0, (uint64_t) s->gns * s->gnb * sizeof(int64_t)); }
+}
+
 /* ------------------------------------------------------------------ trial moves */
 
 /* qad2, src/jmmMCState.cpp:1160-1464.  Left partners (ii<nm, :1213-1268) and right partners
@@ -287,7 +369,7 @@ static int displacement_trial(jmo_state *s, uint64_t nm, double rn) {
     const double cut = s->cfg.cutoff, l = s->l;
     double md = (rn - 0.5) * 2 * s->maxStep;                         /* :1182 */
     double rT = s->r[nm] + md;                                       /* :1183 */
-    if (fabs(rT) > l / 2.0) { s->dAcc[1]++; return 0; }              /* :1188-1193 */
+    if (fabs(rT) > l / 2.0) { s->dAcc[1]++; if (s->hist) hist_ugrho(s); return 0; }   /* :1188-1193, ugrho :1453 */
 
     double dL[9] = {0}, dR[9] = {0}, po[9], pn[9];
     uint64_t lo = (nbn < 0 || (uint64_t) nbn > nm) ? 0 : nm - (uint64_t) nbn;
@@ -326,7 +408,9 @@ static int displacement_trial(jmo_state *s, uint64_t nm, double rn) {
             for (uint64_t i = 0; i < nm; i++)     s->rij[pair_index(N, i, nm)] += md;
             for (uint64_t j = nm + 1; j < N; j++) s->rij[pair_index(N, nm, j)] -= md;
         }
+        if (s->hist) hist_qagrho(s, nm, md);                                     /* :1431 */
     } else s->dAcc[1]++;                                                         /* :1447 */
+    if (s->hist) hist_ugrho(s);                                                  /* :1453 */
     return accept;
 }
 
@@ -364,9 +448,11 @@ static int volume_trial_LJ(jmo_state *s, double rn) {
         /* HV, HV12, HV6 are left untouched by the reference (:1675-1686) */
         for (uint64_t i = 0; i < s->N; i++) s->r[i] = lRat1 * s->r[i];                     /* :1692 */
         if (s->rij) for (uint64_t p = 0; p < s->numPairs; p++) s->rij[p] = lRat1 * s->rij[p];  /* :1699 */
+        if (s->hist) { hist_fgrho(s); hist_ugrho(s); }                                     /* :1717, :1726 */
         return 1;
     }
     s->vAcc[1]++;
+    if (s->hist) hist_ugrho(s);                                                            /* :1726 */
     return 0;
 }
 
@@ -418,8 +504,13 @@ int jmo_step(jmo_state *s) {
     return acc;
 }
 
+static void jmo_cadence_adjust_only(jmo_state *s);
 /* maxDisAdjust :2100-2115, maxDVAdjust :2120-2139, periodic relax src/Main.cpp:173-176 */
 void jmo_cadence(jmo_state *s) {
+    jmo_cadence_adjust_only(s);
+    if (s->sn % 10000 == 0 && s->sn < 1E6 && s->cfg.relax > 0) jmo_relax_volume(s);
+}
+static void jmo_cadence_adjust_only(jmo_state *s) {
     if (s->cfg.mdai && s->sn % s->cfg.mdai == 0) {
         double idealRatio = 0.5;
         double actualRatio = (double) s->dAcc[0] / (s->dAcc[0] + s->dAcc[1]);
@@ -437,7 +528,6 @@ void jmo_cadence(jmo_state *s) {
             else if (s->maxdl > 0.10 * s->N) s->maxdl = 0.50 * s->N;
         }
     }
-    if (s->sn % 10000 == 0 && s->sn < 1E6 && s->cfg.relax > 0) jmo_relax_volume(s);
 }
 
 void jmo_run(jmo_state *s, uint64_t nsteps) {
@@ -484,6 +574,57 @@ void jmo_run_deck(jmo_state *s, uint64_t numsteps, uint64_t tpi, uint64_t cpi,
         fprintf(log, "\nE = %.8G\n", s->tot[JMO_E]);
         fprintf(log, "Accepted/Rejected: %lu/%lu %lu/%lu\n", (unsigned long) s->dAcc[0], (unsigned long) s->dAcc[1],
                 (unsigned long) s->vAcc[0], (unsigned long) s->vAcc[1]);
+    }
+}
+
+/* printRho :1021-1038 and printG :1042-1064, byte-compatible */
+static void print_rho(jmo_state *s, FILE *f) {
+    uint64_t ns = s->sn - s->slrho;
+    if (f) fprintf(f, "%lu", (unsigned long) s->sn);
+    for (uint64_t b = 0; b < s->rhonb; b++) {
+        double m = (double) (int) s->rhoA[b] / ns / s->rbw;
+        if (f) fprintf(f, " %.8G", m);
+        s->rhoA[b] = 0;
+    }
+    if (f) fprintf(f, "\n");
+    s->slrho = s->sn;
+}
+static void print_g(jmo_state *s, FILE **gf) {
+    uint64_t ns = s->sn - s->slg;
+    for (int k = 0; k < s->gns; k++) {
+        FILE *f = gf ? gf[k] : NULL;
+        if (f) fprintf(f, "%lu", (unsigned long) s->sn);
+        for (uint64_t b = 0; b < s->gnb; b++) {
+            double m = (double) (int) s->gA[k * s->gnb + b] / ns / s->gsw / s->gbw;
+            if (f) fprintf(f, " %.8G", m);
+            s->gA[k * s->gnb + b] = 0;
+        }
+        if (f) fprintf(f, "\n");
+    }
+    s->slg = s->sn;
+}
+
+/* src/Main.cpp:66-180 with all four kinds of output */
+void jmo_run_deck_hist(jmo_state *s, uint64_t numsteps, uint64_t tpi, uint64_t cpi, uint64_t rhopi, uint64_t gpi,
+                       FILE *thermo, FILE *config, FILE *rho, FILE **gfiles, FILE *log) {
+    if (thermo) fprintf(thermo, "Step    Econf           Econf2          L       L2  "
+                                "    LEconf          rho             rho2            Virial      "
+                                "   Virial2         EconfVir        HV              HV2 \n");
+    jmo_step0(s);
+    if (s->cfg.relax > 0) jmo_relax_volume(s);
+    print_coords(s, config);
+    print_rho(s, rho);
+    jmo_update_thermo(s);
+    print_thermo(s, thermo, log);
+    print_g(s, gfiles);
+    while (s->sn != numsteps) {
+        jmo_step(s);
+        if (cpi && s->sn % cpi == 0) print_coords(s, config);
+        if (tpi && s->sn % tpi == 0) print_thermo(s, thermo, log);
+        if (rhopi && s->sn % rhopi == 0) print_rho(s, rho);
+        jmo_cadence_adjust_only(s);
+        if (gpi && s->sn % gpi == 0) print_g(s, gfiles);
+        if (s->sn % 10000 == 0 && s->sn < 1E6 && s->cfg.relax > 0) jmo_relax_volume(s);
     }
 }
 

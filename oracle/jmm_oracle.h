@@ -100,6 +100,16 @@ void     jmo_taus2_seed(uint32_t st[3], uint64_t seed);
 uint32_t jmo_taus2_next(uint32_t st[3]);
 void     jmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
+/* density / two-particle-density histograms: fgrho :1069-1127, qagrho :2297-2384,
+ * ugrho :1131-1149, printRho :1021-1038, printG :1042-1064.  Enabled per chain; the restatement keeps the
+ * reference's add-the-whole-histogram-every-step accumulation. */
+void jmo_enable_histograms(jmo_state *s, uint64_t rhonb, double rbw, int gns, uint64_t gnb, double gsw, double gbw);
+/* accumulated counts since the last call (then zeroed, like printRho/printG); either pointer may be NULL */
+void jmo_take_histograms(jmo_state *s, int64_t *rhoA /*[rhonb]*/, int64_t *gA /*[gns][gnb]*/);
+/* full run with all four kinds of output files; gfiles[k] may be NULL */
+void jmo_run_deck_hist(jmo_state *s, uint64_t numsteps, uint64_t tpi, uint64_t cpi, uint64_t rhopi, uint64_t gpi,
+                       FILE *thermo, FILE *config, FILE *rho, FILE **gfiles, FILE *log);
+
 /* large-chain checkerboard sweep (configs C3/C5): one colour half-sweep over every particle of
  * colour `colour` (index mod ncolours), recompute mode, Philox keyed by (seed, chain, sweep step,
  * particle).  Returns the number of accepted moves; dtot[9] receives the summed deltas. */

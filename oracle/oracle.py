@@ -221,6 +221,35 @@ class Chain:
     def config_totals(self, scale=1.0, virflag=1, l=None):
         a = np.empty(9); self.L.jmo_config_totals(self.h, scale, virflag, self.l if l is None else l, _dp(a)); return a
 
+    def enable_histograms(self, rhonb, rbw, gns, gnb, gsw, gbw):
+        self.L.jmo_enable_histograms.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_uint64, C.c_double, C.c_double]
+        self.L.jmo_enable_histograms(self.h, int(rhonb), float(rbw), int(gns), int(gnb), float(gsw), float(gbw))
+        self._hist = (int(rhonb), int(gns), int(gnb))
+
+    def take_histograms(self):
+        rhonb, gns, gnb = self._hist
+        a = np.zeros(rhonb, dtype=np.int64); g = np.zeros((gns, gnb), dtype=np.int64)
+        self.L.jmo_take_histograms.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        self.L.jmo_take_histograms(self.h, a.ctypes.data_as(C.POINTER(C.c_int64)), g.ctypes.data_as(C.POINTER(C.c_int64)))
+        return a, g
+
+    def run_deck_hist(self, d, outdir):
+        """Full run of deck dict `d` with thermo/config/rho/g<k> files written into outdir."""
+        outdir = Path(outdir)
+        self.enable_histograms(d["RHONB"], d["RBW"], d["GNS"], d["GNB"], d["GSW"], d["GBW"])
+        libc = C.CDLL(None)
+        libc.fopen.restype = C.c_void_p; libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+        libc.fclose.argtypes = [C.c_void_p]
+        op = lambda n: libc.fopen(str(outdir / n).encode(), b"w")
+        tf, cf, rf = op("thermo.dat.mcs"), op("config.dat.mcs"), op("rho.dat.mcs")
+        gns = int(d["GNS"])
+        gfs = (C.c_void_p * gns)(*[op(f"g{k}.dat.mcs") for k in range(gns)])
+        self.L.jmo_run_deck_hist.argtypes = [C.c_void_p] + [C.c_uint64] * 5 + [C.c_void_p] * 5
+        self.L.jmo_run_deck_hist(self.h, int(d["NUMSTEPS"]), int(d["TPI"]), int(d["CPI"]), int(d["RHOPI"]), int(d["GPI"]),
+                                 tf, cf, rf, gfs, None)
+        for f in [tf, cf, rf] + list(gfs):
+            libc.fclose(f)
+
     def run_deck(self, numsteps, tpi, cpi, thermo_path=None, config_path=None, log_path=None):
         libc = C.CDLL(None)
         libc.fopen.restype = C.c_void_p; libc.fopen.argtypes = [C.c_char_p, C.c_char_p]

@@ -56,7 +56,7 @@ def last_frame(config_text: str):
     return box, [float(x.split()[3]) for x in frame[2:]]
 
 
-def run(name, deck, keep_rng=True, keep_files=True):
+def run(name, deck, keep_rng=True, keep_files=True, keep_hist=False):
     out = HERE / name
     out.mkdir(exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
@@ -79,6 +79,10 @@ def run(name, deck, keep_rng=True, keep_files=True):
             (out / "config.dat.mcs").write_bytes(config)
         else:
             (out / "thermo.tail.mcs").write_bytes(b"\n".join(thermo.splitlines()[-5:]) + b"\n")
+        if keep_hist:
+            for f in sorted(Path(tmp).glob("rho.dat.mcs")) + sorted(Path(tmp).glob("g*.dat.mcs")):
+                (out / f.name).write_bytes(f.read_bytes())
+                s[f.name + "_md5"] = hashlib.md5(f.read_bytes()).hexdigest()
         if keep_rng:
             R["rng"].tofile(out / "rng.u32")
         (out / "summary.json").write_text(json.dumps(s, indent=1) + "\n")
@@ -116,6 +120,11 @@ def main():
     run("inputstd", (REF_TEST / "INPUTstd").read_text())
     big = (REF_TEST / "INPUT").read_text()
     run("input_n2000_40", deck_with(big, NUMSTEPS=40, CPI=40, TPI=5), keep_rng=True)
+    # density / two-particle-density histograms (rho.dat.mcs, g<k>.dat.mcs): SURVEY §8f N2
+    run("smalltest_hist", deck_with(small, NUMSTEPS=3000, TPI=500, CPI=1500, RBW=0.5, RHONB=40, RHOPI=500, GSW=5.0, GNS=4,
+                                    GBW=0.2, GNB=60, GPI=1000), keep_rng=False, keep_hist=True)
+    run("inputstd_hist", deck_with((REF_TEST / "INPUTstd").read_text(), NUMSTEPS=2000, TPI=500, CPI=1000, RBW=0.5, RHONB=40,
+                                   RHOPI=250, GSW=10, GNS=2, GBW=0.1, GNB=50, GPI=500), keep_rng=False, keep_hist=True)
     # block averages for the 2-sigma ensemble test (north_star): 32 reference runs x 5 blocks of 200 000 steps, no RELAX
     blocks = deck_with(small.replace("RELAX\n", ""), NUMSTEPS=1000000, TPI=200000, CPI=1000000)
     reference_ensemble("smalltest_ensemble", blocks)

@@ -137,3 +137,19 @@ def test_checkerboard_oracle_is_a_valid_sampler(O):
     fresh = O.totals_of(r, nbn, O.POT["LJcut"], 5.0, 1.0, 1, L)
     assert np.allclose(tot, fresh, rtol=1e-11, atol=1e-9)
     assert np.all(np.diff(r) > 0)
+
+
+@pytest.mark.parametrize("name", ["smalltest_hist", "inputstd_hist"])
+def test_oracle_histograms_reproduce_reference_files(O, gold, tmp_path, name):
+    """rho.dat.mcs and g<k>.dat.mcs (fgrho/qagrho/ugrho/printRho/printG) byte for byte, including the reference's
+    quirks: fav never updates or accumulates the histograms, the old bin is re-derived from r[nm]-md."""
+    g = gold(name)
+    d = O.parse_deck(g["deck_text"])
+    c = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_TAUS2, mode=O.MODE_TABLE))
+    c.run_deck_hist(d, tmp_path)
+    files = ["rho.dat.mcs", "config.dat.mcs"] + [f"g{k}.dat.mcs" for k in range(int(d["GNS"]))]
+    if d["POT"] != "HARMONIC":
+        files.append("thermo.dat.mcs")
+    for f in files:
+        assert (tmp_path / f).read_bytes() == (g["dir"] / f).read_bytes(), f
+    assert [int(x) for x in c.counters] == g["summary"]["counters"]
