@@ -168,6 +168,18 @@ jmm_status jmm_echeck_stats(jmm_handle *h, uint64_t *checks, uint64_t *discrepan
 /* words of the recorded stream consumed so far */
 uint64_t   jmm_stream_cursor(const jmm_handle *h);
 
+/* Density rho(x) and two-particle density g(x) histograms for many-chain handles:
+ * fgrho :1069-1127, qagrho :2297-2384, ugrho :1131-1149 with the reference's bins —
+ *   rho bin  = floor(r/RBW + RHONB/2);  g segment = floor(r/GSW + GNS/2);  g bin = floor(|rij|/GBW).
+ * Call after jmm_create/jmm_set_state and before jmm_start: it performs the fgrho + ugrho of setupMCS
+ * (:773-776) on the current configuration.  The reference's quirks are kept: fav and relaxVolume never
+ * touch the histograms, a fav step is not accumulated.  Accumulation is lazy (per changed bin), the
+ * integers are the reference's. */
+jmm_status jmm_enable_histograms(jmm_handle *h, uint64_t rhonb, double rbw, int32_t gns, uint64_t gnb, double gsw, double gbw);
+/* What printRho :1021-1038 / printG :1042-1064 read and reset: the counts accumulated since the last call.
+ * rhoA [nchains][rhonb], gA [nchains][gns][gnb]; a NULL pointer leaves that histogram untouched. */
+jmm_status jmm_take_histograms(jmm_handle *h, int64_t *rhoA, int64_t *gA);
+
 /* JMM_MODE_CHECKERBOARD (no reference counterpart — the reference moves
  * one particle per Step and cannot allocate its O(N^2) tables beyond N ~ 1e4).  One call performs
  * n_halfsweeps colour half-sweeps: in each, a colour c in [0, NBN+1) is drawn (Philox) and every

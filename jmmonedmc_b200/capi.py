@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         "jmm_echeck_stats": (C.c_int32, [H, u64p, u64p]),
         "jmm_stream_cursor": (C.c_uint64, [H]),
         "jmm_sweep": (C.c_int32, [H, C.c_uint64, u64p]),
+        "jmm_enable_histograms": (C.c_int32, [H, C.c_uint64, C.c_double, C.c_int32, C.c_uint64, C.c_double, C.c_double]),
+        "jmm_take_histograms": (C.c_int32, [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "jmm_kernel_launches": (C.c_uint64, [H]),
         "jmm_last_kernel_ms": (C.c_double, [H]),
         "jmm_set_stream": (C.c_int32, [H, C.c_void_p]),
@@ -241,6 +243,18 @@ class Handle:
         a, b = C.c_uint64(), C.c_uint64()
         _check(self.L.jmm_echeck_stats(self.h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def enable_histograms(self, rhonb, rbw, gns, gnb, gsw, gbw):
+        _check(self.L.jmm_enable_histograms(self.h, int(rhonb), float(rbw), int(gns), int(gnb), float(gsw), float(gbw)))
+        self._hist = (int(rhonb), int(gns), int(gnb))
+
+    def take_histograms(self, rho=True, g=True):
+        rhonb, gns, gnb = self._hist
+        a = np.zeros((self.C, rhonb), dtype=np.int64) if rho else None
+        b = np.zeros((self.C, gns, gnb), dtype=np.int64) if g else None
+        p = lambda x: x.ctypes.data_as(C.POINTER(C.c_int64)) if x is not None else None
+        _check(self.L.jmm_take_histograms(self.h, p(a), p(b)))
+        return a, b
 
     def sweep(self, n_halfsweeps):
         t = C.c_uint64()

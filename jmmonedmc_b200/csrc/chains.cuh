@@ -49,6 +49,88 @@ struct StepArgs {
     int pos_in_smem;
 };
 
+__device__ __forceinline__ uint64_t pair_index(uint64_t N, uint64_t i, uint64_t j) {   // :142-148
+    return i * (N - 1) - (i * (i + 1)) / 2 + j - 1;
+}
+
+// Density rho(x) and two-particle density g(x) histograms: fgrho :1069-1127, qagrho :2297-2384,
+// ugrho :1131-1149.  The reference adds the WHOLE histogram to the accumulator on every step (54 % of its run
+// time at N = 80); here a bin's accumulator is brought up to date only when the bin changes or is read:
+//   acc += value * (ugrho calls since the bin was last touched)        — the same integers, O(changed bins).
+// Layout: chain-major [chain][bin]; null pointers = histograms off.
+struct HistDev {
+    uint64_t rhonb, gnb;
+    int gns;
+    double rbw, gsw, gbw;
+    int32_t *rhol, *gl;          // current counts                      (rhol :180, gl :187)
+    long long *rhoA, *gA;        // accumulated counts since last print (rhoA :182, gA :189)
+    uint64_t *rhoLast, *gLast;   // ugrho count at which the bin's accumulator was last updated
+    uint64_t *ucount;            // [nchains] ugrho calls so far
+};
+
+__device__ __forceinline__ void hist_bump(int32_t *val, long long *acc, uint64_t *last, uint64_t idx, int delta, uint64_t u) {
+    acc[idx] += (long long) val[idx] * (long long) (u - last[idx]);
+    last[idx] = u;
+    val[idx] += delta;
+}
+
+// fgrho :1069-1127 for one chain (positions r, stride rs; rij table when TABLE)
+template <bool TABLE>
+__device__ __forceinline__ void hist_fgrho(const HistDev &H, uint64_t c, const double *r, size_t rs, const double *rij, size_t ts,
+                                           uint32_t N, uint64_t u) {
+    int32_t *rl = H.rhol + c * H.rhonb;
+    long long *ra = H.rhoA + c * H.rhonb;
+    uint64_t *rt = H.rhoLast + c * H.rhonb;
+    for (uint64_t b = 0; b < H.rhonb; ++b) { ra[b] += (long long) rl[b] * (long long) (u - rt[b]); rt[b] = u; rl[b] = 0; }
+    for (uint32_t i = 0; i < N; ++i) {
+        const long long rb = (long long) floor(r[i * rs] / H.rbw + (double) H.rhonb / 2.0);
+        if (rb >= 0 && rb < (long long) H.rhonb) rl[rb]++;
+    }
+    const uint64_t ng = (uint64_t) H.gns * H.gnb;
+    int32_t *gl = H.gl + c * ng;
+    long long *ga = H.gA + c * ng;
+    uint64_t *gt = H.gLast + c * ng;
+    for (uint64_t b = 0; b < ng; ++b) { ga[b] += (long long) gl[b] * (long long) (u - gt[b]); gt[b] = u; gl[b] = 0; }
+    for (uint32_t i = 0; i + 1 < N; ++i)
+        for (uint32_t j = i + 1; j < N; ++j) {
+            const long long gs1 = (long long) floor(r[i * rs] / H.gsw + H.gns / 2.0);
+            const long long gs2 = (long long) floor(r[j * rs] / H.gsw + H.gns / 2.0);
+            const double d = TABLE ? rij[pair_index(N, i, j) * ts] : r[j * rs] - r[i * rs];
+            const long long gb = (long long) floor(d / H.gbw);
+            if (gb >= 0 && gb < (long long) H.gnb) {
+                if (gs1 >= 0 && gs1 < H.gns) gl[gs1 * H.gnb + gb]++;
+                if (gs2 >= 0 && gs2 < H.gns) gl[gs2 * H.gnb + gb]++;
+            }
+        }
+}
+
+// qagrho :2297-2384 after an accepted displacement of particle nm by md (old position re-derived as r[nm]-md)
+__device__ __forceinline__ void hist_qagrho(const HistDev &H, uint64_t c, const double *r, size_t rs, uint32_t N, uint32_t nm,
+                                            double md, uint64_t u) {
+    const double rn = r[nm * rs];
+    const long long rbn1 = (long long) floor((rn - md) / H.rbw + (double) H.rhonb / 2.0);
+    const long long rbn2 = (long long) floor(rn / H.rbw + (double) H.rhonb / 2.0);
+    if (rbn1 >= 0 && rbn1 < (long long) H.rhonb) hist_bump(H.rhol, H.rhoA, H.rhoLast, c * H.rhonb + rbn1, -1, u);
+    if (rbn2 >= 0 && rbn2 < (long long) H.rhonb) hist_bump(H.rhol, H.rhoA, H.rhoLast, c * H.rhonb + rbn2, +1, u);
+    const long long gs11 = (long long) floor((rn - md) / H.gsw + H.gns / 2.0);
+    const long long gs12 = (long long) floor(rn / H.gsw + H.gns / 2.0);
+    const bool in11 = gs11 >= 0 && gs11 < H.gns, in12 = gs12 >= 0 && gs12 < H.gns;
+    const uint64_t base = c * (uint64_t) H.gns * H.gnb;
+    for (uint32_t i = 0; i < N; ++i) {
+        if (i == nm) continue;
+        const double ri = r[i * rs];
+        const long long gs2 = (long long) floor(ri / H.gsw + H.gns / 2.0);
+        const bool in2 = gs2 >= 0 && gs2 < H.gns;
+        const long long gb1 = (long long) (unsigned long long) floor(fabs(rn - md - ri) / H.gbw);
+        const long long gb2 = (long long) (unsigned long long) floor(fabs(rn - ri) / H.gbw);
+        const bool b1 = gb1 >= 0 && gb1 < (long long) H.gnb, b2 = gb2 >= 0 && gb2 < (long long) H.gnb;
+        if (in11 && b1) hist_bump(H.gl, H.gA, H.gLast, base + gs11 * H.gnb + gb1, -1, u);
+        if (in12 && b2) hist_bump(H.gl, H.gA, H.gLast, base + gs12 * H.gnb + gb2, +1, u);
+        if (in2 && b1) hist_bump(H.gl, H.gA, H.gLast, base + gs2 * H.gnb + gb1, -1, u);
+        if (in2 && b2) hist_bump(H.gl, H.gA, H.gLast, base + gs2 * H.gnb + gb2, +1, u);
+    }
+}
+
 // ---------------------------------------------------------------- per-thread chain context
 
 template <int POT>
@@ -65,10 +147,6 @@ struct Chain {
     uint64_t cnt[kNCnt];
     uint64_t vAErr, echecks, discrepancies;
 };
-
-__device__ __forceinline__ uint64_t pair_index(uint64_t N, uint64_t i, uint64_t j) {   // :142-148
-    return i * (N - 1) - (i * (i + 1)) / 2 + j - 1;
-}
 
 template <int POT>
 __device__ __forceinline__ uint32_t row_end(const Chain<POT> &ch, uint32_t i) {       // last j of row i
@@ -394,6 +472,20 @@ __device__ __forceinline__ void adjust_max_dl(Chain<POT> &ch, double log_ideal) 
     }
 }
 
+// What qad2 / qavLJ do to the histograms after the trial (:1431, :1453, :1717, :1726); fav does nothing (:2161-2293).
+template <int POT, bool TABLE>
+__device__ __forceinline__ void hist_after_trial(const HistDev &H, uint64_t c, const Chain<POT> &ch, uint32_t nm, double rn,
+                                                 double maxStep_used, uint8_t flags, bool scaling_volume, uint64_t &u) {
+    if (flags & kLogVolume) {
+        if (!scaling_volume) return;                                   // fav: no fgrho, no ugrho
+        if (flags & kLogAccepted) hist_fgrho<TABLE>(H, c, ch.r, ch.rs, ch.rij, ch.ts, ch.N, u);
+        ++u;
+        return;
+    }
+    if (flags & kLogAccepted) hist_qagrho(H, c, ch.r, ch.rs, ch.N, nm, (rn - 0.5) * 2 * maxStep_used, u);
+    ++u;                                                               // ugrho :1453 on every displacement trial
+}
+
 // ---------------------------------------------------------------- state load / store
 
 // CG: read through L2 (ld.global.cg) — needed when another SM may have written the state earlier in the
@@ -495,7 +587,7 @@ __global__ void k_chains_totals_exact(ChainsDev S, double *out /*[9][nchains]*/)
 
 // nsteps x Step() for every chain
 template <int POT, bool TABLE, int RNG>
-__global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a) {
+__global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a, HistDev H) {
     extern __shared__ double smem[];
     const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= S.nchains) return;
@@ -521,11 +613,13 @@ __global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a) {
     uint64_t mvai_left = (a.adapt_device && a.mvai) ? a.mvai - sn % a.mvai : ~0ull;
     uint64_t relax_left = (a.adapt_device && S.relax > 0 && S.ensemble == kEnsNPT) ? 10000 - sn % 10000 : ~0ull;
 
+    uint64_t hist_u = H.ucount ? H.ucount[c] : 0;
     for (uint64_t s = 0; s < a.nsteps; ++s) {
         ++sn;                                                                         // incrementStep :1745
         rng.begin(sn);
         const uint32_t nm = rng.trial_type(ntt, scale);                               // :1762
         const double rn = rng.rn();                                                   // :1763
+        const double maxStep_used = ch.maxStep;
         uint8_t flags;
         if (nm < ch.N) flags = displacement_trial<POT, TABLE>(ch, nm, rn, rng);       // :1783-1785
         else {
@@ -534,6 +628,7 @@ __global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a) {
                                        : volume_trial_full<POT, TABLE>(ch, rn, rng);
             } else flags = volume_trial_full<POT, TABLE>(ch, rn, rng);                // :1786-1788
         }
+        if (H.ucount) hist_after_trial<POT, TABLE>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u);
         if (--eci_left == 0) { energy_check<POT, TABLE>(ch); eci_left = a.eci; }      // :1800-1802
         update_thermo(ch);                                                            // :1805
         if (a.accept_log) a.accept_log[s * S.nchains + c] = flags;
@@ -550,7 +645,28 @@ __global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a) {
         *a.cursor = rng.cur;
         if (rng.exhausted) *a.err = 1;
     }
+    if (H.ucount) H.ucount[c] = hist_u;
     store_chain(ch, S, c, a.pos_in_smem != 0);
+}
+
+// histogram set-up (setupMCS :773-776: fgrho + one ugrho on the initial configuration) and read-out
+template <bool TABLE>
+__global__ void k_hist_init(ChainsDev S, HistDev H) {
+    const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= S.nchains) return;
+    hist_fgrho<TABLE>(H, c, S.r + c, S.nchains, S.rij ? S.rij + c : nullptr, S.nchains, (uint32_t) S.N, 0);
+    H.ucount[c] = 1;
+}
+
+// bring every bin's accumulator up to date, copy it out, zero it (printRho :1021-1038 / printG :1042-1064)
+__global__ void k_hist_take(const int32_t *val, long long *acc, uint64_t *last, const uint64_t *ucount, uint64_t bins_per_chain,
+                            uint64_t nchains, long long *out) {
+    const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bins_per_chain * nchains) return;
+    const uint64_t u = ucount[t / bins_per_chain];
+    out[t] = acc[t] + (long long) val[t] * (long long) (u - last[t]);
+    acc[t] = 0;
+    last[t] = u;
 }
 
 // chain-major host layout <-> chain-fastest device layout

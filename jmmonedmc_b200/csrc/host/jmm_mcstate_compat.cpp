@@ -15,7 +15,8 @@
 // driving maxDisAdjust/maxDVAdjust/relaxVolume exactly as in the reference.  JMM_COMPAT_PRODUCTION=1
 // switches to the production arithmetic (positions only, Philox).
 //
-// Not provided (out of scope): rho(x) / g(x) histograms — printRho/printG create no rows.
+// rho(x) / g(x) histograms: jmm_enable_histograms / jmm_take_histograms; printRho and printG write
+// rho.dat.mcs and g<k>.dat.mcs in the reference's format.
 #include <math.h>
 #include <omp.h>
 #include <stdio.h>
@@ -37,6 +38,11 @@ struct MCState {
     int relaxFlag;
     char potStr[80], ensembleStr[80];
     FILE *cf, *tf, *rhof;
+    std::vector<FILE *> gf;
+    unsigned long int rhonb, gnb, slrho, slg;
+    int gns;
+    double rbw, gsw, gbw;
+    std::vector<int64_t> hist;
     std::vector<double> r;
     double l, tot[9], acc[12];
     uint64_t cnt[4];
@@ -109,9 +115,17 @@ struct MCState *setupMCS(struct MCInput inp) {
     printMCP(m);
     if (m->isRestart) { printf("jmm compat: RESTART is not supported (SURVEY §2: out of scope)\n"); exit(1); }
     if (jmm_create(&c, &m->h) != JMM_OK) die("jmm_create");
+    m->rhonb = inp.rhonb; m->gnb = inp.gnb; m->gns = inp.gns; m->rbw = inp.rbw; m->gsw = inp.gsw; m->gbw = inp.gbw;
+    m->slrho = (unsigned long int) -1; m->slg = (unsigned long int) -1;                                  // :538-539
+    JCK(jmm_enable_histograms(m->h, m->rhonb, m->rbw, m->gns, m->gnb, m->gsw, m->gbw));                  // fgrho + ugrho, :773-776
     m->cf = fopen("config.dat.mcs", "w");                                                                // :526-528
     m->tf = fopen("thermo.dat.mcs", "w");
     m->rhof = fopen("rho.dat.mcs", "w");
+    for (int k = 0; k < m->gns; k++) {                                                                   // :530-533
+        char name[32];
+        snprintf(name, sizeof name, "g%d.dat.mcs", k);
+        m->gf.push_back(fopen(name, "w"));
+    }
     fprintf(m->tf, "Step    Econf           Econf2          L       L2  "                                // :566-568
                    "    LEconf          rho             rho2            Virial      "
                    "   Virial2         EconfVir        HV              HV2 \n");
@@ -126,6 +140,7 @@ void freeMCS(struct MCState *m) {                                              /
     if (m->cf) fclose(m->cf);
     if (m->tf) fclose(m->tf);
     if (m->rhof) fclose(m->rhof);
+    for (FILE *f : m->gf) if (f) fclose(f);
     delete m;
 }
 
@@ -179,8 +194,34 @@ int printThermo(struct MCState *m) {                                           /
     return 0;
 }
 
-int printRho(struct MCState *) { return 0; }                                   // :1021-1038 — histograms: out of scope
-int printG(struct MCState *) { return 0; }                                     // :1042-1064
+int printRho(struct MCState *m) {                                              // :1021-1038
+    m->hist.resize(m->rhonb);
+    JCK(jmm_take_histograms(m->h, m->hist.data(), NULL));
+    const unsigned long int ns = m->sn - m->slrho;
+    fprintf(m->rhof, "%lu", m->sn);
+    for (unsigned long int b = 0; b < m->rhonb; b++) fprintf(m->rhof, " %.8G", (double) (int) m->hist[b] / ns / m->rbw);
+    fprintf(m->rhof, "\n");
+    fflush(m->rhof);
+    m->slrho = m->sn;
+    return 0;
+}
+
+int printG(struct MCState *m) {                                                // :1042-1064 (entered by every thread)
+    MASTER_ONLY(
+        m->hist.resize((size_t) m->gns * m->gnb);
+        JCK(jmm_take_histograms(m->h, NULL, m->hist.data()));
+        const unsigned long int ns = m->sn - m->slg;
+        for (int k = 0; k < m->gns; k++) {
+            fprintf(m->gf[k], "%lu", m->sn);
+            for (unsigned long int b = 0; b < m->gnb; b++)
+                fprintf(m->gf[k], " %.8G", (double) (int) m->hist[(size_t) k * m->gnb + b] / ns / m->gsw / m->gbw);
+            fprintf(m->gf[k], "\n");
+            fflush(m->gf[k]);
+        }
+        m->slg = m->sn;
+    );
+    return 0;
+}
 
 unsigned long int incrementStep(struct MCState *m) {                           // :1734-1754
     if (m->sn == m->numSteps) return 0;
@@ -198,8 +239,8 @@ int Step(struct MCState *m) {                                                  /
 
 int isCoordPrint(struct MCState *m) { return m->sn % m->cpi == 0; }            // :1815
 int isThermoPrint(struct MCState *m) { return m->sn % m->tpi == 0; }           // :1825
-int isRhoPrint(struct MCState *) { return 0; }                                 // :1836 — no histograms
-int isGPrint(struct MCState *) { return 0; }                                   // :1847
+int isRhoPrint(struct MCState *m) { return m->sn % m->rhopi == 0; }            // :1836
+int isGPrint(struct MCState *m) { return m->sn % m->gpi == 0; }                // :1847
 int isMaxDisAdjust(struct MCState *m) { return m->sn % m->mdai == 0; }         // :1870
 int isMaxDVAdjust(struct MCState *m) { return m->sn % m->mvai == 0; }          // :1883
 

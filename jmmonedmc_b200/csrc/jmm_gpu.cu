@@ -37,6 +37,7 @@ static jmm_status fail(jmm_status code, const std::string &msg) {
 struct jmm_handle {
     jmm_config cfg{};
     ChainsDev S{};
+    HistDev H{};                    // null pointers = histograms off
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -377,7 +378,7 @@ static cudaError_t launch_step_rng(jmm_handle *h, const StepArgs &a) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<nblk(h->S.nchains, h->block), h->block, h->smem, h->stream>>>(h->S, a);
+    kern<<<nblk(h->S.nchains, h->block), h->block, h->smem, h->stream>>>(h->S, a, h->H);
     h->launches++;
     return cudaGetLastError();
 }
@@ -435,10 +436,11 @@ static cudaError_t launch_step_prod(jmm_handle *h, const StepArgs &a) {
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
     const unsigned slots = (unsigned) std::max(1, per_sm * nsm);
     const double waves = (double) ntiles / slots;
-    const bool slice = getenv("JMM_FORCE_SLICE") ||
-                       (!getenv("JMM_NO_SLICE") && ntiles > slots && (waves - floor(waves)) < 0.85 && a.nsteps >= 16);
+    const bool slice = !h->H.ucount &&             // histogram bins are read through L1: keep a chain on one SM per launch
+                       (getenv("JMM_FORCE_SLICE") ||
+                        (!getenv("JMM_NO_SLICE") && ntiles > slots && (waves - floor(waves)) < 0.85 && a.nsteps >= 16));
     if (!slice) {
-        kern<<<ntiles, kTile, h->smem, h->stream>>>(h->S, a);
+        kern<<<ntiles, kTile, h->smem, h->stream>>>(h->S, a, h->H);
         h->launches++;
         return cudaGetLastError();
     }
@@ -453,7 +455,7 @@ static cudaError_t launch_step_prod(jmm_handle *h, const StepArgs &a) {
         h->work_words = (size_t) ntiles + 1;
     }
     if ((e = cudaMemsetAsync(h->d_work, 0, ((size_t) ntiles + 1) * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
-    sliced<<<std::min(slots, ntiles * nchunks), kTile, h->smem, h->stream>>>(h->S, a, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
+    sliced<<<std::min(slots, ntiles * nchunks), kTile, h->smem, h->stream>>>(h->S, a, h->H, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
     h->launches++;
     return cudaGetLastError();
 }
@@ -638,6 +640,51 @@ extern "C" jmm_status jmm_echeck_stats(jmm_handle *h, uint64_t *checks, uint64_t
     if (checks) *checks = a;
     if (discrepancies) *discrepancies = b;
     return JMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// histograms
+// ------------------------------------------------------------------------------------------------
+extern "C" jmm_status jmm_enable_histograms(jmm_handle *h, uint64_t rhonb, double rbw, int32_t gns, uint64_t gnb, double gsw, double gbw) {
+    if (!h || is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_enable_histograms: many-chain handles only");
+    if (h->H.ucount) return fail(JMM_ERR_INVALID, "histograms are already enabled");
+    if (h->sn != 0) return fail(JMM_ERR_INVALID, "enable histograms before the first step");
+    if (!(rbw > 0) || !(gsw > 0) || !(gbw > 0) || gns < 0) return fail(JMM_ERR_INVALID, "bad histogram geometry");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains, ng = (uint64_t) gns * gnb;
+    HistDev H{};
+    H.rhonb = rhonb; H.gnb = gnb; H.gns = gns; H.rbw = rbw; H.gsw = gsw; H.gbw = gbw;
+    CK(dalloc(h, &H.rhol, C * rhonb)); CK(dalloc(h, &H.rhoA, C * rhonb)); CK(dalloc(h, &H.rhoLast, C * rhonb));
+    CK(dalloc(h, &H.gl, C * ng)); CK(dalloc(h, &H.gA, C * ng)); CK(dalloc(h, &H.gLast, C * ng));
+    CK(dalloc(h, &H.ucount, C));
+    h->H = H;
+    h->coop_g = 0; h->bond = 0;                    // the per-thread kernels carry the histogram hooks
+    // distances from the positions: setupMCS fills rij = r[j]-r[i] (:768) just before its fgrho, the same doubles
+    k_hist_init<false><<<nblk(C, 32), 32, 0, h->stream>>>(h->S, h->H);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_take_histograms(jmm_handle *h, int64_t *rhoA, int64_t *gA) {
+    if (!h || !h->H.ucount) return fail(JMM_ERR_INVALID, "histograms are not enabled on this handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint64_t C = h->S.nchains;
+    auto take = [&](const int32_t *val, long long *acc, uint64_t *last, uint64_t bins, int64_t *out) -> jmm_status {
+        if (!out || bins == 0) return JMM_OK;
+        jmm_status st = ensure_stage(h, C * bins * sizeof(long long));
+        if (st != JMM_OK) return st;
+        k_hist_take<<<nblk(C * bins, 256), 256, 0, h->stream>>>(val, acc, last, h->H.ucount, bins, C, (long long *) h->d_stage);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, h->d_stage, C * bins * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return JMM_OK;
+    };
+    jmm_status st = take(h->H.rhol, h->H.rhoA, h->H.rhoLast, h->H.rhonb, rhoA);
+    if (st != JMM_OK) return st;
+    return take(h->H.gl, h->H.gA, h->H.gLast, (uint64_t) h->H.gns * h->H.gnb, gA);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -110,7 +110,7 @@ __device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, const 
 // COHERENT: chain state is read with ld.global.cg (L2) because another SM may just have written it
 // (persistent time-sliced launch below).
 template <int POT, int ARITH, bool LOG, bool COHERENT>
-__device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs &a, uint64_t c, double *smem,
+__device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs &a, const HistDev &H, uint64_t c, double *smem,
                                               uint64_t sn0, uint32_t count, uint64_t log_row0) {
     Chain<POT> ch;
     load_chain<POT, COHERENT>(ch, S, c, smem + threadIdx.x, kTile);   // ch.r -> shared tile (rare paths use it generically)
@@ -136,12 +136,14 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
     const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
     const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
     double l_seen = ch.l, rho = (double) ch.N / ch.l;         // N/l only changes with l
+    uint64_t hist_u = H.ucount ? ld_state<COHERENT>(H.ucount + c) : 0;
 
     for (uint32_t s = 0; s < count; ++s) {
         ++sn;
         rng.begin(sn);
         const uint32_t nm = rng.trial_type(ntt, scale);
         const double rn = rng.rn();
+        const double maxStep_used = ch.maxStep;
         uint8_t flags;
         if (nm < ch.N) {
             if constexpr (ARITH == kArithFast) flags = prod_displacement_fast<POT>(ch, rs, rs_w, nm, rn, rng.ran());
@@ -151,6 +153,7 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
                 flags = scaling_volume ? volume_trial_scaling<POT, false>(ch, rn, rng) : volume_trial_full<POT, false>(ch, rn, rng);
             } else flags = volume_trial_full<POT, false>(ch, rn, rng);
         }
+        if (H.ucount) hist_after_trial<POT, false>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u);
         if (--eci_left == 0) { energy_check<POT, false>(ch); eci_left = eci32; }
         if (ch.l != l_seen) { l_seen = ch.l; rho = (double) ch.N / ch.l; }
         {   // updateThermo :1941-1961 with the cached N/l
@@ -172,15 +175,16 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
             if (--relax_left == 0) { if (sn < 1000000ull) relax_volume<POT, false>(ch); relax_left = 10000; }
         }
     }
+    if (H.ucount) H.ucount[c] = hist_u;
     store_chain(ch, S, c, true);
 }
 
 template <int POT, int ARITH, bool LOG>
-__global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArgs a) {
+__global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArgs a, HistDev H) {
     extern __shared__ double smem[];
     const uint64_t c = (uint64_t) blockIdx.x * kTile + threadIdx.x;
     if (c >= S.nchains) return;
-    prod_run_tile<POT, ARITH, LOG, false>(S, a, c, smem, a.sn0, (uint32_t) a.nsteps, 0);
+    prod_run_tile<POT, ARITH, LOG, false>(S, a, H, c, smem, a.sn0, (uint32_t) a.nsteps, 0);
 }
 
 // Persistent, time-sliced variant for launches that would otherwise need a fractional number of waves
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArg
 // (release/acquire).  Every earlier item is held by a running CTA, so the wait always ends.  Chain state goes
 // through L2 between chunks (8N+256 B per chain per chunk: negligible next to `chunk` steps of work).
 template <int POT, int ARITH, bool LOG>
-__global__ void __launch_bounds__(kTile) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, uint32_t chunk, uint32_t ntiles,
+__global__ void __launch_bounds__(kTile) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, HistDev H, uint32_t chunk, uint32_t ntiles,
                                                                    uint32_t nchunks, unsigned int *work, unsigned int *progress) {
     extern __shared__ double smem[];
     for (;;) {
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod_sliced(ChainsDev S, 
         const uint64_t c = (uint64_t) tile * kTile + threadIdx.x;
         const uint32_t s0 = k * chunk;
         const uint32_t count = min(chunk, (uint32_t) a.nsteps - s0);
-        if (c < S.nchains) prod_run_tile<POT, ARITH, LOG, true>(S, a, c, smem, a.sn0 + s0, count, s0);
+        if (c < S.nchains) prod_run_tile<POT, ARITH, LOG, true>(S, a, H, c, smem, a.sn0 + s0, count, s0);
         __threadfence();
         __syncwarp();
         if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(progress + tile), "r"(k + 1) : "memory");

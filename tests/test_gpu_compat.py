@@ -44,6 +44,20 @@ def test_reference_main_on_gpu_engine_writes_identical_files(gold, tmp_path, nam
     assert "PROGRAM COMPLETED SUCCESSFULLY!" in stdout
 
 
+@pytest.mark.parametrize("name", ["smalltest_hist", "inputstd_hist"])
+def test_reference_main_on_gpu_engine_histogram_files(gold, tmp_path, name):
+    """rho.dat.mcs and g<k>.dat.mcs written by the reference's Main.cpp driving the GPU engine: byte-identical."""
+    if not BIN.exists():
+        pytest.skip("oracle/_ref/jmmOneDMC_gpu not built")
+    g = gold(name)
+    _run(g["deck_text"], tmp_path)
+    files = ["rho.dat.mcs", "config.dat.mcs"] + sorted(p.name for p in g["dir"].glob("g*.dat.mcs"))
+    if name != "inputstd_hist":
+        files.append("thermo.dat.mcs")
+    for f in files:
+        assert (tmp_path / f).read_bytes() == (g["dir"] / f).read_bytes(), f
+
+
 def test_reference_main_on_gpu_engine_production_mode_runs(gold, tmp_path):
     if not BIN.exists():
         pytest.skip("oracle/_ref/jmmOneDMC_gpu not built")

@@ -311,3 +311,48 @@ def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C, arith):
         # incrementally maintained totals: thousands of added deltas on both sides, in different orders
         assert totals_close(s["totals"][c], fresh[c], 1e-11) and totals_close(tot, fresh[c], 1e-11)
     assert trials == sum(int(x) for x in s["counters"].sum(axis=1))
+
+
+@pytest.mark.parametrize("name", ["small", "std", "ljcut_nbn"])
+@pytest.mark.parametrize("engine", ["prod", "generic", "table"])
+def test_histograms_match_oracle_integers(J, O, name, engine, monkeypatch):
+    """rho(x) and g(x) counts (fgrho/qagrho/ugrho) accumulated lazily on the device must equal, integer for integer,
+    the oracle's add-the-whole-histogram-every-step accumulation — at every read-out, for every chain."""
+    if engine == "generic":
+        monkeypatch.setenv("JMM_NO_PROD", "1")
+    d = DECKS[name]
+    C, id0 = 21, 300
+    geo = dict(rhonb=48, rbw=0.5, gns=4, gnb=70, gsw=6.0, gbw=0.25)
+    table = engine == "table"
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_TABLE if table else J.MODE_RECOMPUTE,
+                               adapt=J.ADAPT_HOST, nchains=C, chain_id0=id0)
+    chains = []
+    for c in range(C):
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_TABLE if table else O.MODE_RECOMPUTE, chain_id=id0 + c))
+        oc.enable_histograms(**geo)
+        oc.start()
+        chains.append(oc)
+    with J.Handle(cfg) as h:
+        h.enable_histograms(**geo)
+        h.start()
+        for nsteps, take_rho, take_g in ((0, True, True), (700, True, False), (500, False, True), (900, True, True)):
+            if nsteps:
+                h.step(nsteps)
+                for oc in chains:
+                    oc.run(nsteps)
+            rho, g = h.take_histograms(rho=take_rho, g=take_g)
+            for c, oc in enumerate(chains):
+                wr, wg = oc.take_histograms() if (take_rho and take_g) else (None, None)
+                if wr is None:       # take only one of the two on the oracle side as well
+                    import ctypes as Ct
+                    a = np.zeros(geo["rhonb"], dtype=np.int64); b = np.zeros((geo["gns"], geo["gnb"]), dtype=np.int64)
+                    oc.L.jmo_take_histograms(oc.h, a.ctypes.data_as(Ct.POINTER(Ct.c_int64)) if take_rho else None,
+                                             b.ctypes.data_as(Ct.POINTER(Ct.c_int64)) if take_g else None)
+                    wr, wg = a, b
+                if take_rho:
+                    assert np.array_equal(rho[c], wr), f"chain {c}: rho counts after {nsteps} more steps"
+                if take_g:
+                    assert np.array_equal(g[c], wg), f"chain {c}: g counts after {nsteps} more steps"
+        s = h.get_state()
+    for c, oc in enumerate(chains):
+        assert bits_equal(s["r"][c], oc.r)
