@@ -62,7 +62,8 @@ int main(int argc, char **argv) {
     if (C == 0) { fprintf(stderr, "jmm_run: rank %lu has no chains\n", (unsigned long) rank); return 1; }
     cfg.nchains = C;
     cfg.chain_id0 = c0;
-    if (lockstep) { cfg.rng_kind = JMM_RNG_TAUS2; cfg.mode = JMM_MODE_TABLE; cfg.adapt = JMM_ADAPT_HOST; }
+    // lock-step: the host drives maxDisAdjust/maxDVAdjust/relaxVolume itself, in Main.cpp's order between the prints
+    if (lockstep) { cfg.rng_kind = JMM_RNG_TAUS2; cfg.mode = JMM_MODE_TABLE; cfg.adapt = JMM_ADAPT_CALLER; }
     if (cfg.ensemble == JMM_ENS_NPT) printf("ENSEMBLE = NPT\n"); else printf("ENSEMBLE = NLT\n");
     printf("N: %lu  chains: %lu (global %lu..%lu of %lu)  numSteps: %lu  POT %s  NBN %d\n", (unsigned long) cfg.N,
            (unsigned long) C, (unsigned long) c0, (unsigned long) c1 - 1, (unsigned long) total,
@@ -89,6 +90,17 @@ int main(int argc, char **argv) {
     if (!tf || (single && !cf)) { fprintf(stderr, "jmm_run: cannot open output files in %s\n", outdir.c_str()); return 1; }
     if (single) fputs(kThermoHeader, tf); else fprintf(tf, "chain\t%s", kThermoHeader);
 
+    // histograms: a single chain writes rho.dat.mcs and g<k>.dat.mcs like the reference (src/jmmMCState.cpp:526-533)
+    const bool hist = single && deck.rhonb > 0 && deck.rbw > 0 && deck.gsw > 0 && deck.gbw > 0 && !getenv("JMM_RUN_NO_HIST");
+    FILE *rhof = nullptr;
+    std::vector<FILE *> gf;
+    std::vector<int64_t> hbuf;
+    uint64_t slrho = (uint64_t) -1, slg = (uint64_t) -1;
+    if (hist) {
+        JCK(jmm_enable_histograms(h, deck.rhonb, deck.rbw, deck.gns, deck.gnb, deck.gsw, deck.gbw));
+        rhof = fopen((outdir + "/rho.dat.mcs").c_str(), "w");
+        for (int k = 0; k < deck.gns; ++k) gf.push_back(fopen((outdir + "/g" + std::to_string(k) + ".dat.mcs").c_str(), "w"));
+    }
     std::vector<double> r(single ? cfg.N : 0), l(C), tot(C * 9), acc(C * 12), run(C * 12, 0.0);
     std::vector<uint64_t> cnt(C * 4);
     uint64_t sn = 0, sltp = (uint64_t) -1, samples = 0;
@@ -120,21 +132,63 @@ int main(int argc, char **argv) {
         return 0;
     };
 
+    auto print_rho = [&]() -> int {                                      // printRho, :1021-1038
+        if (!hist) return 0;
+        hbuf.resize(deck.rhonb);
+        JCK(jmm_take_histograms(h, hbuf.data(), nullptr));
+        const uint64_t ns = sn - slrho;
+        fprintf(rhof, "%lu", (unsigned long) sn);
+        for (uint64_t b = 0; b < deck.rhonb; ++b) fprintf(rhof, " %.8G", (double) (int) hbuf[b] / ns / deck.rbw);
+        fprintf(rhof, "\n");
+        fflush(rhof);
+        slrho = sn;
+        return 0;
+    };
+    auto print_g = [&]() -> int {                                        // printG, :1042-1064
+        if (!hist) return 0;
+        hbuf.resize((size_t) deck.gns * deck.gnb);
+        JCK(jmm_take_histograms(h, nullptr, hbuf.data()));
+        const uint64_t ns = sn - slg;
+        for (int k = 0; k < deck.gns; ++k) {
+            fprintf(gf[k], "%lu", (unsigned long) sn);
+            for (uint64_t b = 0; b < deck.gnb; ++b) fprintf(gf[k], " %.8G", (double) (int) hbuf[(size_t) k * deck.gnb + b] / ns / deck.gsw / deck.gbw);
+            fprintf(gf[k], "\n");
+            fflush(gf[k]);
+        }
+        slg = sn;
+        return 0;
+    };
+
     printf("Step: 0...\n");
     JCK(jmm_start(h));                                                   // src/Main.cpp:66-96
     if (print_coords()) return 2;
+    if (print_rho()) return 2;
     if (print_thermo()) return 2;
+    if (print_g()) return 2;
     const uint64_t tpi = deck.tpi ? deck.tpi : deck.numsteps, cpi = deck.cpi ? deck.cpi : deck.numsteps;
     while (sn < deck.numsteps) {                                         // src/Main.cpp:114-180, batched
         uint64_t n = deck.numsteps - sn;
         if (tpi) n = std::min(n, tpi - sn % tpi);
         if (single && cpi) n = std::min(n, cpi - sn % cpi);
+        if (hist && deck.rhopi) n = std::min(n, deck.rhopi - sn % deck.rhopi);
+        if (hist && deck.gpi) n = std::min(n, deck.gpi - sn % deck.gpi);
+        const bool relax_on = lockstep && cfg.relax > 0 && cfg.ensemble == JMM_ENS_NPT;
+        if (lockstep && cfg.mdai) n = std::min(n, cfg.mdai - sn % cfg.mdai);
+        if (lockstep && cfg.mvai) n = std::min(n, cfg.mvai - sn % cfg.mvai);
+        if (relax_on && sn < 1000000) n = std::min<uint64_t>(n, 10000 - sn % 10000);
         JCK(jmm_step(h, n, nullptr, 0, nullptr));
         const uint64_t before = sn;
         sn += n;
         if (sn / 10000 != before / 10000) printf("Step: %lu...\n", (unsigned long) (sn / 10000 * 10000));
         if (single && cpi && sn % cpi == 0 && print_coords()) return 2;
         if (tpi && sn % tpi == 0 && print_thermo()) return 2;
+        if (hist && deck.rhopi && sn % deck.rhopi == 0 && print_rho()) return 2;
+        if (lockstep) {                                                  // src/Main.cpp:145-165
+            const bool dis = cfg.mdai && sn % cfg.mdai == 0, vol = cfg.mvai && sn % cfg.mvai == 0;
+            if (dis || vol) JCK(jmm_adjust_step_sizes(h, dis, vol));
+        }
+        if (hist && deck.gpi && sn % deck.gpi == 0 && print_g()) return 2;
+        if (relax_on && sn % 10000 == 0 && sn < 1000000) JCK(jmm_relax_volume(h));   // src/Main.cpp:173-176
         fflush(stdout);
     }
     JCK(jmm_get_state(h, nullptr, l.data(), tot.data(), acc.data(), cnt.data()));
@@ -163,6 +217,8 @@ int main(int argc, char **argv) {
            (unsigned long) jmm_kernel_launches(h));
     fclose(tf);
     if (cf) fclose(cf);
+    if (rhof) fclose(rhof);
+    for (FILE *f : gf) if (f) fclose(f);
     jmm_destroy(h);
     return 0;
 }

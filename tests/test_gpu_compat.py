@@ -87,6 +87,16 @@ def test_batch_driver_lockstep_files_identical(gold, tmp_path, name):
     assert f"{c[0]}/{c[1]}          {c[2]}/{c[3]}" in out.stdout
 
 
+@pytest.mark.parametrize("name", ["smalltest_hist"])
+def test_batch_driver_lockstep_histogram_files(gold, tmp_path, name):
+    g = gold(name)
+    (tmp_path / "INPUT").write_text(g["deck_text"])
+    out = subprocess.run([str(RUN), "INPUT", "--lockstep"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    for f in ["rho.dat.mcs", "thermo.dat.mcs", "config.dat.mcs"] + sorted(p.name for p in g["dir"].glob("g*.dat.mcs")):
+        assert (tmp_path / f).read_bytes() == (g["dir"] / f).read_bytes(), f
+
+
 def test_batch_driver_state_point_sweep(gold, tmp_path):
     """A P x T grid in one process (what scripts/RunJobs.bash does with one LSF job per point)."""
     deck = gold("smalltest_2000")["deck_text"].replace("NUMSTEPS   2000", "NUMSTEPS   4000")
