@@ -365,6 +365,8 @@ def extra_arm(args) -> None:
         g = np.linspace(0.1, 1.0, 256)
         ids = rank * C + np.arange(C)
         h.set_state(P=g[(ids // 256) % 256], T=g[ids % 256])
+        if args.hist:      # scripts/RunJobs.bash:46-54 histogram geometry: RBW 0.1 x 1000, GSW 200 x 10, GBW 0.1 x 1000
+            h.enable_histograms(1000, 0.1, 10, 1000, 200.0, 0.1)
     h.start()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
@@ -409,7 +411,7 @@ def extra_arm(args) -> None:
         tf = per_gpu * w["flop"] / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": args.arith,
+                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": args.arith, "histograms": bool(args.hist),
                                                 "l2": "flushed between timed iterations (256 MiB fill)"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -435,7 +437,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
-    ap.add_argument("--arith", default="reference", choices=["reference", "fast"], help="c4 only: JMM_ARITH_*")
+    ap.add_argument("--arith", default="reference", choices=["reference", "fast"], help="c3/c4/c5: JMM_ARITH_*")
+    ap.add_argument("--hist", action="store_true", help="c4 only: rho(x)/g(x) histograms with the RunJobs geometry")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -57,40 +57,53 @@ __device__ __forceinline__ uint64_t pair_index(uint64_t N, uint64_t i, uint64_t 
 // ugrho :1131-1149.  The reference adds the WHOLE histogram to the accumulator on every step (54 % of its run
 // time at N = 80); here a bin's accumulator is brought up to date only when the bin changes or is read:
 //   acc += value * (ugrho calls since the bin was last touched)        — the same integers, O(changed bins).
-// Layout: chain-major [chain][bin]; null pointers = histograms off.
+// Layout: chain-major [chain][bin], one 16-byte record per bin so that a bump is one sector read + one write;
+// null pointers = histograms off.
+struct __align__(16) HistBin {
+    int32_t val;        // current count                                   (rhol :180, gl :187)
+    uint32_t last;      // ugrho count (mod 2^32) at which acc was last brought up to date
+    long long acc;      // accumulated count since the last print          (rhoA :182, gA :189)
+};
+
 struct HistDev {
     uint64_t rhonb, gnb;
     int gns;
     double rbw, gsw, gbw;
-    int32_t *rhol, *gl;          // current counts                      (rhol :180, gl :187)
-    long long *rhoA, *gA;        // accumulated counts since last print (rhoA :182, gA :189)
-    uint64_t *rhoLast, *gLast;   // ugrho count at which the bin's accumulator was last updated
+    HistBin *rho;                // [nchains][rhonb]
+    HistBin *g;                  // [nchains][gns][gnb]
     uint64_t *ucount;            // [nchains] ugrho calls so far
 };
 
-__device__ __forceinline__ void hist_bump(int32_t *val, long long *acc, uint64_t *last, uint64_t idx, int delta, uint64_t u) {
-    acc[idx] += (long long) val[idx] * (long long) (u - last[idx]);
-    last[idx] = u;
-    val[idx] += delta;
+__device__ __forceinline__ void hist_bump(HistBin *bins, uint64_t idx, int delta, uint32_t u) {
+    HistBin b = bins[idx];
+    b.acc += (long long) b.val * (long long) (uint32_t) (u - b.last);
+    b.last = u;
+    b.val += delta;
+    bins[idx] = b;
 }
 
 // fgrho :1069-1127 for one chain (positions r, stride rs; rij table when TABLE)
 template <bool TABLE>
 __device__ __forceinline__ void hist_fgrho(const HistDev &H, uint64_t c, const double *r, size_t rs, const double *rij, size_t ts,
-                                           uint32_t N, uint64_t u) {
-    int32_t *rl = H.rhol + c * H.rhonb;
-    long long *ra = H.rhoA + c * H.rhonb;
-    uint64_t *rt = H.rhoLast + c * H.rhonb;
-    for (uint64_t b = 0; b < H.rhonb; ++b) { ra[b] += (long long) rl[b] * (long long) (u - rt[b]); rt[b] = u; rl[b] = 0; }
+                                           uint32_t N, uint64_t u64) {
+    const uint32_t u = (uint32_t) u64;
+    HistBin *rb = H.rho + c * H.rhonb;
+    for (uint64_t b = 0; b < H.rhonb; ++b) {
+        HistBin x = rb[b];
+        x.acc += (long long) x.val * (long long) (uint32_t) (u - x.last); x.last = u; x.val = 0;
+        rb[b] = x;
+    }
     for (uint32_t i = 0; i < N; ++i) {
-        const long long rb = (long long) floor(r[i * rs] / H.rbw + (double) H.rhonb / 2.0);
-        if (rb >= 0 && rb < (long long) H.rhonb) rl[rb]++;
+        const long long k = (long long) floor(r[i * rs] / H.rbw + (double) H.rhonb / 2.0);
+        if (k >= 0 && k < (long long) H.rhonb) rb[k].val++;
     }
     const uint64_t ng = (uint64_t) H.gns * H.gnb;
-    int32_t *gl = H.gl + c * ng;
-    long long *ga = H.gA + c * ng;
-    uint64_t *gt = H.gLast + c * ng;
-    for (uint64_t b = 0; b < ng; ++b) { ga[b] += (long long) gl[b] * (long long) (u - gt[b]); gt[b] = u; gl[b] = 0; }
+    HistBin *gb_ = H.g + c * ng;
+    for (uint64_t b = 0; b < ng; ++b) {
+        HistBin x = gb_[b];
+        x.acc += (long long) x.val * (long long) (uint32_t) (u - x.last); x.last = u; x.val = 0;
+        gb_[b] = x;
+    }
     for (uint32_t i = 0; i + 1 < N; ++i)
         for (uint32_t j = i + 1; j < N; ++j) {
             const long long gs1 = (long long) floor(r[i * rs] / H.gsw + H.gns / 2.0);
@@ -98,20 +111,25 @@ __device__ __forceinline__ void hist_fgrho(const HistDev &H, uint64_t c, const d
             const double d = TABLE ? rij[pair_index(N, i, j) * ts] : r[j * rs] - r[i * rs];
             const long long gb = (long long) floor(d / H.gbw);
             if (gb >= 0 && gb < (long long) H.gnb) {
-                if (gs1 >= 0 && gs1 < H.gns) gl[gs1 * H.gnb + gb]++;
-                if (gs2 >= 0 && gs2 < H.gns) gl[gs2 * H.gnb + gb]++;
+                if (gs1 >= 0 && gs1 < H.gns) gb_[gs1 * H.gnb + gb].val++;
+                if (gs2 >= 0 && gs2 < H.gns) gb_[gs2 * H.gnb + gb].val++;
             }
         }
 }
 
-// qagrho :2297-2384 after an accepted displacement of particle nm by md (old position re-derived as r[nm]-md)
+// qagrho :2297-2384 after an accepted displacement of particle nm by md (old position re-derived as r[nm]-md).
+// A decrement and an increment of the SAME bin cancel (the reference does both); they are skipped together.
 __device__ __forceinline__ void hist_qagrho(const HistDev &H, uint64_t c, const double *r, size_t rs, uint32_t N, uint32_t nm,
-                                            double md, uint64_t u) {
+                                            double md, uint64_t u64) {
+    const uint32_t u = (uint32_t) u64;
     const double rn = r[nm * rs];
     const long long rbn1 = (long long) floor((rn - md) / H.rbw + (double) H.rhonb / 2.0);
     const long long rbn2 = (long long) floor(rn / H.rbw + (double) H.rhonb / 2.0);
-    if (rbn1 >= 0 && rbn1 < (long long) H.rhonb) hist_bump(H.rhol, H.rhoA, H.rhoLast, c * H.rhonb + rbn1, -1, u);
-    if (rbn2 >= 0 && rbn2 < (long long) H.rhonb) hist_bump(H.rhol, H.rhoA, H.rhoLast, c * H.rhonb + rbn2, +1, u);
+    const bool r1 = rbn1 >= 0 && rbn1 < (long long) H.rhonb, r2 = rbn2 >= 0 && rbn2 < (long long) H.rhonb;
+    if (!(r1 && r2 && rbn1 == rbn2)) {
+        if (r1) hist_bump(H.rho, c * H.rhonb + rbn1, -1, u);
+        if (r2) hist_bump(H.rho, c * H.rhonb + rbn2, +1, u);
+    }
     const long long gs11 = (long long) floor((rn - md) / H.gsw + H.gns / 2.0);
     const long long gs12 = (long long) floor(rn / H.gsw + H.gns / 2.0);
     const bool in11 = gs11 >= 0 && gs11 < H.gns, in12 = gs12 >= 0 && gs12 < H.gns;
@@ -124,10 +142,16 @@ __device__ __forceinline__ void hist_qagrho(const HistDev &H, uint64_t c, const 
         const long long gb1 = (long long) (unsigned long long) floor(fabs(rn - md - ri) / H.gbw);
         const long long gb2 = (long long) (unsigned long long) floor(fabs(rn - ri) / H.gbw);
         const bool b1 = gb1 >= 0 && gb1 < (long long) H.gnb, b2 = gb2 >= 0 && gb2 < (long long) H.gnb;
-        if (in11 && b1) hist_bump(H.gl, H.gA, H.gLast, base + gs11 * H.gnb + gb1, -1, u);
-        if (in12 && b2) hist_bump(H.gl, H.gA, H.gLast, base + gs12 * H.gnb + gb2, +1, u);
-        if (in2 && b1) hist_bump(H.gl, H.gA, H.gLast, base + gs2 * H.gnb + gb1, -1, u);
-        if (in2 && b2) hist_bump(H.gl, H.gA, H.gLast, base + gs2 * H.gnb + gb2, +1, u);
+        // moved particle's segment(s)
+        if (!(in11 && b1 && in12 && b2 && gs11 == gs12 && gb1 == gb2)) {
+            if (in11 && b1) hist_bump(H.g, base + gs11 * H.gnb + gb1, -1, u);
+            if (in12 && b2) hist_bump(H.g, base + gs12 * H.gnb + gb2, +1, u);
+        }
+        // the other particle's segment
+        if (in2 && !(b1 && b2 && gb1 == gb2)) {
+            if (b1) hist_bump(H.g, base + gs2 * H.gnb + gb1, -1, u);
+            if (b2) hist_bump(H.g, base + gs2 * H.gnb + gb2, +1, u);
+        }
     }
 }
 
@@ -650,23 +674,24 @@ __global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a, Hi
 }
 
 // histogram set-up (setupMCS :773-776: fgrho + one ugrho on the initial configuration) and read-out
-template <bool TABLE>
 __global__ void k_hist_init(ChainsDev S, HistDev H) {
     const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= S.nchains) return;
-    hist_fgrho<TABLE>(H, c, S.r + c, S.nchains, S.rij ? S.rij + c : nullptr, S.nchains, (uint32_t) S.N, 0);
+    // distances from the positions: setupMCS fills rij = r[j]-r[i] (:768) just before its fgrho, the same doubles
+    hist_fgrho<false>(H, c, S.r + c, S.nchains, nullptr, 0, (uint32_t) S.N, 0);
     H.ucount[c] = 1;
 }
 
 // bring every bin's accumulator up to date, copy it out, zero it (printRho :1021-1038 / printG :1042-1064)
-__global__ void k_hist_take(const int32_t *val, long long *acc, uint64_t *last, const uint64_t *ucount, uint64_t bins_per_chain,
-                            uint64_t nchains, long long *out) {
+__global__ void k_hist_take(HistBin *bins, const uint64_t *ucount, uint64_t bins_per_chain, uint64_t nchains, long long *out) {
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bins_per_chain * nchains) return;
-    const uint64_t u = ucount[t / bins_per_chain];
-    out[t] = acc[t] + (long long) val[t] * (long long) (u - last[t]);
-    acc[t] = 0;
-    last[t] = u;
+    const uint32_t u = (uint32_t) ucount[t / bins_per_chain];
+    HistBin b = bins[t];
+    out[t] = b.acc + (long long) b.val * (long long) (uint32_t) (u - b.last);
+    b.acc = 0;
+    b.last = u;
+    bins[t] = b;
 }
 
 // chain-major host layout <-> chain-fastest device layout

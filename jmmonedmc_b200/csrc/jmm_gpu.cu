@@ -654,13 +654,11 @@ extern "C" jmm_status jmm_enable_histograms(jmm_handle *h, uint64_t rhonb, doubl
     const uint64_t C = h->S.nchains, ng = (uint64_t) gns * gnb;
     HistDev H{};
     H.rhonb = rhonb; H.gnb = gnb; H.gns = gns; H.rbw = rbw; H.gsw = gsw; H.gbw = gbw;
-    CK(dalloc(h, &H.rhol, C * rhonb)); CK(dalloc(h, &H.rhoA, C * rhonb)); CK(dalloc(h, &H.rhoLast, C * rhonb));
-    CK(dalloc(h, &H.gl, C * ng)); CK(dalloc(h, &H.gA, C * ng)); CK(dalloc(h, &H.gLast, C * ng));
+    CK(dalloc(h, &H.rho, C * rhonb)); CK(dalloc(h, &H.g, C * ng));
     CK(dalloc(h, &H.ucount, C));
     h->H = H;
     h->coop_g = 0; h->bond = 0;                    // the per-thread kernels carry the histogram hooks
-    // distances from the positions: setupMCS fills rij = r[j]-r[i] (:768) just before its fgrho, the same doubles
-    k_hist_init<false><<<nblk(C, 32), 32, 0, h->stream>>>(h->S, h->H);
+    k_hist_init<<<nblk(C, 32), 32, 0, h->stream>>>(h->S, h->H);
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -671,20 +669,20 @@ extern "C" jmm_status jmm_take_histograms(jmm_handle *h, int64_t *rhoA, int64_t 
     if (!h || !h->H.ucount) return fail(JMM_ERR_INVALID, "histograms are not enabled on this handle");
     CK(cudaSetDevice(h->cfg.device));
     const uint64_t C = h->S.nchains;
-    auto take = [&](const int32_t *val, long long *acc, uint64_t *last, uint64_t bins, int64_t *out) -> jmm_status {
+    auto take = [&](HistBin *b, uint64_t bins, int64_t *out) -> jmm_status {
         if (!out || bins == 0) return JMM_OK;
         jmm_status st = ensure_stage(h, C * bins * sizeof(long long));
         if (st != JMM_OK) return st;
-        k_hist_take<<<nblk(C * bins, 256), 256, 0, h->stream>>>(val, acc, last, h->H.ucount, bins, C, (long long *) h->d_stage);
+        k_hist_take<<<nblk(C * bins, 256), 256, 0, h->stream>>>(b, h->H.ucount, bins, C, (long long *) h->d_stage);
         h->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, h->d_stage, C * bins * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return JMM_OK;
     };
-    jmm_status st = take(h->H.rhol, h->H.rhoA, h->H.rhoLast, h->H.rhonb, rhoA);
+    jmm_status st = take(h->H.rho, h->H.rhonb, rhoA);
     if (st != JMM_OK) return st;
-    return take(h->H.gl, h->H.gA, h->H.gLast, (uint64_t) h->H.gns * h->H.gnb, gA);
+    return take(h->H.g, (uint64_t) h->H.gns * h->H.gnb, gA);
 }
 
 // ------------------------------------------------------------------------------------------------
