@@ -278,6 +278,22 @@ def gpu_arm(args) -> None:
     nchains_total = int(rec.shape[0])
     disc = h.echeck_stats()[1]
 
+    # ---- the throughput-bound BASELINE.json configurations (C3, C4, C5), short runs, both arithmetic modes:
+    #      carried in the same JSON line as "other_workloads" so that one bench run shows every kernel family
+    others = {}
+    if not args.no_extras:
+        for wl in ("c3", "c4", "c5"):
+            for ar in ("fast", "reference"):
+                try:
+                    ln = measure_extra(wl, ar, False, 3, 3, rank, world, local)
+                    if ln:
+                        others[f"{wl}_{ar}"] = {"workload": ln["config"]["workload"], "arith": ar, "value": ln["value"], "unit": UNIT,
+                                                "ms_per_step": ln["ms_per_step"], "gpu_launches": ln["gpu_launches"],
+                                                "fp64_tflops": ln["roofline"]["achieved"], "fp64_frac": ln["roofline"]["frac"],
+                                                "flop_per_trial": ln["roofline"]["flop_per_trial"], "acceptance": ln["acceptance"]}
+                except Exception as e:                      # a secondary workload never fails the headline line
+                    others[f"{wl}_{ar}"] = {"error": str(e)[:200]}
+
     if rank == 0:
         peaks = {}
         try:
@@ -308,7 +324,7 @@ def gpu_arm(args) -> None:
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
-            "roofline": {"bound": "fp64", "kernel": "k_chains_step_coop<HARMONIC,G=16> (coop.cuh)",
+            "roofline": {"bound": "fp64", "kernel": "k_chains_step_bond (bond.cuh: HARMONIC NBN 1, 16 lanes per chain)",
                          "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None,
                          "peak_source": "DFMA microbenchmark in libjmmgpu (jmm_fp64_peak_tflops), measured in this run; "
@@ -323,6 +339,7 @@ def gpu_arm(args) -> None:
                                  "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
                                  "bytes_per_launch": C * BYTES_PER_CHAIN_PER_LAUNCH}},
             "cpu_baseline": cpu,
+            "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     h.close()
@@ -330,34 +347,30 @@ def gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
-def extra_arm(args) -> None:
-    """Secondary workloads (one GPU per rank, weak scaling): same JSON shape, no e2e/cpu legs beyond a note."""
+def measure_extra(workload: str, arith: str, hist: bool, steps: int, warmup: int, rank: int, world: int, local: int):
+    """One secondary workload on an initialised device/process group; returns the JSON line on rank 0 (None elsewhere)."""
     import numpy as np
     import torch
     import torch.distributed as dist
     import jmmonedmc_b200 as J
     from jmmonedmc_b200.capi import config
 
-    w = EXTRA[args.workload]
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device")
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    J.build()
+    w = dict(EXTRA[workload])
+    if os.environ.get("JMM_BENCH_CHAINS"):          # experiments only: a smaller/larger chain count than the named config
+        w["nchains"] = int(os.environ["JMM_BENCH_CHAINS"]); w["desc"] += f" [chains overridden: {w['nchains']}]"
+    if os.environ.get("JMM_BENCH_PER_STEP"):
+        w["per_step"] = int(os.environ["JMM_BENCH_PER_STEP"])
     pot = {"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT, "HARMONIC": J.POT_HARMONIC}[w["pot"]]
     C, N = w["nchains"], w["N"]
     if w["kind"] == "sweep":
         cfg = config(N=N, pot=pot, nbn=w["nbn"], cutoff=w["cutoff"], ensemble=J.ENS_NLT, L=1.12 * N, T=w["T"],
                      maxStep=w["maxStep"], seed=w["seed"], nchains=C, chain_id0=rank * C, mode=J.MODE_CHECKERBOARD, device=local,
-                     arith=J.ARITH_FAST if args.arith == "fast" else J.ARITH_REFERENCE)
+                     arith=J.ARITH_FAST if arith == "fast" else J.ARITH_REFERENCE)
     else:
         cfg = config(N=N, pot=pot, nbn=w["nbn"], cutoff=w["cutoff"], ensemble=J.ENS_NPT, relax=w["relax"], P=0.5, T=0.5,
                      maxStep=w["maxStep"], maxdl=w["maxdl"], eci=w["eci"], mdai=w["mdai"], mvai=w["mvai"], seed=w["seed"],
                      nchains=C, chain_id0=rank * C, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE,
-                     device=local, arith=J.ARITH_FAST if args.arith == "fast" else J.ARITH_REFERENCE)
+                     device=local, arith=J.ARITH_FAST if arith == "fast" else J.ARITH_REFERENCE)
     h = J.Handle(cfg)
     stream = torch.cuda.current_stream()
     h.set_stream(stream.cuda_stream)
@@ -365,7 +378,7 @@ def extra_arm(args) -> None:
         g = np.linspace(0.1, 1.0, 256)
         ids = rank * C + np.arange(C)
         h.set_state(P=g[(ids // 256) % 256], T=g[ids % 256])
-        if args.hist:      # scripts/RunJobs.bash:46-54 histogram geometry: RBW 0.1 x 1000, GSW 200 x 10, GBW 0.1 x 1000
+        if hist:      # scripts/RunJobs.bash:46-54 histogram geometry: RBW 0.1 x 1000, GSW 200 x 10, GBW 0.1 x 1000
             h.enable_histograms(1000, 0.1, 10, 1000, 200.0, 0.1)
     h.start()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
@@ -373,7 +386,7 @@ def extra_arm(args) -> None:
     def one():
         return h.sweep(w["per_step"]) if w["kind"] == "sweep" else (h.step(w["per_step"]) or C * w["per_step"])
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         one()
     torch.cuda.synchronize()
     if world > 1:
@@ -381,7 +394,7 @@ def extra_arm(args) -> None:
     sampler = ClockSampler(local); sampler.start()
     l0 = h.kernel_launches
     ev, trials = [], 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.fill_(1.0)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream); n = one(); b.record(stream)
@@ -399,6 +412,7 @@ def extra_arm(args) -> None:
     launches = h.kernel_launches - l0
     one(); k_ms = h.last_kernel_ms
     st = h.get_state(r=False)
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -409,9 +423,9 @@ def extra_arm(args) -> None:
         value = trials / (ms * 1e-3)
         per_gpu = value / world
         tf = per_gpu * w["flop"] / 1e12
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": args.arith, "histograms": bool(args.hist),
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": arith, "histograms": bool(hist),
                                                 "l2": "flushed between timed iterations (256 MiB fill)"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -424,8 +438,28 @@ def extra_arm(args) -> None:
                                  "frac": per_gpu * w["bytes_per_trial"] / 1e9 / float(peaks.get("hbm_gbs", 6650.0))}},
                 "acceptance": float(st["counters"][:, 0].sum() / max(1, st["counters"][:, :2].sum())),
                 "e2e": None, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
     h.close()
+    del flush
+    return line
+
+
+def extra_arm(args) -> None:
+    """Secondary workloads (one GPU per rank, weak scaling): same JSON shape, no e2e/cpu legs beyond a note."""
+    import torch
+    import torch.distributed as dist
+    import jmmonedmc_b200 as J
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    J.build()
+    line = measure_extra(args.workload, args.arith, args.hist, args.steps, args.warmup, rank, world, local)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -439,6 +473,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--arith", default="reference", choices=["reference", "fast"], help="c3/c4/c5: JMM_ARITH_*")
     ap.add_argument("--hist", action="store_true", help="c4 only: rho(x)/g(x) histograms with the RunJobs geometry")
+    ap.add_argument("--no-extras", action="store_true", help="c2: skip the short C3/C4/C5 runs reported as other_workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -23,7 +23,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if force or _stale():
         env = dict(os.environ)
         env.setdefault("NVCC", "/usr/local/cuda/bin/nvcc" if Path("/usr/local/cuda/bin/nvcc").exists() else "nvcc")
-        args = ["make", "-C", str(CSRC), "all"] + (["-B"] if force else [])
+        args = ["make", "-j", "4", "-C", str(CSRC), "all"] + (["-B"] if force else [])
         r = subprocess.run(args, env=env, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             print(r.stdout)

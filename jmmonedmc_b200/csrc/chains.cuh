@@ -55,14 +55,18 @@ __device__ __forceinline__ uint64_t pair_index(uint64_t N, uint64_t i, uint64_t 
 
 // Density rho(x) and two-particle density g(x) histograms: fgrho :1069-1127, qagrho :2297-2384,
 // ugrho :1131-1149.  The reference adds the WHOLE histogram to the accumulator on every step (54 % of its run
-// time at N = 80); here a bin's accumulator is brought up to date only when the bin changes or is read:
-//   acc += value * (ugrho calls since the bin was last touched)        — the same integers, O(changed bins).
-// Layout: chain-major [chain][bin], one 16-byte record per bin so that a bump is one sector read + one write;
+// time at N = 80).  Here a bin keeps its current count `val` and  W = sum over its changes of delta * u,  u = the
+// number of ugrho calls made before the change.  A change of delta at u is seen by the ugrho calls u+1 .. U, so
+//     accumulated count after U calls  =  sum_k delta_k (U - u_k)  =  U * val - W          (the same integers),
+// and a change is two commutative additions with no result: two fire-and-forget RED instructions, no load, no
+// dependent latency (the earlier read-modify-write form ran C4 at 2.7e7 trials/s).  A read-out
+// returns U*val - W and rebases W := U*val.  All arithmetic is modulo 2^64, exact while the true sum fits int64.
+// Layout: chain-major [chain][bin], one 16-byte record per bin (one 32-byte sector holds two bins);
 // null pointers = histograms off.
 struct __align__(16) HistBin {
-    int32_t val;        // current count                                   (rhol :180, gl :187)
-    uint32_t last;      // ugrho count (mod 2^32) at which acc was last brought up to date
-    long long acc;      // accumulated count since the last print          (rhoA :182, gA :189)
+    unsigned long long W;  // sum of delta * u over the changes since the last read-out (mod 2^64)
+    int32_t val;           // current count                                   (rhol :180, gl :187)
+    int32_t pad;
 };
 
 struct HistDev {
@@ -74,36 +78,33 @@ struct HistDev {
     uint64_t *ucount;            // [nchains] ugrho calls so far
 };
 
-__device__ __forceinline__ void hist_bump(HistBin *bins, uint64_t idx, int delta, uint32_t u) {
-    HistBin b = bins[idx];
-    b.acc += (long long) b.val * (long long) (uint32_t) (u - b.last);
-    b.last = u;
-    b.val += delta;
-    bins[idx] = b;
+__device__ __forceinline__ void hist_bump(HistBin *bins, uint64_t idx, int delta, uint64_t u) {
+    atomicAdd(&bins[idx].val, delta);                                                   // RED.ADD (result unused)
+    atomicAdd(&bins[idx].W, (unsigned long long) ((long long) delta * (long long) u));  // RED.ADD.64
+}
+
+// set every bin of a histogram to zero at ugrho count u: only the non-zero bins are touched
+__device__ __forceinline__ void hist_clear(HistBin *bins, uint64_t n, uint64_t u) {
+    for (uint64_t b = 0; b < n; ++b) {
+        const int v = __ldcg(&bins[b].val);              // L2: the REDs above never update L1
+        if (v != 0) hist_bump(bins, b, -v, u);
+    }
 }
 
 // fgrho :1069-1127 for one chain (positions r, stride rs; rij table when TABLE)
 template <bool TABLE>
 __device__ __forceinline__ void hist_fgrho(const HistDev &H, uint64_t c, const double *r, size_t rs, const double *rij, size_t ts,
-                                           uint32_t N, uint64_t u64) {
-    const uint32_t u = (uint32_t) u64;
+                                           uint32_t N, uint64_t u) {
+    __threadfence();                                     // this thread's earlier REDs are performed before the reads below
     HistBin *rb = H.rho + c * H.rhonb;
-    for (uint64_t b = 0; b < H.rhonb; ++b) {
-        HistBin x = rb[b];
-        x.acc += (long long) x.val * (long long) (uint32_t) (u - x.last); x.last = u; x.val = 0;
-        rb[b] = x;
-    }
+    hist_clear(rb, H.rhonb, u);
     for (uint32_t i = 0; i < N; ++i) {
         const long long k = (long long) floor(r[i * rs] / H.rbw + (double) H.rhonb / 2.0);
-        if (k >= 0 && k < (long long) H.rhonb) rb[k].val++;
+        if (k >= 0 && k < (long long) H.rhonb) hist_bump(rb, (uint64_t) k, +1, u);
     }
     const uint64_t ng = (uint64_t) H.gns * H.gnb;
     HistBin *gb_ = H.g + c * ng;
-    for (uint64_t b = 0; b < ng; ++b) {
-        HistBin x = gb_[b];
-        x.acc += (long long) x.val * (long long) (uint32_t) (u - x.last); x.last = u; x.val = 0;
-        gb_[b] = x;
-    }
+    hist_clear(gb_, ng, u);
     for (uint32_t i = 0; i + 1 < N; ++i)
         for (uint32_t j = i + 1; j < N; ++j) {
             const long long gs1 = (long long) floor(r[i * rs] / H.gsw + H.gns / 2.0);
@@ -111,8 +112,8 @@ __device__ __forceinline__ void hist_fgrho(const HistDev &H, uint64_t c, const d
             const double d = TABLE ? rij[pair_index(N, i, j) * ts] : r[j * rs] - r[i * rs];
             const long long gb = (long long) floor(d / H.gbw);
             if (gb >= 0 && gb < (long long) H.gnb) {
-                if (gs1 >= 0 && gs1 < H.gns) gb_[gs1 * H.gnb + gb].val++;
-                if (gs2 >= 0 && gs2 < H.gns) gb_[gs2 * H.gnb + gb].val++;
+                if (gs1 >= 0 && gs1 < H.gns) hist_bump(gb_, (uint64_t) (gs1 * H.gnb + gb), +1, u);
+                if (gs2 >= 0 && gs2 < H.gns) hist_bump(gb_, (uint64_t) (gs2 * H.gnb + gb), +1, u);
             }
         }
 }
@@ -120,8 +121,7 @@ __device__ __forceinline__ void hist_fgrho(const HistDev &H, uint64_t c, const d
 // qagrho :2297-2384 after an accepted displacement of particle nm by md (old position re-derived as r[nm]-md).
 // A decrement and an increment of the SAME bin cancel (the reference does both); they are skipped together.
 __device__ __forceinline__ void hist_qagrho(const HistDev &H, uint64_t c, const double *r, size_t rs, uint32_t N, uint32_t nm,
-                                            double md, uint64_t u64) {
-    const uint32_t u = (uint32_t) u64;
+                                            double md, uint64_t u) {
     const double rn = r[nm * rs];
     const long long rbn1 = (long long) floor((rn - md) / H.rbw + (double) H.rhonb / 2.0);
     const long long rbn2 = (long long) floor(rn / H.rbw + (double) H.rhonb / 2.0);
@@ -170,7 +170,17 @@ struct Chain {
     double acc[kNAcc];
     uint64_t cnt[kNCnt];
     uint64_t vAErr, echecks, discrepancies;
+    // lanes sharing this chain (prod.cuh, G > 1): every lane holds the same scalars; position updates that read what
+    // they overwrite are split over the lanes (scale_positions).  One chain per thread: sub = 0, nsub = 1.
+    uint32_t sub, nsub, gmask;
 };
+
+// r *= f for the whole chain (qavLJ :1692, fav :2264-2266, moveVolume :2847-2849)
+template <int POT>
+__device__ __forceinline__ void scale_positions(Chain<POT> &ch, double f) {
+    for (uint32_t i = ch.sub; i < ch.N; i += ch.nsub) ch.r[i * ch.rs] = ch.r[i * ch.rs] * f;
+    if (ch.nsub > 1) __syncwarp(ch.gmask);
+}
 
 template <int POT>
 __device__ __forceinline__ uint32_t row_end(const Chain<POT> &ch, uint32_t i) {       // last j of row i
@@ -272,7 +282,7 @@ __device__ __forceinline__ void update_thermo(Chain<POT> &ch) {
 template <int POT, bool TABLE>
 __device__ __forceinline__ void move_volume(Chain<POT> &ch, double lnew) {
     const double lRat1 = lnew / ch.l;
-    for (uint32_t i = 0; i < ch.N; ++i) ch.r[i * ch.rs] = ch.r[i * ch.rs] * lRat1;
+    scale_positions(ch, lRat1);
     ch.l = lnew;
     recompute_into_state<POT, TABLE>(ch);
 }
@@ -436,7 +446,7 @@ __device__ __forceinline__ uint8_t volume_trial_scaling(Chain<POT> &ch, double r
     ch.tot[5] = lRat7 * ch.tot[5];
     ch.tot[3] = lRat13 * ch.tot[3];
     ch.tot[1] = (double) ch.N * ch.T / ch.l + ch.tot[3] - ch.tot[5];                 // :1686
-    for (uint32_t i = 0; i < ch.N; ++i) ch.r[i * ch.rs] = lRat1 * ch.r[i * ch.rs];   // :1692
+    scale_positions(ch, lRat1);                                                      // :1692
     if (TABLE) {
         const uint64_t np = (uint64_t) ch.N * (ch.N - 1) / 2;
         for (uint64_t q = 0; q < np; ++q) ch.rij[q * ch.ts] = lRat1 * ch.rij[q * ch.ts];   // :1699
@@ -461,7 +471,7 @@ __device__ __forceinline__ uint8_t volume_trial_full(Chain<POT> &ch, double rn, 
     ch.l = ch.l + dl;
 #pragma unroll
     for (int k = 0; k < NC; ++k) ch.tot[k] = t[k];
-    for (uint32_t i = 0; i < ch.N; ++i) ch.r[i * ch.rs] = ch.r[i * ch.rs] * lRat1;
+    scale_positions(ch, lRat1);
     table_from_positions<POT, TABLE>(ch);
     return kLogVolume | kLogAccepted;
 }
@@ -524,6 +534,7 @@ __device__ __forceinline__ void load_chain(Chain<POT> &ch, const ChainsDev &S, u
                                            uint32_t smem_stride) {
     constexpr int NC = PotTraits<POT>::NC;
     ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff;
+    ch.sub = 0; ch.nsub = 1; ch.gmask = 0;
     ch.l = ld_state<CG>(S.l + c); ch.P = ld_state<CG>(S.P + c); ch.T = ld_state<CG>(S.T + c);
     ch.maxStep = ld_state<CG>(S.maxStep + c); ch.maxdl = ld_state<CG>(S.maxdl + c);
     ch.invT = 1.0 / ch.T;
@@ -599,6 +610,7 @@ __global__ void k_chains_totals_exact(ChainsDev S, double *out /*[9][nchains]*/)
     if (c >= S.nchains) return;
     Chain<POT> ch;
     ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff; ch.l = S.l[c];
+    ch.sub = 0; ch.nsub = 1; ch.gmask = 0;
     ch.r = S.r + c; ch.rs = S.nchains;
     constexpr int NC = PotTraits<POT>::NC;
     double t[NC];
@@ -674,7 +686,7 @@ __global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a, Hi
 }
 
 // histogram set-up (setupMCS :773-776: fgrho + one ugrho on the initial configuration) and read-out
-__global__ void k_hist_init(ChainsDev S, HistDev H) {
+static __global__ void k_hist_init(ChainsDev S, HistDev H) {
     const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= S.nchains) return;
     // distances from the positions: setupMCS fills rij = r[j]-r[i] (:768) just before its fgrho, the same doubles
@@ -682,34 +694,35 @@ __global__ void k_hist_init(ChainsDev S, HistDev H) {
     H.ucount[c] = 1;
 }
 
-// bring every bin's accumulator up to date, copy it out, zero it (printRho :1021-1038 / printG :1042-1064)
-__global__ void k_hist_take(HistBin *bins, const uint64_t *ucount, uint64_t bins_per_chain, uint64_t nchains, long long *out) {
+// read-out: accumulated counts since the last read-out = U*val - W, then rebase W := U*val
+// (printRho :1021-1038 / printG :1042-1064)
+static __global__ void k_hist_take(HistBin *bins, const uint64_t *ucount, uint64_t bins_per_chain, uint64_t nchains, long long *out) {
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bins_per_chain * nchains) return;
-    const uint32_t u = (uint32_t) ucount[t / bins_per_chain];
+    const unsigned long long U = ucount[t / bins_per_chain];
     HistBin b = bins[t];
-    out[t] = b.acc + (long long) b.val * (long long) (uint32_t) (u - b.last);
-    b.acc = 0;
-    b.last = u;
+    const unsigned long long uv = U * (unsigned long long) (long long) b.val;
+    out[t] = (long long) (uv - b.W);
+    b.W = uv;
     bins[t] = b;
 }
 
 // chain-major host layout <-> chain-fastest device layout
-__global__ void k_transpose_in(const double *__restrict__ src /*[nchains][n]*/, double *__restrict__ dst /*[n][nchains]*/,
+static __global__ void k_transpose_in(const double *__restrict__ src /*[nchains][n]*/, double *__restrict__ dst /*[n][nchains]*/,
                                uint64_t nchains, uint64_t n) {
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchains * n) return;
     const uint64_t i = t / nchains, c = t % nchains;
     dst[t] = src[c * n + i];
 }
-__global__ void k_transpose_out(const double *__restrict__ src /*[n][nchains]*/, double *__restrict__ dst /*[nchains][n]*/,
+static __global__ void k_transpose_out(const double *__restrict__ src /*[n][nchains]*/, double *__restrict__ dst /*[nchains][n]*/,
                                 uint64_t nchains, uint64_t n) {
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchains * n) return;
     const uint64_t c = t / n, i = t % n;
     dst[t] = src[i * nchains + c];
 }
-__global__ void k_lattice(double *r /*[N][nchains]*/, const double *l, uint64_t nchains, uint64_t N) {   // :561
+static __global__ void k_lattice(double *r /*[N][nchains]*/, const double *l, uint64_t nchains, uint64_t N) {   // :561
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchains * N) return;
     const uint64_t i = t / nchains, c = t % nchains;

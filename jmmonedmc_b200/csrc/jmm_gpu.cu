@@ -12,12 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/jmm_gpu.h"
-#include "chains.cuh"
-#include "sweep.cuh"
-#include "coop.cuh"
-#include "prod.cuh"
-#include "bond.cuh"
+#include "handle.h"
 
 using namespace jmm;
 
@@ -33,47 +28,6 @@ static jmm_status fail(jmm_status code, const std::string &msg) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(JMM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
-
-struct jmm_handle {
-    jmm_config cfg{};
-    ChainsDev S{};
-    HistDev H{};                    // null pointers = histograms off
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
-    uint64_t sn = 0, launches = 0;
-    // many-chain launch shape
-    int block = 32, pos_in_smem = 1;
-    size_t smem = 0;
-    int bond = 0;                   // bond.cuh serves this handle (HARMONIC, NBN 1, N <= 17, no RELAX)
-    int coop_g = 0;                 // lanes per chain of the cooperative kernel (0 = one chain per thread)
-    int coop_npad = 0;
-    size_t coop_smem = 0;
-    // recorded stream
-    uint32_t *d_stream = nullptr;
-    uint64_t stream_cap = 0;
-    uint64_t *d_cursor = nullptr;
-    int *d_err = nullptr;
-    uint64_t cursor = 0;
-    // time-sliced production launches: work counter + per-tile progress words
-    unsigned int *d_work = nullptr;
-    size_t work_words = 0;
-    // scratch
-    double *d_stage = nullptr;
-    size_t stage_bytes = 0;
-    uint8_t *d_log = nullptr;
-    size_t log_bytes = 0;
-    double *d_partial = nullptr;
-    size_t partial_bytes = 0;
-    // checkerboard mode: chain-major positions, double-buffered
-    double *cb_r[2] = {nullptr, nullptr};
-    int cb_cur = 0;
-    double *cb_tot = nullptr, *cb_acc = nullptr;
-    unsigned long long *cb_counts = nullptr;
-    uint64_t halfsweeps = 0;
-    std::vector<void *> allocs;
-};
 
 template <class T>
 static cudaError_t dalloc(jmm_handle *h, T **p, size_t n) {
@@ -95,7 +49,6 @@ static jmm_status ensure_stage(jmm_handle *h, size_t bytes) {
 }
 
 static bool is_cb(const jmm_handle *h) { return h->cfg.mode == JMM_MODE_CHECKERBOARD; }
-static unsigned nblk(uint64_t n, unsigned b) { return (unsigned) ((n + b - 1) / b); }
 
 static void tick(jmm_handle *h) { if (!h->timed) { cudaEventRecord(h->ev0, h->stream); h->timed = true; } }
 static void tock(jmm_handle *h) { cudaEventRecord(h->ev1, h->stream); }
@@ -337,7 +290,7 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
             if (const char *e = getenv("JMM_COOP_G")) g = atoi(e);
             if (g == 8 || g == 16 || g == 32) {
                 const int nc = (cfg->pot == JMM_POT_HARMONIC) ? 2 : 9;
-                const int scratch = kCoopChunk * 2 * nc;
+                const int scratch = kCoopScratchRows * 2 * nc;
                 int npad = (int) N;
                 npad += (17 - ((npad + scratch) % 16)) % 16;          // rows of different groups hit different banks
                 const size_t bytes = (size_t) (128 / g) * (npad + scratch) * sizeof(double);
@@ -383,93 +336,12 @@ static cudaError_t launch_step_rng(jmm_handle *h, const StepArgs &a) {
     return cudaGetLastError();
 }
 
-template <int POT, int G>
-static cudaError_t launch_step_coop_g(jmm_handle *h, const StepArgs &a) {
-    auto kern = a.accept_log ? k_chains_step_coop<POT, G, true> : k_chains_step_coop<POT, G, false>;
-    if (h->coop_smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->coop_smem);
-        if (e != cudaSuccess) return e;
-    }
-    const unsigned per_block = 128 / G;
-    kern<<<nblk(h->S.nchains, per_block), 128, h->coop_smem, h->stream>>>(h->S, a, h->coop_npad);
-    h->launches++;
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
-    int npad = (int) h->S.N;
-    npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
-    const bool inf = std::isinf(h->S.cutoff);
-    auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
-                             : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
-    const unsigned per_block = 128 / kB2G;
-    kern<<<nblk(h->S.nchains, per_block), 128, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
-    h->launches++;
-    return cudaGetLastError();
-}
-
-template <int POT>
-static cudaError_t launch_step_coop(jmm_handle *h, const StepArgs &a) {
-    if constexpr (POT == kPotHarmonic) {
-        if (h->bond) return launch_step_bond(h, a);
-    }
-    switch (h->coop_g) {
-        case 8: return launch_step_coop_g<POT, 8>(h, a);
-        case 16: return launch_step_coop_g<POT, 16>(h, a);
-        default: return launch_step_coop_g<POT, 32>(h, a);
-    }
-}
-
-template <int POT, int ARITH>
-static cudaError_t launch_step_prod(jmm_handle *h, const StepArgs &a) {
-    auto kern = a.accept_log ? k_chains_step_prod<POT, ARITH, true> : k_chains_step_prod<POT, ARITH, false>;
-    auto sliced = a.accept_log ? k_chains_step_prod_sliced<POT, ARITH, true> : k_chains_step_prod_sliced<POT, ARITH, false>;
-    cudaError_t e;
-    if (h->smem > 48 * 1024) {
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(sliced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem)) != cudaSuccess) return e;
-    }
-    const unsigned ntiles = nblk(h->S.nchains, kTile);
-    // how many CTAs of the sliced kernel are co-resident on this device
-    int per_sm = 0, nsm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sliced, kTile, h->smem)) != cudaSuccess) return e;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    const unsigned slots = (unsigned) std::max(1, per_sm * nsm);
-    const double waves = (double) ntiles / slots;
-    const bool slice = !h->H.ucount &&             // histogram bins are read through L1: keep a chain on one SM per launch
-                       (getenv("JMM_FORCE_SLICE") ||
-                        (!getenv("JMM_NO_SLICE") && ntiles > slots && (waves - floor(waves)) < 0.85 && a.nsteps >= 16));
-    if (!slice) {
-        kern<<<ntiles, kTile, h->smem, h->stream>>>(h->S, a, h->H);
-        h->launches++;
-        return cudaGetLastError();
-    }
-    // ~12+ chunks per launch bounds the imbalance to one chunk in twelve; at least 8 steps per chunk
-    uint32_t chunk = (uint32_t) std::max<uint64_t>(8, (a.nsteps + 11) / 12);
-    if (const char *ev = getenv("JMM_SLICE_CHUNK")) chunk = (uint32_t) std::max(1, atoi(ev));
-    const uint32_t nchunks = (uint32_t) ((a.nsteps + chunk - 1) / chunk);
-    if (h->work_words < (size_t) ntiles + 1) {
-        if (h->d_work) cudaFree(h->d_work);
-        h->d_work = nullptr; h->work_words = 0;
-        if ((e = cudaMalloc((void **) &h->d_work, ((size_t) ntiles + 1) * sizeof(unsigned int))) != cudaSuccess) return e;
-        h->work_words = (size_t) ntiles + 1;
-    }
-    if ((e = cudaMemsetAsync(h->d_work, 0, ((size_t) ntiles + 1) * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
-    sliced<<<std::min(slots, ntiles * nchunks), kTile, h->smem, h->stream>>>(h->S, a, h->H, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
-    h->launches++;
-    return cudaGetLastError();
-}
-
 template <int POT, bool TABLE>
 static cudaError_t launch_step_table(jmm_handle *h, const StepArgs &a) {
     if constexpr (!TABLE) {
-        if (h->coop_g) return launch_step_coop<POT>(h, a);
-        if (h->cfg.rng_kind == JMM_RNG_PHILOX && h->pos_in_smem && h->block == kTile && !getenv("JMM_NO_PROD")) {
-            if constexpr (POT != kPotHarmonic) {
-                if (h->cfg.arith == JMM_ARITH_FAST) return launch_step_prod<POT, kArithFast>(h, a);
-            }
-            return launch_step_prod<POT, kArithReference>(h, a);
-        }
+        if (h->coop_g) return jmm_launch_coop(h, a);
+        if (h->cfg.rng_kind == JMM_RNG_PHILOX && h->pos_in_smem && h->block == 32 && !getenv("JMM_NO_PROD"))
+            return jmm_launch_prod(h, a);
     }
     switch (h->cfg.rng_kind) {
         case JMM_RNG_TAUS2: return launch_step_rng<POT, TABLE, kRngTaus2>(h, a);
@@ -924,19 +796,26 @@ extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *r
 // ------------------------------------------------------------------------------------------------
 // checkerboard sweeps
 // ------------------------------------------------------------------------------------------------
-struct SweepShape { int tile, halo, nsub, threads, G; size_t smem; };
 
 static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     SweepShape s{};
     const int nbn = h->cfg.nbn, ncol = nbn + 1;
     const uint64_t N = h->S.N, C = h->S.nchains;
-    s.G = nbn >= 16 ? 32 : 1;
-    // fast-arithmetic kernels fit two CTAs per SM (<= 64 registers): more warps to hide the division latency
-    const bool two_per_sm = h->cfg.arith == JMM_ARITH_FAST && h->cfg.pot != JMM_POT_HARMONIC;
-    const int budget = (two_per_sm ? 100 : 200) * 1024 / 8 - 1024;   // doubles of shared memory for the window
+    // fast-arithmetic kernels fit two CTAs per SM (<= 64 registers): more warps to hide the reciprocal latency
+    const bool fast = h->cfg.arith == JMM_ARITH_FAST && h->cfg.pot != JMM_POT_HARMONIC;
+    if (fast) {
+        // lanes per trial: the largest power of two <= min(NBN, 32) that still leaves every resident thread
+        // (148 SMs x 1024) a trial of its own per half-sweep
+        const uint64_t trials = std::max<uint64_t>(1, C * ((N + ncol - 1) / ncol));
+        int g = 1;
+        while (g * 2 <= std::min(nbn, 32) && trials * (uint64_t) (g * 2) <= 148ull * 1024) g *= 2;
+        if (const char *e = getenv("JMM_SWEEP_G")) { const int v = atoi(e); if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) g = v; }
+        s.G = g;
+    } else s.G = nbn >= 16 ? 32 : 1;
+    const int budget = (fast ? 100 : 200) * 1024 / 8 - 1024;   // doubles of shared memory for the window
     // k CTAs per SM and ONE wave: tiles per chain = m * floor(148 k / nchains), the smallest m whose tile
     // (plus halos) fits in shared memory.  152 CTAs on 148 SMs would cost a whole second wave.
-    const uint64_t base = std::max<uint64_t>(1, (two_per_sm ? 296 : 148) / C);
+    const uint64_t base = std::max<uint64_t>(1, (fast ? 296 : 148) / C);
     int nsub = (int) std::min<uint64_t>(want_sub, 64);
     int tile = 0, halo = 0;
     for (;;) {
@@ -954,29 +833,18 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     }
     if (tile < 2) tile = 2;
     s.tile = tile; s.halo = halo; s.nsub = nsub;
-    const int per_sub = (tile + ncol - 1) / ncol;           // trials per half-sweep per tile
-    int threads = s.G == 1 ? per_sub : per_sub * 32;
+    // trials per half-sweep per tile (first half-sweep of a launch: the halos are still tried)
+    const int per_sub = (tile + 2 * std::max(0, halo - nbn) + ncol - 1) / ncol;
+    int threads;
+    if (fast) {
+        // a whole number of rounds: each group makes `rounds` trials per half-sweep, none idles through a last partial round
+        const int rounds = std::max(1, (per_sub * s.G + 511) / 512);
+        threads = ((per_sub + rounds - 1) / rounds) * s.G;
+    } else threads = s.G == 1 ? per_sub : per_sub * 32;
     threads = std::min(512, std::max(64, ((threads + 31) / 32) * 32));
     s.threads = threads;
     s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) nsub * 8 + 16;
     return s;
-}
-
-template <int POT, int G, int ARITH>
-static cudaError_t launch_sweep_inst(jmm_handle *h, const SweepShape &s, const SweepDev &W, uint64_t step0, int nsub, unsigned ntiles) {
-    dim3 grid(ntiles, (unsigned) h->S.nchains);
-    cudaError_t e = cudaFuncSetAttribute(k_sweep<POT, G, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
-    if (e != cudaSuccess) return e;
-    k_sweep<POT, G, ARITH><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, h->d_partial, h->cb_counts);
-    h->launches++;
-    return cudaGetLastError();
-}
-
-template <int POT>
-static cudaError_t launch_sweep(jmm_handle *h, const SweepShape &s, const SweepDev &W, uint64_t step0, int nsub, unsigned ntiles) {
-    const bool fast = h->cfg.arith == JMM_ARITH_FAST && POT != kPotHarmonic;
-    if (s.G == 1) return fast ? launch_sweep_inst<POT, 1, 1>(h, s, W, step0, nsub, ntiles) : launch_sweep_inst<POT, 1, 0>(h, s, W, step0, nsub, ntiles);
-    return fast ? launch_sweep_inst<POT, 32, 1>(h, s, W, step0, nsub, ntiles) : launch_sweep_inst<POT, 32, 0>(h, s, W, step0, nsub, ntiles);
 }
 
 extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *trials_out) {
@@ -1008,13 +876,7 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
                 if (col < N) trials += (N - col + W.ncol - 1) / W.ncol;
             }
         tick(h);
-        cudaError_t e;
-        switch (h->cfg.pot) {
-            case JMM_POT_LJ: e = launch_sweep<kPotLJ>(h, s, W, h->halfsweeps, nsub, ntiles); break;
-            case JMM_POT_LJCUT: e = launch_sweep<kPotLJcut>(h, s, W, h->halfsweeps, nsub, ntiles); break;
-            default: e = launch_sweep<kPotHarmonic>(h, s, W, h->halfsweeps, nsub, ntiles); break;
-        }
-        CK(e);
+        CK(jmm_launch_sweep(h, s, W, h->halfsweeps, nsub, ntiles));
         k_sweep_finish<<<(unsigned) C, 288, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, N, h->S.l, h->cb_tot, h->cb_acc, 0);
         h->launches++;
         CK(cudaGetLastError());

@@ -1,0 +1,56 @@
+// Launches of the few-chain kernels: coop.cuh (G lanes per chain, any potential) and bond.cuh (HARMONIC, NBN 1).
+#include <math.h>
+#include <cmath>
+
+#include "handle.h"
+#include "coop.cuh"
+#include "bond.cuh"
+
+using namespace jmm;
+
+static_assert(kCoopScratchRows == kCoopChunk, "jmm_create sizes the scratch of coop.cuh");
+
+template <int POT, int G>
+static cudaError_t launch_step_coop_g(jmm_handle *h, const StepArgs &a) {
+    auto kern = a.accept_log ? k_chains_step_coop<POT, G, true> : k_chains_step_coop<POT, G, false>;
+    if (h->coop_smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->coop_smem);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned per_block = 128 / G;
+    kern<<<nblk(h->S.nchains, per_block), 128, h->coop_smem, h->stream>>>(h->S, a, h->coop_npad);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
+    int npad = (int) h->S.N;
+    npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
+    const bool inf = std::isinf(h->S.cutoff);
+    auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
+                             : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
+    const unsigned per_block = 128 / kB2G;
+    kern<<<nblk(h->S.nchains, per_block), 128, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <int POT>
+static cudaError_t launch_step_coop(jmm_handle *h, const StepArgs &a) {
+    if constexpr (POT == kPotHarmonic) {
+        if (h->bond) return launch_step_bond(h, a);
+    }
+    switch (h->coop_g) {
+        case 8: return launch_step_coop_g<POT, 8>(h, a);
+        case 16: return launch_step_coop_g<POT, 16>(h, a);
+        default: return launch_step_coop_g<POT, 32>(h, a);
+    }
+}
+
+cudaError_t jmm_launch_coop(jmm_handle *h, const StepArgs &a) {
+    switch (h->cfg.pot) {
+        case JMM_POT_LJ: return launch_step_coop<kPotLJ>(h, a);
+        case JMM_POT_LJCUT: return launch_step_coop<kPotLJcut>(h, a);
+        default: return launch_step_coop<kPotHarmonic>(h, a);
+    }
+}

@@ -1,0 +1,77 @@
+// Launches of the many-chain production kernels (prod.cuh).
+#include <math.h>
+
+#include "handle.h"
+#include "prod.cuh"
+
+using namespace jmm;
+
+template <int POT, int ARITH, int G>
+static cudaError_t launch_step_prod_g(jmm_handle *h, const StepArgs &a) {
+    auto kern = a.accept_log ? k_chains_step_prod<POT, ARITH, true, G> : k_chains_step_prod<POT, ARITH, false, G>;
+    auto sliced = a.accept_log ? k_chains_step_prod_sliced<POT, ARITH, true, G> : k_chains_step_prod_sliced<POT, ARITH, false, G>;
+    cudaError_t e;
+    const size_t smem = h->smem / G;                      // [N][32/G] doubles
+    if (smem > 48 * 1024) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(sliced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
+    }
+    const unsigned ntiles = nblk(h->S.nchains, kTile / G);
+    // how many CTAs of the sliced kernel are co-resident on this device
+    int per_sm = 0, nsm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sliced, kTile, smem)) != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const unsigned slots = (unsigned) std::max(1, per_sm * nsm);
+    const double waves = (double) ntiles / slots;
+    // (histogram bins are only touched by REDs and L2 reads, so a chain may change SM between chunks)
+    const bool slice = getenv("JMM_FORCE_SLICE") ||
+                       (!getenv("JMM_NO_SLICE") && ntiles > slots && (waves - floor(waves)) < 0.85 && a.nsteps >= 16);
+    if (!slice) {
+        kern<<<ntiles, kTile, smem, h->stream>>>(h->S, a, h->H);
+        h->launches++;
+        return cudaGetLastError();
+    }
+    // ~12+ chunks per launch bounds the imbalance to one chunk in twelve; at least 8 steps per chunk
+    uint32_t chunk = (uint32_t) std::max<uint64_t>(8, (a.nsteps + 11) / 12);
+    if (const char *ev = getenv("JMM_SLICE_CHUNK")) chunk = (uint32_t) std::max(1, atoi(ev));
+    const uint32_t nchunks = (uint32_t) ((a.nsteps + chunk - 1) / chunk);
+    if (h->work_words < (size_t) ntiles + 1) {
+        if (h->d_work) cudaFree(h->d_work);
+        h->d_work = nullptr; h->work_words = 0;
+        if ((e = cudaMalloc((void **) &h->d_work, ((size_t) ntiles + 1) * sizeof(unsigned int))) != cudaSuccess) return e;
+        h->work_words = (size_t) ntiles + 1;
+    }
+    if ((e = cudaMemsetAsync(h->d_work, 0, ((size_t) ntiles + 1) * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
+    sliced<<<std::min(slots, ntiles * nchunks), kTile, smem, h->stream>>>(h->S, a, h->H, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+// Lanes per chain of the fast-arithmetic production kernel (prod.cuh): G = 2 halves a warp's position tile, so twice
+// as many warps are resident per SM.  JMM_PROD_G overrides (1, 2, 4).
+template <int POT, int ARITH>
+static cudaError_t launch_step_prod(jmm_handle *h, const StepArgs &a) {
+    if constexpr (ARITH == kArithFast) {
+        int g = 2;
+        if (const char *e = getenv("JMM_PROD_G")) g = atoi(e);
+        if (g == 4) return launch_step_prod_g<POT, ARITH, 4>(h, a);
+        if (g == 2) return launch_step_prod_g<POT, ARITH, 2>(h, a);
+    }
+    return launch_step_prod_g<POT, ARITH, 1>(h, a);
+}
+
+template <int POT>
+static cudaError_t launch_step_prod_pot(jmm_handle *h, const StepArgs &a) {
+    if constexpr (POT != kPotHarmonic) {
+        if (h->cfg.arith == JMM_ARITH_FAST) return launch_step_prod<POT, kArithFast>(h, a);
+    }
+    return launch_step_prod<POT, kArithReference>(h, a);
+}
+
+cudaError_t jmm_launch_prod(jmm_handle *h, const StepArgs &a) {
+    switch (h->cfg.pot) {
+        case JMM_POT_LJ: return launch_step_prod_pot<kPotLJ>(h, a);
+        case JMM_POT_LJCUT: return launch_step_prod_pot<kPotLJcut>(h, a);
+        default: return launch_step_prod_pot<kPotHarmonic>(h, a);
+    }
+}

@@ -13,6 +13,7 @@
 //     an accept/reject decision can differ only if exp(-dE/T) and ran agree to ~1e-15.
 #pragma once
 #include "chains.cuh"
+#include "fastlj.cuh"
 
 namespace jmm {
 
@@ -58,64 +59,80 @@ __device__ __forceinline__ uint8_t prod_displacement_ref(Chain<POT> &ch, const d
     return kLogAccepted;
 }
 
-// LJ / LJcut only
-template <int POT>
-__device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, const double *rs, double *rs_w,
-                                                          uint32_t nm, double rn, double ran) {
+// LJ / LJcut only.  G lanes (1, 2 or 4) share a chain: lane g of the group takes the partners p = lo+g, lo+g+G, ...
+// and the two sums are combined by an xor butterfly (a + b == b + a, so every lane of the group holds the same
+// doubles afterwards and takes the same decision).  Everything outside the partner loop is executed redundantly by
+// the G lanes on identical values.  What this buys: the [N][32/G] position tile of a warp shrinks by G, so G times
+// more warps fit beside each other in shared memory, which is what hides the dependent fp64 latency
+// ("wait" was the dominant stall with one chain per thread: profiles/r01_c4_k_chains_step_prod_fast.txt).
+//
+// The moved particle itself is taken out of the loop without a per-partner test: its slot in the tile is
+// overwritten with a far-away sentinel for the duration of the loop (every lane of the group writes the same
+// value, and the only lane that reads the slot is one of the writers).  LJcut masks the sentinel "pair" to exactly
+// zero (distance > cutoff); LJ adds ~6|md|/1e56 to s6, far below one ulp of any partner term.
+constexpr double kFarAway = 1.0e8;
+
+template <int POT, int G>
+__device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, double *rs, uint32_t g, uint32_t nm, double rn, double ran) {
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
+    constexpr int TILE = kTile / G;
     const double md = (rn - 0.5) * 2 * ch.maxStep;
-    const double rnm = rs[nm * kTile];
+    const double rnm = rs[nm * TILE];
     const double rT = rnm + md;
     if (fabs(rT) > ch.l / 2.0) { ch.cnt[1]++; return kLogWall; }
     const uint32_t N = ch.N;
     const uint32_t lo = (ch.nbn < 0 || (uint32_t) ch.nbn > nm) ? 0u : nm - (uint32_t) ch.nbn;
     const uint32_t hi = (ch.nbn < 0 || nm + (uint32_t) ch.nbn > N - 1) ? N - 1 : nm + (uint32_t) ch.nbn;
+    rs[nm * TILE] = kFarAway;
+    const long long cb = __double_as_longlong(ch.cutoff);
     double s6 = 0, s12 = 0;
-    const double *rp = rs + lo * kTile;
-    // branch-free body (the moved particle itself is given old = new = 1, which contributes exactly 0),
-    // so the unrolled iterations interleave and hide the division latency
+    const double *rp = rs + (lo + g) * TILE;
 #pragma unroll 4
-    for (uint32_t p = lo; p <= hi; ++p, rp += kTile) {
+    for (uint32_t p = lo + g; p <= hi; p += G, rp += G * TILE) {
         const double r = *rp;
-        const bool self = (p == nm);
-        // |d| is what matters for the even powers; the sign only enters LJcut's d <= cutoff test (src/pot.cpp:53)
-        double a = (p < nm) ? rnm - r : r - rnm;              // old distance
-        double b = (p < nm) ? rT - r : r - rT;                // new distance
-        a = self ? 1.0 : a;
-        b = self ? 1.0 : b;
-        const double a3 = a * a * a, b3 = b * b * b;
-        const double A = a3 * a3, B = b3 * b3;
-        const double inv = 1.0 / (A * B);
-        double o6 = B * inv, n6 = A * inv;                   // a^-6, b^-6
         if constexpr (POT == kPotLJcut) {
-            o6 = (a <= ch.cutoff) ? o6 : 0.0;
-            n6 = (b <= ch.cutoff) ? n6 : 0.0;
+            // signed distances in the reference's orientation: `d <= cutOff` is a test on the signed d (src/pot.cpp:53)
+            const bool left = p < nm;
+            lj_partner<true>(left ? rnm - r : r - rnm, left ? rT - r : r - rT, cb, s6, s12);
+        } else {
+            lj_partner<false>(r - rnm, r - rT, cb, s6, s12);      // even powers only: the orientation does not matter
         }
-        s6 += n6 - o6;
-        s12 += n6 * n6 - o6 * o6;
+    }
+    // group mask, not the full warp: the other chains of the warp may be in a volume trial or past a wall reject
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+        s6 += __shfl_xor_sync(ch.gmask, s6, off);
+        s12 += __shfl_xor_sync(ch.gmask, s12, off);
     }
     const double dE12 = 4 * s12, dE6 = 4 * s6;
     const double dE = dE12 - dE6;
-    if (!metropolis_accept(dE, ch.T, ch.invT, ran)) { ch.cnt[1]++; return 0; }
+    if (!metropolis_accept(dE, ch.T, ch.invT, ran)) { rs[nm * TILE] = rnm; ch.cnt[1]++; return 0; }
     ch.cnt[0]++;
     const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
     ch.tot[0] += dE;  ch.tot[2] += dE12; ch.tot[4] += dE6;
     ch.tot[1] += dV12 - dV6; ch.tot[3] += dV12; ch.tot[5] += dV6;
     ch.tot[6] += dH12 - dH6; ch.tot[7] += dH12; ch.tot[8] += dH6;
-    rs_w[nm * kTile] = rT;
+    rs[nm * TILE] = rT;
     return kLogAccepted;
 }
 
-// One tile (32 chains) advanced by `count` steps starting after step sn0 (log rows from log_row0).
+// One tile (32/G chains, G lanes each) advanced by `count` steps starting after step sn0 (log rows from log_row0).
 // COHERENT: chain state is read with ld.global.cg (L2) because another SM may just have written it
 // (persistent time-sliced launch below).
-template <int POT, int ARITH, bool LOG, bool COHERENT>
+template <int POT, int ARITH, bool LOG, bool COHERENT, int G>
 __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs &a, const HistDev &H, uint64_t c, double *smem,
-                                              uint64_t sn0, uint32_t count, uint64_t log_row0) {
+                                              uint64_t sn0, uint32_t count, uint64_t log_row0, bool own = true) {
+    static_assert(G == 1 || ARITH == kArithFast, "reference-order sums are serial: one lane per chain");
+    constexpr int TILE = kTile / G;
+    const uint32_t col = threadIdx.x / G, g = threadIdx.x % G;
+    const bool lead = own && g == 0;                         // the lane that owns the chain's global state
     Chain<POT> ch;
-    load_chain<POT, COHERENT>(ch, S, c, smem + threadIdx.x, kTile);   // ch.r -> shared tile (rare paths use it generically)
-    const double *rs = smem + threadIdx.x;                    // same column, known to be shared memory
-    double *rs_w = smem + threadIdx.x;
+    load_chain<POT, COHERENT>(ch, S, c, smem + col, TILE);   // ch.r -> shared tile (rare paths use it generically)
+    double *rs = smem + col;                                 // same column, known to be shared memory
+    if constexpr (G > 1) {
+        ch.sub = g; ch.nsub = G; ch.gmask = ((1u << G) - 1u) << (threadIdx.x & ~(G - 1));
+        __syncwarp(ch.gmask);                                // the G lanes filled the column with the same values
+    }
 
     Rng<kRngPhilox> rng;
     rng.k0 = (uint32_t) S.seed; rng.k1 = (uint32_t)(S.seed >> 32); rng.chain = (uint32_t)(S.chain_id0 + c);
@@ -139,6 +156,7 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
     uint64_t hist_u = H.ucount ? ld_state<COHERENT>(H.ucount + c) : 0;
 
     for (uint32_t s = 0; s < count; ++s) {
+        if constexpr (G > 1) __syncwarp(ch.gmask);           // the group's (identical) position writes of the last step
         ++sn;
         rng.begin(sn);
         const uint32_t nm = rng.trial_type(ntt, scale);
@@ -146,14 +164,14 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
         const double maxStep_used = ch.maxStep;
         uint8_t flags;
         if (nm < ch.N) {
-            if constexpr (ARITH == kArithFast) flags = prod_displacement_fast<POT>(ch, rs, rs_w, nm, rn, rng.ran());
-            else flags = prod_displacement_ref<POT>(ch, rs, rs_w, nm, rn, rng.ran());
+            if constexpr (ARITH == kArithFast) flags = prod_displacement_fast<POT, G>(ch, rs, g, nm, rn, rng.ran());
+            else flags = prod_displacement_ref<POT>(ch, rs, rs, nm, rn, rng.ran());
         } else {
             if constexpr (POT == kPotLJ) {
                 flags = scaling_volume ? volume_trial_scaling<POT, false>(ch, rn, rng) : volume_trial_full<POT, false>(ch, rn, rng);
             } else flags = volume_trial_full<POT, false>(ch, rn, rng);
         }
-        if (H.ucount) hist_after_trial<POT, false>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u);
+        if (H.ucount && lead) hist_after_trial<POT, false>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u);
         if (--eci_left == 0) { energy_check<POT, false>(ch); eci_left = eci32; }
         if (ch.l != l_seen) { l_seen = ch.l; rho = (double) ch.N / ch.l; }
         {   // updateThermo :1941-1961 with the cached N/l
@@ -168,23 +186,31 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
                 ch.acc[10] = ch.acc[10] + HV;   ch.acc[11] = ch.acc[11] + HV * HV;
             }
         }
-        if (LOG) a.accept_log[(log_row0 + s) * S.nchains + c] = flags;
+        if (LOG && lead) a.accept_log[(log_row0 + s) * S.nchains + c] = flags;
         if (a.adapt_device) {
             if (--mdai_left == 0) { adjust_max_step(ch, a.log_ideal); mdai_left = mdai32; }
             if (--mvai_left == 0) { adjust_max_dl(ch, a.log_ideal); mvai_left = mvai32; }
             if (--relax_left == 0) { if (sn < 1000000ull) relax_volume<POT, false>(ch); relax_left = 10000; }
         }
     }
-    if (H.ucount) H.ucount[c] = hist_u;
-    store_chain(ch, S, c, true);
+    if (lead) {
+        if (H.ucount) H.ucount[c] = hist_u;
+        store_chain(ch, S, c, true);
+    }
 }
 
-template <int POT, int ARITH, bool LOG>
-__global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArgs a, HistDev H) {
+// resident warps per SM the kernels are compiled for: the register budget that goes with the G-times smaller tile
+constexpr int prod_min_ctas(int G) { return G == 1 ? 10 : (G == 2 ? 16 : 24); }
+
+template <int POT, int ARITH, bool LOG, int G>
+__global__ void __launch_bounds__(kTile, prod_min_ctas(G)) k_chains_step_prod(ChainsDev S, StepArgs a, HistDev H) {
     extern __shared__ double smem[];
-    const uint64_t c = (uint64_t) blockIdx.x * kTile + threadIdx.x;
-    if (c >= S.nchains) return;
-    prod_run_tile<POT, ARITH, LOG, false>(S, a, H, c, smem, a.sn0, (uint32_t) a.nsteps, 0);
+    const uint64_t c = (uint64_t) blockIdx.x * (kTile / G) + threadIdx.x / G;
+    if (G == 1 && c >= S.nchains) return;
+    // a ragged last tile (G > 1): the surplus groups shadow the last chain and store nothing, so that the
+    // full-mask shuffles of the partner loop stay convergent
+    const bool own = c < S.nchains;
+    prod_run_tile<POT, ARITH, LOG, false, G>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0, (uint32_t) a.nsteps, 0, own);
 }
 
 // Persistent, time-sliced variant for launches that would otherwise need a fractional number of waves
@@ -193,8 +219,8 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod(ChainsDev S, StepArg
 // out by an atomic counter; a tile's chunk k+1 waits for its chunk k through a per-tile progress word
 // (release/acquire).  Every earlier item is held by a running CTA, so the wait always ends.  Chain state goes
 // through L2 between chunks (8N+256 B per chain per chunk: negligible next to `chunk` steps of work).
-template <int POT, int ARITH, bool LOG>
-__global__ void __launch_bounds__(kTile) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, HistDev H, uint32_t chunk, uint32_t ntiles,
+template <int POT, int ARITH, bool LOG, int G>
+__global__ void __launch_bounds__(kTile, prod_min_ctas(G)) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, HistDev H, uint32_t chunk, uint32_t ntiles,
                                                                    uint32_t nchunks, unsigned int *work, unsigned int *progress) {
     extern __shared__ double smem[];
     for (;;) {
@@ -211,10 +237,11 @@ __global__ void __launch_bounds__(kTile) k_chains_step_prod_sliced(ChainsDev S, 
             } while (seen < k);
         }
         __syncwarp();
-        const uint64_t c = (uint64_t) tile * kTile + threadIdx.x;
+        const uint64_t c = (uint64_t) tile * (kTile / G) + threadIdx.x / G;
         const uint32_t s0 = k * chunk;
         const uint32_t count = min(chunk, (uint32_t) a.nsteps - s0);
-        if (c < S.nchains) prod_run_tile<POT, ARITH, LOG, true>(S, a, H, c, smem, a.sn0 + s0, count, s0);
+        const bool own = c < S.nchains;
+        if (G > 1 || own) prod_run_tile<POT, ARITH, LOG, true, G>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0 + s0, count, s0, own);
         __threadfence();
         __syncwarp();
         if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(progress + tile), "r"(k + 1) : "memory");

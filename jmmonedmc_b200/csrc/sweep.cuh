@@ -21,6 +21,7 @@
 #pragma once
 #include <math.h>
 #include "pot.cuh"
+#include "fastlj.cuh"
 
 namespace jmm {
 
@@ -45,8 +46,8 @@ __device__ __forceinline__ int colour_of(uint64_t seed, uint32_t chain, uint64_t
 // G lanes cooperate on one particle's trial.  G = 1: reference summation order; G = 32: one warp per
 // particle, lane-strided partners + xor butterfly, for wide neighbour sets (only 1 and 32 are
 // instantiated: a group must be a whole warp for the full-mask shuffles below).
-template <int POT, int G, int ARITH>
-__global__ void __launch_bounds__(512, (ARITH == 1 && POT != kPotHarmonic) ? 2 : 1) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
+template <int POT, int G>
+__global__ void __launch_bounds__(512, 1) k_sweep(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
                                                  double *partial /*[nchains][nsub][ntiles][9]*/,
                                                  unsigned long long *counts /*[nchains][2] accepted, trials*/) {
     constexpr int NC = PotTraits<POT>::NC;
@@ -110,8 +111,7 @@ __global__ void __launch_bounds__(512, (ARITH == 1 && POT != kPotHarmonic) ? 2 :
         // particles whose whole neighbourhood is still valid in this window
         const int64_t uhi = (g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn;
         const int64_t first = g0 + firsts[t];
-        constexpr bool kFast = (ARITH == 1 && POT != kPotHarmonic);
-        constexpr int NA = kFast ? 2 : NC;                // fast arithmetic carries only the r^-12 and r^-6 sums
+        constexpr int NA = NC;
         double dacc[NA];
 #pragma unroll
         for (int k = 0; k < NA; ++k) dacc[k] = 0;
@@ -133,41 +133,7 @@ __global__ void __launch_bounds__(512, (ARITH == 1 && POT != kPotHarmonic) ? 2 :
             const int lo = (int) max((int64_t) 0, g - nbn) - (int) g0, hi = (int) min(N - 1, g + nbn) - (int) g0;
             double d[NA];
             bool accept;
-            if constexpr (kFast) {
-                // JMM_ARITH_FAST (see prod.cuh): one division per partner, only the r^-6 / r^-12 differences
-                double s6 = 0, s12 = 0;
-                const int pstart = (G == 1) ? x - nbn : lo + lane;
-                const int pend = (G == 1) ? x + nbn : hi;
-#pragma unroll 4
-                for (int p = pstart; p <= pend; p += G) {
-                    const bool valid = (p >= lo) && (p <= hi) && (p != x);
-                    const double rp = w[min(max(p, lo), hi)];
-                    double a = (p < x) ? rnm - rp : rp - rnm;
-                    double b = (p < x) ? rT - rp : rp - rT;
-                    a = valid ? a : 1.0;
-                    b = valid ? b : 1.0;
-                    const double a3 = a * a * a, b3 = b * b * b;
-                    const double A = a3 * a3, B = b3 * b3;
-                    const double inv = 1.0 / (A * B);
-                    double o6 = B * inv, n6 = A * inv;
-                    if constexpr (POT == kPotLJcut) {
-                        o6 = (a <= cutoff) ? o6 : 0.0;
-                        n6 = (b <= cutoff) ? n6 : 0.0;
-                    }
-                    s6 += n6 - o6;
-                    s12 += n6 * n6 - o6 * o6;
-                }
-                double t6 = s6, t12 = s12;                       // lane-local shares (G == 32) or the whole sums (G == 1)
-                if constexpr (G > 1) {
-#pragma unroll
-                    for (int off = G / 2; off > 0; off >>= 1) {
-                        s6 += __shfl_xor_sync(0xffffffffu, s6, off, G);
-                        s12 += __shfl_xor_sync(0xffffffffu, s12, off, G);
-                    }
-                }
-                accept = metropolis_accept(4 * s12 - 4 * s6, T, invT, ran);
-                d[0] = t12; d[1] = t6;
-            } else if constexpr (G == 1) {
+            if constexpr (G == 1) {
                 // every lane walks nbn left partners (ascending index) then nbn right partners: uniform trip
                 // counts, slots outside the chain are skipped; left and right sums apart (:1277, :1354)
                 double dsum[NC], dleft[NC], po[NC], pn[NC];
@@ -234,14 +200,7 @@ __global__ void __launch_bounds__(512, (ARITH == 1 && POT != kPotHarmonic) ? 2 :
         __syncthreads();                       // also orders this half-sweep's position writes before the next reads
         if (threadIdx.x < 9) {
             double s = 0;
-            if constexpr (kFast) {
-                // nine deltas from the two sums, by the exact ratios of src/pot.cpp:56-66
-                double s12 = 0, s6 = 0;
-                for (int wv = 0; wv < nwarps; ++wv) { s12 += rbuf[wv * 9]; s6 += rbuf[wv * 9 + 1]; }
-                const double e12 = 4 * s12, e6 = 4 * s6;
-                const double v[9] = {e12 - e6, 12 * e12 - 6 * e6, e12, 12 * e12, e6, 6 * e6, 144 * e12 - 36 * e6, 144 * e12, 36 * e6};
-                s = v[threadIdx.x];
-            } else if (threadIdx.x < NC) {
+            if (threadIdx.x < NC) {
                 for (int wv = 0; wv < nwarps; ++wv) s += rbuf[wv * 9 + threadIdx.x];
             }
             partial[(((uint64_t) chain * nsub + t) * gridDim.x + blockIdx.x) * 9 + threadIdx.x] = s;
@@ -264,6 +223,154 @@ __global__ void __launch_bounds__(512, (ARITH == 1 && POT != kPotHarmonic) ? 2 :
     }
 }
 
+// JMM_ARITH_FAST variant of k_sweep for the LJ family (fastlj.cuh: one reciprocal per partner, 18 fp64-pipe
+// instructions for the old and the new pair term together; only s6 = sum(b^-6 - a^-6) and s12 are carried).
+// Same staging, same tiling, same random numbers, same trials as k_sweep; what differs is the partner loop:
+//   * G lanes (1, 2, 4, 8, 16, 32) share one particle's trial; lane j takes the partners at index distance
+//     q = j+1, j+1+G, ... on BOTH sides, so one loop iteration holds two independent pair terms and the loop
+//     has no self test, no clamps and (for interior particles) a trip count known to the whole group;
+//   * the orientation of a distance is known statically (left: r[nm]-r[p], right: r[p]-r[nm]), which is all
+//     LJcut's signed `d <= cutOff` test needs (src/pot.cpp:53);
+//   * every lane of a group evaluates the same Philox block (no broadcast shuffles, no divergence);
+//   * the first/last NBN particles of the chain take a bounds-checked copy of the loop.
+// G is chosen by the host so that (trials per half-sweep) x G fills the resident threads (launch_sweep.cu).
+template <int POT, int G>
+__global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
+                                                       double *partial /*[nchains][nsub][ntiles][9]*/,
+                                                       unsigned long long *counts /*[nchains][2] accepted, trials*/) {
+    static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
+    constexpr bool CUT = (POT == kPotLJcut);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nwarps = blockDim.x >> 5;
+    double *w = reinterpret_cast<double *>(smem_raw);                 // window of positions
+    const int64_t N = (int64_t) S.N;
+    const int chain = blockIdx.y;
+    const int64_t tile_lo = (int64_t) blockIdx.x * tile;
+    const int64_t tile_hi = min(tile_lo + tile, N);
+    const int64_t g0 = max((int64_t) 0, tile_lo - halo);              // window = [g0, g1)
+    const int64_t g1 = min(N, tile_hi + halo);
+    const int wlen = (int) (g1 - g0);
+    const int wcap = tile + 2 * halo;
+    double *red = w + wcap;                                           // [2][nwarps][9]
+    int *colours = reinterpret_cast<int *>(red + 2 * nwarps * 9);     // [nsub]
+    int *firsts = colours + nsub;                                     // [nsub] window index of the first particle to try
+    __shared__ __align__(8) unsigned long long mbar;
+
+    const double *src = S.r_in + (uint64_t) chain * S.N + g0;
+    const int body = ((((uintptr_t) src) & 15) == 0) ? (wlen & ~1) : 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && body > 0) {
+        const uint32_t bytes = (uint32_t) body * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(w)), "l"(src), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+    }
+    for (int i = body + threadIdx.x; i < wlen; i += blockDim.x) w[i] = src[i];
+    for (int t = threadIdx.x; t < nsub; t += blockDim.x) {
+        const int col = colour_of(S.seed, (uint32_t)(S.chain_id0 + chain), step0 + t, S.ncol);
+        colours[t] = col;
+        const int64_t ulo = (g0 == 0) ? 0 : g0 + (int64_t)(t + 1) * S.nbn;
+        firsts[t] = (int) (ulo + (((int64_t) col - ulo % S.ncol) + S.ncol) % S.ncol - g0);
+    }
+    if (body > 0) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+        }
+    }
+    __syncthreads();
+
+    const double half_l = S.l[chain] / 2.0, T = S.T[chain], step2 = 2 * S.maxStep[chain];
+    const double invT = 1.0 / T;
+    const long long cb = __double_as_longlong(S.cutoff);
+    const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32);
+    const uint32_t tag = kTagParticle | (uint32_t)(S.chain_id0 + chain);
+    const int nbn = S.nbn, ncol = S.ncol;
+    const int group = threadIdx.x / G, lane = threadIdx.x % G, ngroups = blockDim.x / G;
+    const int warp = threadIdx.x >> 5;
+    // the groups of a warp run different numbers of trials and reject at the wall independently: shuffle within the group only
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    const int x_lo = (int) (tile_lo - g0), x_hi = (int) (tile_hi - g0);     // owned window range
+    const int x_first_interior = (int) max((int64_t) 0, (int64_t) nbn - g0);   // x >= this: all left partners exist
+    const int x_last_interior = (int) (min(g1, N - nbn) - g0) - 1;             // x <= this: all right partners exist
+    uint32_t n_acc = 0, n_try = 0;
+
+    for (int t = 0; t < nsub; ++t) {
+        const int x_end = (int) (((g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn) - g0);
+        const uint32_t s_lo = (uint32_t)(step0 + t), s_hi = (uint32_t)((step0 + t) >> 32);
+        double acc6 = 0, acc12 = 0;
+        for (int x = firsts[t] + group * ncol; x < x_end; x += ngroups * ncol) {
+            const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, k0, k1);
+            const double rn = u01(b4.w[0]), ran = u01(b4.w[1]);
+            const double rnm = w[x];
+            const double md = (rn - 0.5) * step2;                                     // qad2 :1182 ((rn-.5)*2*maxStep, 2*maxStep exact)
+            const double rT = rnm + md;                                               // :1183
+            const bool owned = (x >= x_lo) && (x < x_hi);
+            if (owned && lane == 0) ++n_try;
+            if (fabs(rT) > half_l) continue;                                          // :1188 (group-uniform)
+            double s6 = 0, s12 = 0;
+            if (x >= x_first_interior && x <= x_last_interior) {
+                const double *wl = w + x - 1 - lane, *wr = w + x + 1 + lane;
+#pragma unroll 2
+                for (int q = lane; q < nbn; q += G, wl -= G, wr += G) {
+                    const double rl = *wl, rr = *wr;
+                    lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12);
+                    lj_partner<CUT>(rr - rnm, rr - rT, cb, s6, s12);
+                }
+            } else {
+                for (int q = lane + 1; q <= nbn; q += G) {
+                    if (g0 + x - q >= 0) { const double rl = w[x - q]; lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12); }
+                    if (g0 + x + q < N) { const double rr = w[x + q]; lj_partner<CUT>(rr - rnm, rr - rT, cb, s6, s12); }
+                }
+            }
+            const double m6 = s6, m12 = s12;                 // this lane's share
+#pragma unroll
+            for (int off = 1; off < G; off <<= 1) {
+                s6 += __shfl_xor_sync(gmask, s6, off);
+                s12 += __shfl_xor_sync(gmask, s12, off);
+            }
+            if (metropolis_accept(4 * s12 - 4 * s6, T, invT, ran)) {                  // :1367-1377
+                if (lane == 0) w[x] = rT;
+                if (owned) { acc6 += m6; acc12 += m12; if (lane == 0) ++n_acc; }
+            }
+        }
+        // block-wide sum of this half-sweep's deltas over the owned particles -> partial[chain][t][tile][:]
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc6 += __shfl_xor_sync(0xffffffffu, acc6, off);
+            acc12 += __shfl_xor_sync(0xffffffffu, acc12, off);
+        }
+        double *rbuf = red + (t & 1) * nwarps * 9;
+        if ((threadIdx.x & 31) == 0) { rbuf[warp * 9] = acc12; rbuf[warp * 9 + 1] = acc6; }
+        __syncthreads();                       // also orders this half-sweep's position writes before the next reads
+        if (threadIdx.x < 9) {
+            double t12 = 0, t6 = 0;
+            for (int wv = 0; wv < nwarps; ++wv) { t12 += rbuf[wv * 9]; t6 += rbuf[wv * 9 + 1]; }
+            double v[9];
+            lj_nine(t6, t12, v);
+            partial[(((uint64_t) chain * nsub + t) * gridDim.x + blockIdx.x) * 9 + threadIdx.x] = v[threadIdx.x];
+        }
+    }
+
+    // ---- write back the owned particles
+    double *dst = S.r_out + (uint64_t) chain * S.N;
+    for (int64_t g = tile_lo + threadIdx.x; g < tile_hi; g += blockDim.x) dst[g] = w[g - g0];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_acc += __shfl_xor_sync(0xffffffffu, n_acc, off);
+        n_try += __shfl_xor_sync(0xffffffffu, n_try, off);
+    }
+    if ((threadIdx.x & 31) == 0 && (n_acc | n_try)) {
+        atomicAdd(&counts[2 * chain], (unsigned long long) n_acc);
+        atomicAdd(&counts[2 * chain + 1], (unsigned long long) n_try);
+    }
+}
+
 // After a k_sweep launch: fold the per-tile deltas into the running totals half-sweep by half-sweep
 // (fixed summation order -> reproducible) and sample the twelve sums once per half-sweep
 // (updateThermo :1941-1961 with l constant).
@@ -277,7 +384,7 @@ __device__ __forceinline__ void cb_sample(double (&a)[12], const double *cur, do
 // presample != 0: one extra sample of the current totals first (the updateThermo of src/Main.cpp:96).
 // Launched with 9 warps per chain: warp k owns component k; its lanes add the tiles strided and
 // combine with a fixed butterfly, so the result does not depend on scheduling.
-__global__ void __launch_bounds__(288) k_sweep_finish(const double *partial, int nsub, int ntiles, uint64_t N, const double *l,
+static __global__ void __launch_bounds__(288) k_sweep_finish(const double *partial, int nsub, int ntiles, uint64_t N, const double *l,
                                                       double *tot /*[nchains][9]*/, double *acc /*[nchains][12]*/, int presample) {
     const int chain = blockIdx.x;
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -359,7 +466,7 @@ __global__ void __launch_bounds__(256) k_totals_partial(const double *__restrict
     }
 }
 
-__global__ void k_totals_finish(const double *partial, int nblocks, uint64_t nchains, double *out, uint64_t ks, uint64_t cs) {
+static __global__ void k_totals_finish(const double *partial, int nblocks, uint64_t nchains, double *out, uint64_t ks, uint64_t cs) {
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchains * 9) return;
     const uint64_t chain = t / 9, k = t % 9;

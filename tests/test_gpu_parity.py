@@ -195,11 +195,17 @@ def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
         assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
 
 
+@pytest.mark.parametrize("lanes", ["1", "2", "4", "2-sliced"])
 @pytest.mark.parametrize("name", ["small", "ljcut_nbn", "nlt"])
-def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, monkeypatch):
-    """JMM_ARITH_FAST (prod.cuh): one division per partner, r^-6/r^-12 differences only.  Positions and the
-    accept/reject sequence must equal the oracle's exactly; the nine totals and twelve sums agree to 1e-12."""
+def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, lanes, monkeypatch):
+    """JMM_ARITH_FAST (prod.cuh, fastlj.cuh): one reciprocal per partner, r^-6/r^-12 differences only, 1, 2 or 4
+    lanes per chain (40 chains = a ragged last tile for 2 and 4).  Positions and the accept/reject sequence must
+    equal the oracle's exactly; the nine totals and twelve sums agree to 1e-12."""
     monkeypatch.setenv("JMM_COOP_G", "0")
+    monkeypatch.setenv("JMM_PROD_G", lanes.split("-")[0])
+    if lanes.endswith("sliced"):
+        monkeypatch.setenv("JMM_FORCE_SLICE", "1")
+        monkeypatch.setenv("JMM_SLICE_CHUNK", "7")
     d = DECKS[name]
     C, nsteps, id0 = 40, 1500, 7
     cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C, chain_id0=id0,
@@ -275,13 +281,16 @@ def test_energy_bookkeeping_stays_consistent(J, O):
     assert abs(np.mean(acc[:, 2] / 5001) - np.mean(s["l"])) < 0.2 * np.mean(s["l"])   # ensemble <L> ~ current L
 
 
-@pytest.mark.parametrize("arith", ["reference", "fast"])
+@pytest.mark.parametrize("arith", ["reference", "fast", "fast-g1", "fast-g8", "fast-g32"])
 @pytest.mark.parametrize("pot,nbn,cutoff,N,C", [("LJcut", 4, 5.0, 20000, 2), ("LJ", 2, math.inf, 5001, 1),
                                                  ("HARMONIC", 1, math.inf, 8192, 3), ("LJ", 24, math.inf, 6000, 2)])
-def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C, arith):
+def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C, arith, monkeypatch):
     from jmmonedmc_b200.capi import config
-    if arith == "fast" and pot == "HARMONIC":
+    if arith != "reference" and pot == "HARMONIC":
         pytest.skip("fast arithmetic is an LJ-family path")
+    if "-g" in arith:                       # lanes per trial of k_sweep_fast (default: chosen from the trial count)
+        arith, g = arith.split("-g")
+        monkeypatch.setenv("JMM_SWEEP_G", g)
     P = {"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT, "HARMONIC": J.POT_HARMONIC}[pot]
     seed, id0, T, ms, nhs = 92847, 5, 0.9, 0.12, 3 * (nbn + 1) + 1
     L = N * 1.12
