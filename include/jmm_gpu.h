@@ -180,6 +180,18 @@ jmm_status jmm_enable_histograms(jmm_handle *h, uint64_t rhonb, double rbw, int3
  * rhoA [nchains][rhonb], gA [nchains][gns][gnb]; a NULL pointer leaves that histogram untouched. */
 jmm_status jmm_take_histograms(jmm_handle *h, int64_t *rhoA, int64_t *gA);
 
+/* Exact restart.  The reference's RESTART (src/jmmMCState.cpp:572-765, src/readInput.cpp:69-78)
+ * re-reads the last complete frame of config.dat.mcs and re-seeds the generator with the SAME seed: maxStep, maxdl,
+ * the acceptance counters and the generator state are lost, so a resumed run is only statistically a continuation.
+ * jmm_checkpoint_save writes everything the next step depends on — step number, positions, box, the nine totals,
+ * twelve sums, four counters, step sizes, vAErrNtot, ECheck statistics, taus2 states / recorded-stream cursor, the
+ * pair table in table mode, the histogram bins when enabled (a Philox stream needs nothing: its counter IS the step
+ * number) — to one binary file; jmm_checkpoint_load restores it into a handle created from the same jmm_config
+ * (checked: N, nchains, mode, pot, NBN, ensemble, generator, seed, chain_id0), after which jmm_step / jmm_sweep
+ * continue bit for bit as if the run had never stopped.  JMM_ERR_IO on file errors, JMM_ERR_INVALID on a mismatch. */
+jmm_status jmm_checkpoint_save(jmm_handle *h, const char *path);
+jmm_status jmm_checkpoint_load(jmm_handle *h, const char *path);
+
 /* JMM_MODE_CHECKERBOARD (no reference counterpart — the reference moves
  * one particle per Step and cannot allocate its O(N^2) tables beyond N ~ 1e4).  One call performs
  * n_halfsweeps colour half-sweeps: in each, a colour c in [0, NBN+1) is drawn (Philox) and every

@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
         "jmm_sweep": (C.c_int32, [H, C.c_uint64, u64p]),
         "jmm_enable_histograms": (C.c_int32, [H, C.c_uint64, C.c_double, C.c_int32, C.c_uint64, C.c_double, C.c_double]),
         "jmm_take_histograms": (C.c_int32, [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "jmm_checkpoint_save": (C.c_int32, [H, C.c_char_p]),
+        "jmm_checkpoint_load": (C.c_int32, [H, C.c_char_p]),
         "jmm_kernel_launches": (C.c_uint64, [H]),
         "jmm_last_kernel_ms": (C.c_double, [H]),
         "jmm_set_stream": (C.c_int32, [H, C.c_void_p]),
@@ -255,6 +257,12 @@ class Handle:
         p = lambda x: x.ctypes.data_as(C.POINTER(C.c_int64)) if x is not None else None
         _check(self.L.jmm_take_histograms(self.h, p(a), p(b)))
         return a, b
+
+    def checkpoint_save(self, path):
+        _check(self.L.jmm_checkpoint_save(self.h, str(path).encode()))
+
+    def checkpoint_load(self, path):
+        _check(self.L.jmm_checkpoint_load(self.h, str(path).encode()))
 
     def sweep(self, n_halfsweeps):
         t = C.c_uint64()

@@ -71,14 +71,10 @@ __device__ __forceinline__ B2Trial b2_displacement(const B2Chain &c, uint32_t nm
     const double r0 = hasR ? (0.0 - qo[0] + qn[0]) : 0.0, r1 = hasR ? (0.0 - qo[1] + qn[1]) : 0.0;   // :1339
     t.dE = l0 + r0;                                                                                  // :1354
     t.dV = l1 + r1;
-    // Metropolis by the Taylor bounds of metropolis_accept(); `decided` false = evaluate exp exactly
-    const double x = t.dE * c.invT;
-    const double x2 = x * x;
-    const double p3 = 1.0 - x + x2 * (0.5 - x * (1.0 / 6.0));
-    const double p4 = p3 + x2 * x2 * (1.0 / 24.0);
-    const bool small = x <= 1.5;
+    // Metropolis by the approximation band of metropolis_accept(); `decided` false = evaluate exp exactly
+    const double ea = (double) exp_neg_approx(t.dE * c.invT);
     const bool down = t.dE <= 0;
-    const bool acc_b = small & (ran < p3 - 1e-9), rej_b = small & (ran > p4 + 1e-9);
+    const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
     t.decided = down | acc_b | rej_b;
     t.accept = down | acc_b;
     return t;

@@ -83,39 +83,45 @@ __device__ __forceinline__ void hist_bump(HistBin *bins, uint64_t idx, int delta
     atomicAdd(&bins[idx].W, (unsigned long long) ((long long) delta * (long long) u));  // RED.ADD.64
 }
 
-// set every bin of a histogram to zero at ugrho count u: only the non-zero bins are touched
-__device__ __forceinline__ void hist_clear(HistBin *bins, uint64_t n, uint64_t u) {
-    for (uint64_t b = 0; b < n; ++b) {
-        const int v = __ldcg(&bins[b].val);              // L2: the REDs above never update L1
+// Zero every bin of one chain's histogram at ugrho count u, by ALL the lanes of `wmask` together: lane `rank` of
+// `nlanes` takes bins rank, rank+nlanes, ... (a warp-wide load covers 512 contiguous bytes), and only non-zero bins
+// are touched.  One thread scanning the 11 000 bins of the RunJobs geometry alone is ~11 000 dependent L2 round
+// trips (5 ms per accepted volume move, measured); 32 lanes with four loads in flight each take ~50 us.
+__device__ __forceinline__ void hist_clear_coop(HistBin *bins, uint64_t n, uint64_t u, uint32_t rank, uint32_t nlanes) {
+#pragma unroll 4
+    for (uint64_t b = rank; b < n; b += nlanes) {
+        const int v = __ldcg(&bins[b].val);              // L2: REDs never update L1
         if (v != 0) hist_bump(bins, b, -v, u);
     }
 }
 
-// fgrho :1069-1127 for one chain (positions r, stride rs; rij table when TABLE)
+// The counting half of fgrho :1069-1127 for one chain (positions r, stride rs; rij table when TABLE), split over the
+// `nlanes` lanes that call it together: rho over the particles, g over the partners j of every particle i.  The
+// additions commute, so who counts which pair does not matter (one lane alone: 3160 pairs of ~150 instructions,
+// ~1.9 ms per accepted volume move at N = 80, measured).
 template <bool TABLE>
-__device__ __forceinline__ void hist_fgrho(const HistDev &H, uint64_t c, const double *r, size_t rs, const double *rij, size_t ts,
-                                           uint32_t N, uint64_t u) {
-    __threadfence();                                     // this thread's earlier REDs are performed before the reads below
+__device__ __forceinline__ void hist_recount(const HistDev &H, uint64_t c, const double *r, size_t rs, const double *rij, size_t ts,
+                                             uint32_t N, uint64_t u, uint32_t rank, uint32_t nlanes) {
     HistBin *rb = H.rho + c * H.rhonb;
-    hist_clear(rb, H.rhonb, u);
-    for (uint32_t i = 0; i < N; ++i) {
+    for (uint32_t i = rank; i < N; i += nlanes) {
         const long long k = (long long) floor(r[i * rs] / H.rbw + (double) H.rhonb / 2.0);
         if (k >= 0 && k < (long long) H.rhonb) hist_bump(rb, (uint64_t) k, +1, u);
     }
-    const uint64_t ng = (uint64_t) H.gns * H.gnb;
-    HistBin *gb_ = H.g + c * ng;
-    hist_clear(gb_, ng, u);
-    for (uint32_t i = 0; i + 1 < N; ++i)
-        for (uint32_t j = i + 1; j < N; ++j) {
-            const long long gs1 = (long long) floor(r[i * rs] / H.gsw + H.gns / 2.0);
-            const long long gs2 = (long long) floor(r[j * rs] / H.gsw + H.gns / 2.0);
-            const double d = TABLE ? rij[pair_index(N, i, j) * ts] : r[j * rs] - r[i * rs];
+    HistBin *gb_ = H.g + c * (uint64_t) H.gns * H.gnb;
+    for (uint32_t i = 0; i + 1 < N; ++i) {
+        const double ri = r[i * rs];
+        const long long gs1 = (long long) floor(ri / H.gsw + H.gns / 2.0);
+        for (uint32_t j = i + 1 + rank; j < N; j += nlanes) {
+            const double rj = r[j * rs];
+            const long long gs2 = (long long) floor(rj / H.gsw + H.gns / 2.0);
+            const double d = TABLE ? rij[pair_index(N, i, j) * ts] : rj - ri;
             const long long gb = (long long) floor(d / H.gbw);
             if (gb >= 0 && gb < (long long) H.gnb) {
                 if (gs1 >= 0 && gs1 < H.gns) hist_bump(gb_, (uint64_t) (gs1 * H.gnb + gb), +1, u);
                 if (gs2 >= 0 && gs2 < H.gns) hist_bump(gb_, (uint64_t) (gs2 * H.gnb + gb), +1, u);
             }
         }
+    }
 }
 
 // qagrho :2297-2384 after an accepted displacement of particle nm by md (old position re-derived as r[nm]-md).
@@ -170,16 +176,12 @@ struct Chain {
     double acc[kNAcc];
     uint64_t cnt[kNCnt];
     uint64_t vAErr, echecks, discrepancies;
-    // lanes sharing this chain (prod.cuh, G > 1): every lane holds the same scalars; position updates that read what
-    // they overwrite are split over the lanes (scale_positions).  One chain per thread: sub = 0, nsub = 1.
-    uint32_t sub, nsub, gmask;
 };
 
 // r *= f for the whole chain (qavLJ :1692, fav :2264-2266, moveVolume :2847-2849)
 template <int POT>
 __device__ __forceinline__ void scale_positions(Chain<POT> &ch, double f) {
-    for (uint32_t i = ch.sub; i < ch.N; i += ch.nsub) ch.r[i * ch.rs] = ch.r[i * ch.rs] * f;
-    if (ch.nsub > 1) __syncwarp(ch.gmask);
+    for (uint32_t i = 0; i < ch.N; ++i) ch.r[i * ch.rs] = ch.r[i * ch.rs] * f;
 }
 
 template <int POT>
@@ -507,13 +509,39 @@ __device__ __forceinline__ void adjust_max_dl(Chain<POT> &ch, double log_ideal) 
 }
 
 // What qad2 / qavLJ do to the histograms after the trial (:1431, :1453, :1717, :1726); fav does nothing (:2161-2293).
+// COLLECTIVE over the lanes of `wmask` (every one of them calls it once per step, chain owner or not): the
+// displacement updates are the owner's alone, but an fgrho (accepted qavLJ move) — zero every bin, count every
+// particle and pair again — is done by the whole warp for one chain at a time.  `own` = this lane owns chain c
+// (helpers pass false and ignore the rest).
 template <int POT, bool TABLE>
 __device__ __forceinline__ void hist_after_trial(const HistDev &H, uint64_t c, const Chain<POT> &ch, uint32_t nm, double rn,
-                                                 double maxStep_used, uint8_t flags, bool scaling_volume, uint64_t &u) {
+                                                 double maxStep_used, uint8_t flags, bool scaling_volume, uint64_t &u,
+                                                 bool own, unsigned wmask) {
+    const bool refill = own && (flags & kLogVolume) && scaling_volume && (flags & kLogAccepted);
+    unsigned need = __ballot_sync(wmask, refill);
+    if (need) {
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t rank = __popc(wmask & ((1u << lane) - 1u)), nlanes = __popc(wmask);
+        if (refill) __threadfence();                                   // the owner's earlier REDs are performed before the helpers read
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const uint64_t cc = __shfl_sync(wmask, c, src), uu = __shfl_sync(wmask, u, src);
+            // the owner's positions (its shared-memory column or its global column) and pair table, by generic address
+            const double *pr = (const double *) __shfl_sync(wmask, (unsigned long long) ch.r, src);
+            const double *pt = (const double *) __shfl_sync(wmask, (unsigned long long) ch.rij, src);
+            const size_t prs = (size_t) __shfl_sync(wmask, (unsigned long long) ch.rs, src);
+            const size_t pts = (size_t) __shfl_sync(wmask, (unsigned long long) ch.ts, src);
+            const uint32_t pn = __shfl_sync(wmask, ch.N, src);
+            hist_clear_coop(H.rho + cc * H.rhonb, H.rhonb, uu, rank, nlanes);
+            hist_clear_coop(H.g + cc * (uint64_t) H.gns * H.gnb, (uint64_t) H.gns * H.gnb, uu, rank, nlanes);
+            __syncwarp(wmask);                                         // every lane has read its bins: counting may start
+            hist_recount<TABLE>(H, cc, pr, prs, pt, pts, pn, uu, rank, nlanes);
+        }
+    }
+    if (!own) return;
     if (flags & kLogVolume) {
-        if (!scaling_volume) return;                                   // fav: no fgrho, no ugrho
-        if (flags & kLogAccepted) hist_fgrho<TABLE>(H, c, ch.r, ch.rs, ch.rij, ch.ts, ch.N, u);
-        ++u;
+        if (scaling_volume) ++u;                                       // fav: no fgrho, no ugrho
         return;
     }
     if (flags & kLogAccepted) hist_qagrho(H, c, ch.r, ch.rs, ch.N, nm, (rn - 0.5) * 2 * maxStep_used, u);
@@ -534,7 +562,6 @@ __device__ __forceinline__ void load_chain(Chain<POT> &ch, const ChainsDev &S, u
                                            uint32_t smem_stride) {
     constexpr int NC = PotTraits<POT>::NC;
     ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff;
-    ch.sub = 0; ch.nsub = 1; ch.gmask = 0;
     ch.l = ld_state<CG>(S.l + c); ch.P = ld_state<CG>(S.P + c); ch.T = ld_state<CG>(S.T + c);
     ch.maxStep = ld_state<CG>(S.maxStep + c); ch.maxdl = ld_state<CG>(S.maxdl + c);
     ch.invT = 1.0 / ch.T;
@@ -610,7 +637,6 @@ __global__ void k_chains_totals_exact(ChainsDev S, double *out /*[9][nchains]*/)
     if (c >= S.nchains) return;
     Chain<POT> ch;
     ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff; ch.l = S.l[c];
-    ch.sub = 0; ch.nsub = 1; ch.gmask = 0;
     ch.r = S.r + c; ch.rs = S.nchains;
     constexpr int NC = PotTraits<POT>::NC;
     double t[NC];
@@ -626,8 +652,15 @@ template <int POT, bool TABLE, int RNG>
 __global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a, HistDev H) {
     extern __shared__ double smem[];
     const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= S.nchains) return;
     Chain<POT> ch;
+    if (c >= S.nchains) {
+        // lanes without a chain: with histograms on they stay as helpers of the warp-wide refill (hist_after_trial)
+        if (H.ucount) {
+            uint64_t u = 0;
+            for (uint64_t s = 0; s < a.nsteps; ++s) hist_after_trial<POT, TABLE>(H, 0, ch, 0, 0.0, 0.0, 0, false, u, false, 0xffffffffu);
+        }
+        return;
+    }
     load_chain(ch, S, c, a.pos_in_smem ? smem + threadIdx.x : nullptr, blockDim.x);
 
     Rng<RNG> rng;
@@ -664,7 +697,7 @@ __global__ void __launch_bounds__(128) k_chains_step(ChainsDev S, StepArgs a, Hi
                                        : volume_trial_full<POT, TABLE>(ch, rn, rng);
             } else flags = volume_trial_full<POT, TABLE>(ch, rn, rng);                // :1786-1788
         }
-        if (H.ucount) hist_after_trial<POT, TABLE>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u);
+        if (H.ucount) hist_after_trial<POT, TABLE>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u, true, 0xffffffffu);
         if (--eci_left == 0) { energy_check<POT, TABLE>(ch); eci_left = a.eci; }      // :1800-1802
         update_thermo(ch);                                                            // :1805
         if (a.accept_log) a.accept_log[s * S.nchains + c] = flags;
@@ -690,7 +723,7 @@ static __global__ void k_hist_init(ChainsDev S, HistDev H) {
     const uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= S.nchains) return;
     // distances from the positions: setupMCS fills rij = r[j]-r[i] (:768) just before its fgrho, the same doubles
-    hist_fgrho<false>(H, c, S.r + c, S.nchains, nullptr, 0, (uint32_t) S.N, 0);
+    hist_recount<false>(H, c, S.r + c, S.nchains, nullptr, 0, (uint32_t) S.N, 0, 0, 1);    // the bins were allocated zeroed
     H.ucount[c] = 1;
 }
 

@@ -60,7 +60,12 @@ static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned) ((n + b 
 
 constexpr int kCoopScratchRows = 32;        // = kCoopChunk of coop.cuh (checked there)
 
-struct SweepShape { int tile, halo, nsub, threads, G; size_t smem; };
+struct SweepShape {
+    int tile, halo, nsub, threads, G;
+    size_t smem;
+    int fast;          // k_sweep_fast serves this launch (JMM_ARITH_FAST, LJ family)
+    int rounds, rad;   // k_sweep_fast: trials per group per half-sweep; how far (in warps) a warp's stretch can collide
+};
 
 #define JMM_INTERNAL __attribute__((visibility("hidden")))
 // prod.cuh: many chains, one chain per thread or per G lanes (POT / arithmetic / G dispatch inside)

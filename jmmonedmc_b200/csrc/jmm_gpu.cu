@@ -562,6 +562,110 @@ extern "C" jmm_status jmm_take_histograms(jmm_handle *h, int64_t *rhoA, int64_t 
 // ------------------------------------------------------------------------------------------------
 static jmm_status totals_parallel(jmm_handle *h, const double *r, uint64_t ps, uint64_t cs, double *out, uint64_t ks, uint64_t ocs);
 
+// ------------------------------------------------------------------------------------------------
+// exact restart (N4): one binary file with everything the next step depends on
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct CkptHeader {
+    char magic[8];                 // "JMMCKPT1"
+    uint64_t N, nchains, seed, chain_id0, sn, halfsweeps, cursor;
+    int32_t mode, pot, nbn, ensemble, rng_kind, cb_cur, hist, gns;
+    uint64_t rhonb, gnb;
+    double rbw, gsw, gbw;
+};
+
+// the device arrays of a handle, in file order
+template <class F>
+jmm_status ckpt_arrays(jmm_handle *h, F &&io) {
+    const uint64_t C = h->S.nchains, N = h->S.N;
+    jmm_status st;
+#define IO(ptr, count) if ((st = io((void *) (ptr), (size_t) (count) * sizeof(*(ptr)))) != JMM_OK) return st
+    IO(h->S.l, C); IO(h->S.P, C); IO(h->S.T, C); IO(h->S.maxStep, C); IO(h->S.maxdl, C);
+    if (is_cb(h)) {
+        IO(h->cb_r[h->cb_cur], C * N); IO(h->cb_tot, C * 9); IO(h->cb_acc, C * 12); IO(h->cb_counts, C * 2);
+    } else {
+        IO(h->S.r, C * N); IO(h->S.tot, C * 9); IO(h->S.acc, C * 12); IO(h->S.cnt, C * 4); IO(h->S.vAErr, C);
+        IO(h->S.echeck, C * 2); IO(h->S.taus, C * 3);
+        if (h->S.rij) IO(h->S.rij, C * h->S.npairs);
+    }
+    if (h->H.ucount) {
+        IO(h->H.rho, C * h->H.rhonb); IO(h->H.g, C * (uint64_t) h->H.gns * h->H.gnb); IO(h->H.ucount, C);
+    }
+#undef IO
+    return JMM_OK;
+}
+
+CkptHeader ckpt_header(const jmm_handle *h) {
+    CkptHeader k{};
+    memcpy(k.magic, "JMMCKPT1", 8);
+    k.N = h->S.N; k.nchains = h->S.nchains; k.seed = h->cfg.seed; k.chain_id0 = h->cfg.chain_id0;
+    k.sn = h->sn; k.halfsweeps = h->halfsweeps; k.cursor = h->cursor;
+    k.mode = h->cfg.mode; k.pot = h->cfg.pot; k.nbn = h->cfg.nbn; k.ensemble = h->cfg.ensemble; k.rng_kind = h->cfg.rng_kind;
+    k.cb_cur = 0; k.hist = h->H.ucount ? 1 : 0; k.gns = h->H.gns; k.rhonb = h->H.rhonb; k.gnb = h->H.gnb;
+    k.rbw = h->H.rbw; k.gsw = h->H.gsw; k.gbw = h->H.gbw;
+    return k;
+}
+}  // namespace
+
+extern "C" jmm_status jmm_checkpoint_save(jmm_handle *h, const char *path) {
+    if (!h || !path) return fail(JMM_ERR_INVALID, "jmm_checkpoint_save: null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(JMM_ERR_IO, std::string("cannot write ") + path);
+    const CkptHeader k = ckpt_header(h);
+    bool ok = fwrite(&k, sizeof(k), 1, f) == 1;
+    std::vector<char> buf;
+    jmm_status st = ckpt_arrays(h, [&](void *d, size_t bytes) -> jmm_status {
+        buf.resize(bytes);
+        CK(cudaMemcpy(buf.data(), d, bytes, cudaMemcpyDeviceToHost));
+        ok = ok && fwrite(buf.data(), 1, bytes, f) == bytes;
+        return JMM_OK;
+    });
+    ok = (fclose(f) == 0) && ok;
+    if (st != JMM_OK) return st;
+    return ok ? JMM_OK : fail(JMM_ERR_IO, std::string("short write to ") + path);
+}
+
+extern "C" jmm_status jmm_checkpoint_load(jmm_handle *h, const char *path) {
+    if (!h || !path) return fail(JMM_ERR_INVALID, "jmm_checkpoint_load: null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(JMM_ERR_IO, std::string("cannot read ") + path);
+    CkptHeader k{};
+    if (fread(&k, sizeof(k), 1, f) != 1 || memcmp(k.magic, "JMMCKPT1", 8) != 0) {
+        fclose(f);
+        return fail(JMM_ERR_IO, std::string(path) + " is not a jmm checkpoint");
+    }
+    const CkptHeader me = ckpt_header(h);
+    if (k.N != me.N || k.nchains != me.nchains || k.seed != me.seed || k.chain_id0 != me.chain_id0 || k.mode != me.mode ||
+        k.pot != me.pot || k.nbn != me.nbn || k.ensemble != me.ensemble || k.rng_kind != me.rng_kind) {
+        fclose(f);
+        return fail(JMM_ERR_INVALID, "checkpoint was written by a handle with a different configuration "
+                                     "(N, nchains, mode, pot, NBN, ensemble, generator, seed or chain_id0)");
+    }
+    if (k.hist != me.hist || (k.hist && (k.rhonb != me.rhonb || k.gnb != me.gnb || k.gns != me.gns || k.rbw != me.rbw ||
+                                         k.gsw != me.gsw || k.gbw != me.gbw))) {
+        fclose(f);
+        return fail(JMM_ERR_INVALID, "checkpoint and handle disagree about the histograms (call jmm_enable_histograms "
+                                     "with the same geometry before jmm_checkpoint_load, or not at all)");
+    }
+    std::vector<char> buf;
+    bool ok = true;
+    jmm_status st = ckpt_arrays(h, [&](void *d, size_t bytes) -> jmm_status {
+        buf.resize(bytes);
+        if (fread(buf.data(), 1, bytes, f) != bytes) { ok = false; return fail(JMM_ERR_IO, std::string("truncated checkpoint ") + path); }
+        CK(cudaMemcpy(d, buf.data(), bytes, cudaMemcpyHostToDevice));
+        return JMM_OK;
+    });
+    fclose(f);
+    if (st != JMM_OK) return st;
+    h->sn = k.sn; h->halfsweeps = k.halfsweeps; h->cursor = k.cursor;
+    if (h->d_cursor) CK(cudaMemcpy(h->d_cursor, &h->cursor, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    return ok ? JMM_OK : JMM_ERR_IO;
+}
+
 extern "C" jmm_status jmm_start(jmm_handle *h) {
     if (!h) return fail(JMM_ERR_INVALID, "null handle");
     CK(cudaSetDevice(h->cfg.device));
@@ -570,7 +674,7 @@ extern "C" jmm_status jmm_start(jmm_handle *h) {
         // first updateThermo (src/Main.cpp:96) as a zero-length "finish"
         jmm_status st = totals_parallel(h, h->cb_r[h->cb_cur], 1, h->S.N, h->cb_tot, 1, 9);
         if (st != JMM_OK) return st;
-        k_sweep_finish<<<(unsigned) h->S.nchains, 288, 0, h->stream>>>(nullptr, 0, 0, h->S.N, h->S.l, h->cb_tot, h->cb_acc, 1);
+        k_sweep_finish<<<(unsigned) h->S.nchains, 32, 0, h->stream>>>(nullptr, 0, h->S.N, h->S.l, h->cb_tot, h->cb_acc, 1);
         h->launches++;
         CK(cudaGetLastError());
         return JMM_OK;
@@ -835,12 +939,22 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     s.tile = tile; s.halo = halo; s.nsub = nsub;
     // trials per half-sweep per tile (first half-sweep of a launch: the halos are still tried)
     const int per_sub = (tile + 2 * std::max(0, halo - nbn) + ncol - 1) / ncol;
-    int threads;
+    s.fast = fast ? 1 : 0;
     if (fast) {
-        // a whole number of rounds: each group makes `rounds` trials per half-sweep, none idles through a last partial round
+        // warp w owns the trials [wK, (w+1)K) of every half-sweep, K = rounds * (32/G); a whole number of rounds,
+        // so that no group idles through a last partial round
+        const int gpw = 32 / s.G;
         const int rounds = std::max(1, (per_sub * s.G + 511) / 512);
-        threads = ((per_sub + rounds - 1) / rounds) * s.G;
-    } else threads = s.G == 1 ? per_sub : per_sub * 32;
+        const int K = rounds * gpw;
+        const int nwarps = std::max(2, std::min(16, (per_sub + K - 1) / K));
+        s.rounds = (per_sub + nwarps * gpw - 1) / (nwarps * gpw);        // >= rounds when nwarps was clipped
+        s.threads = nwarps * 32;
+        // colour offsets drift by at most nsub*NBN + ncol over the launch; reads reach NBN either side
+        s.rad = 1 + (nsub * nbn + ncol + 2 * nbn) / (s.rounds * gpw * ncol);
+        s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) nsub * 4 + (size_t) nwarps * 4 + 32;
+        return s;
+    }
+    int threads = s.G == 1 ? per_sub : per_sub * 32;
     threads = std::min(512, std::max(64, ((threads + 31) / 32) * 32));
     s.threads = threads;
     s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) nsub * 8 + 16;
@@ -858,8 +972,13 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
         const SweepShape s = sweep_shape(h, remaining);
         const int nsub = (int) std::min<uint64_t>(remaining, (uint64_t) s.nsub);
         const unsigned ntiles = (unsigned) ((N + s.tile - 1) / s.tile);
-        jmm_status st = ensure_partial(h, C * (size_t) nsub * ntiles * 9 * sizeof(double));
+        // per-tile deltas [C][nsub][ntiles][9] (k_sweep) or per-warp sums [C][nsub][ntiles*nwarps][2] (k_sweep_fast),
+        // then their sums over the tiles [C][nsub][9]
+        const size_t nslots = (size_t) ntiles * (s.threads / 32);
+        const size_t n_partial = s.fast ? C * (size_t) nsub * nslots * 2 : C * (size_t) nsub * ntiles * 9;
+        jmm_status st = ensure_partial(h, (n_partial + C * (size_t) nsub * 9) * sizeof(double));
         if (st != JMM_OK) return st;
+        double *tsum = h->d_partial + n_partial;
         SweepDev W{};
         W.nchains = C; W.N = N; W.nbn = h->cfg.nbn; W.ncol = h->cfg.nbn + 1; W.cutoff = h->S.cutoff;
         W.r_in = h->cb_r[h->cb_cur]; W.r_out = h->cb_r[h->cb_cur ^ 1];
@@ -877,8 +996,10 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
             }
         tick(h);
         CK(jmm_launch_sweep(h, s, W, h->halfsweeps, nsub, ntiles));
-        k_sweep_finish<<<(unsigned) C, 288, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, N, h->S.l, h->cb_tot, h->cb_acc, 0);
-        h->launches++;
+        if (s.fast) k_sweep_reduce2<<<dim3((unsigned) nsub, (unsigned) C), 256, 0, h->stream>>>(h->d_partial, nsub, nslots, tsum);
+        else k_sweep_reduce<<<dim3((unsigned) nsub, (unsigned) C), 288, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, tsum);
+        k_sweep_finish<<<(unsigned) C, 32, (size_t) nsub * 9 * sizeof(double), h->stream>>>(tsum, nsub, N, h->S.l, h->cb_tot, h->cb_acc, 0);
+        h->launches += 2;
         CK(cudaGetLastError());
         tock(h);
         h->cb_cur ^= 1;

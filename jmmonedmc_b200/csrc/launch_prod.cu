@@ -6,17 +6,17 @@
 
 using namespace jmm;
 
-template <int POT, int ARITH, int G>
-static cudaError_t launch_step_prod_g(jmm_handle *h, const StepArgs &a) {
-    auto kern = a.accept_log ? k_chains_step_prod<POT, ARITH, true, G> : k_chains_step_prod<POT, ARITH, false, G>;
-    auto sliced = a.accept_log ? k_chains_step_prod_sliced<POT, ARITH, true, G> : k_chains_step_prod_sliced<POT, ARITH, false, G>;
+template <int POT, int ARITH, int UNROLL>
+static cudaError_t launch_step_prod_u(jmm_handle *h, const StepArgs &a) {
+    auto kern = a.accept_log ? k_chains_step_prod<POT, ARITH, true, UNROLL> : k_chains_step_prod<POT, ARITH, false, UNROLL>;
+    auto sliced = a.accept_log ? k_chains_step_prod_sliced<POT, ARITH, true, UNROLL> : k_chains_step_prod_sliced<POT, ARITH, false, UNROLL>;
     cudaError_t e;
-    const size_t smem = h->smem / G;                      // [N][32/G] doubles
+    const size_t smem = h->smem;                          // [N][32] doubles
     if (smem > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(sliced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
     }
-    const unsigned ntiles = nblk(h->S.nchains, kTile / G);
+    const unsigned ntiles = nblk(h->S.nchains, kTile);
     // how many CTAs of the sliced kernel are co-resident on this device
     int per_sm = 0, nsm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sliced, kTile, smem)) != cudaSuccess) return e;
@@ -47,17 +47,14 @@ static cudaError_t launch_step_prod_g(jmm_handle *h, const StepArgs &a) {
     return cudaGetLastError();
 }
 
-// Lanes per chain of the fast-arithmetic production kernel (prod.cuh): G = 2 halves a warp's position tile, so twice
-// as many warps are resident per SM.  JMM_PROD_G overrides (1, 2, 4).
 template <int POT, int ARITH>
 static cudaError_t launch_step_prod(jmm_handle *h, const StepArgs &a) {
     if constexpr (ARITH == kArithFast) {
-        int g = 2;
-        if (const char *e = getenv("JMM_PROD_G")) g = atoi(e);
-        if (g == 4) return launch_step_prod_g<POT, ARITH, 4>(h, a);
-        if (g == 2) return launch_step_prod_g<POT, ARITH, 2>(h, a);
+        // partners in flight per thread: 8 (C4: 7.74e9 trials/s) or 4 (7.54e9)
+        const char *e = getenv("JMM_PROD_UNROLL");
+        if (!(e && atoi(e) == 4)) return launch_step_prod_u<POT, ARITH, 8>(h, a);
     }
-    return launch_step_prod_g<POT, ARITH, 1>(h, a);
+    return launch_step_prod_u<POT, ARITH, 4>(h, a);
 }
 
 template <int POT>

@@ -18,7 +18,8 @@ static cudaError_t launch_sweep_fast_inst(jmm_handle *h, const SweepShape &s, co
     dim3 grid(ntiles, (unsigned) h->S.nchains);
     cudaError_t e = cudaFuncSetAttribute(k_sweep_fast<POT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
     if (e != cudaSuccess) return e;
-    k_sweep_fast<POT, G><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, h->d_partial, h->cb_counts);
+    k_sweep_fast<POT, G><<<grid, s.threads, s.smem, h->stream>>>(W, step0, nsub, s.tile, s.halo, s.rounds, s.rad, h->d_partial,
+                                                                   h->cb_counts);
     h->launches++;
     return cudaGetLastError();
 }
@@ -26,7 +27,7 @@ static cudaError_t launch_sweep_fast_inst(jmm_handle *h, const SweepShape &s, co
 template <int POT>
 static cudaError_t launch_sweep(jmm_handle *h, const SweepShape &s, const SweepDev &W, uint64_t step0, int nsub, unsigned ntiles) {
     if constexpr (POT != kPotHarmonic) {
-        if (h->cfg.arith == JMM_ARITH_FAST) {
+        if (s.fast) {
             switch (s.G) {
                 case 1: return launch_sweep_fast_inst<POT, 1>(h, s, W, step0, nsub, ntiles);
                 case 2: return launch_sweep_fast_inst<POT, 2>(h, s, W, step0, nsub, ntiles);

@@ -62,27 +62,31 @@ __device__ __forceinline__ double phi_energy(double d, double cutoff) {
     }
 }
 
+// e^-x for x >= 0 in single precision: MUFU.EX2 of -x*log2(e).  Error budget: (float) x and the product round at
+// 2^-24 each, so t = -x log2 e carries |t| 2^-22.6 and 2^t a relative |t| 2^-23.1; ex2.approx.ftz.f32 itself is
+// good to 2^-22 (PTX ISA).  Absolute error <= e^-x (1.6e-7 x + 2.4e-7) <= 3e-7 for every x >= 0.
+__device__ __forceinline__ float exp_neg_approx(double x) {
+    const float t = (float) x * -1.4426950408889634f;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return e;
+}
+constexpr double kMetropolisBand = 1e-5;     // > 30 x the error bound of exp_neg_approx
+
 // Metropolis rule of qad2, src/jmmMCState.cpp:1367-1377: accept iff dE <= 0 || exp(-dE/T) > ran.
-// exp() and the division are ~70 instructions, and ran is uniform, so the decision is almost always
-// settled by the Taylor bounds  P3(x) <= exp(-x) <= P4(x)  (valid for every x >= 0):
-//   ran < P3(x) - 1e-9  -> accept,   ran > P4(x) + 1e-9 -> reject,   otherwise evaluate exactly
-// (for x > 1.5 the reciprocal of the degree-4 partial sum of e^x bounds exp(-x) from above instead).
-// The 1e-9 margins dwarf the rounding of x = dE*(1/T) and of the polynomials (~1e-15), so the result is
-// always the one exp(-dE/T) > ran would give: decisions stay bit-identical to the reference-order code.
+// exp() and the IEEE division are ~70 instructions; ran is uniform, so the decision is settled by a cheap
+// approximation ea of exp(-dE/T) unless ran falls within 1e-5 of it (2e-5 of the trials):
+//   ran > ea + 1e-5 -> reject,   ran < ea - 1e-5 -> accept,   otherwise evaluate exactly.
+// The band is > 30 times the error of ea, so the result is always the one exp(-dE/T) > ran would give: decisions
+// stay bit-identical to the reference-order code.  (Earlier version: Taylor bounds P3 <= e^-x <= P4, which left
+// 4-20 % of the draws with x in (1, 1.5) undecided and a warp takes the slow path if ANY lane does: 7 % of the
+// instructions of the C3 kernel, profiles/r01_c3_k_sweep_fast.txt.)  A NaN dE fails every comparison and is
+// rejected by the exact test, like in the reference.
 __device__ __forceinline__ bool metropolis_accept(double dE, double T, double invT, double ran) {
     if (dE <= 0) return true;
-    const double x = dE * invT;
-    if (x <= 1.5) {
-        const double x2 = x * x;
-        const double p3 = 1.0 - x + x2 * (0.5 - x * (1.0 / 6.0));
-        if (ran < p3 - 1e-9) return true;
-        const double p4 = p3 + x2 * x2 * (1.0 / 24.0);
-        if (ran > p4 + 1e-9) return false;
-    } else {
-        // large x: e^x >= 1 + x + x^2/2 + x^3/6 + x^4/24, so exp(-x) <= 1/(that): almost every draw is rejected here
-        const double q = 1.0 + x * (1.0 + x * (0.5 + x * ((1.0 / 6.0) + x * (1.0 / 24.0))));
-        if (ran * q > 1.0 + 1e-9 * q) return false;
-    }
+    const double ea = (double) exp_neg_approx(dE * invT);
+    if (ran > ea + kMetropolisBand) return false;
+    if (ran < ea - kMetropolisBand) return true;
     return exp(-dE / T) > ran;
 }
 

@@ -59,36 +59,34 @@ __device__ __forceinline__ uint8_t prod_displacement_ref(Chain<POT> &ch, const d
     return kLogAccepted;
 }
 
-// LJ / LJcut only.  G lanes (1, 2 or 4) share a chain: lane g of the group takes the partners p = lo+g, lo+g+G, ...
-// and the two sums are combined by an xor butterfly (a + b == b + a, so every lane of the group holds the same
-// doubles afterwards and takes the same decision).  Everything outside the partner loop is executed redundantly by
-// the G lanes on identical values.  What this buys: the [N][32/G] position tile of a warp shrinks by G, so G times
-// more warps fit beside each other in shared memory, which is what hides the dependent fp64 latency
-// ("wait" was the dominant stall with one chain per thread: profiles/r01_c4_k_chains_step_prod_fast.txt).
+// LJ / LJcut only: fastlj.cuh arithmetic, one chain per thread.
 //
 // The moved particle itself is taken out of the loop without a per-partner test: its slot in the tile is
-// overwritten with a far-away sentinel for the duration of the loop (every lane of the group writes the same
-// value, and the only lane that reads the slot is one of the writers).  LJcut masks the sentinel "pair" to exactly
+// overwritten with a far-away sentinel for the duration of the loop.  LJcut masks the sentinel "pair" to exactly
 // zero (distance > cutoff); LJ adds ~6|md|/1e56 to s6, far below one ulp of any partner term.
+//
+// Measured and dropped: G = 2 or 4 lanes per chain (lane-strided partners, xor-butterfly of the two sums, [N][32/G]
+// tile so that G times more warps are resident).  C4, trial moves/s: G = 1 7.25e9, G = 2 6.22e9, G = 4 4.35e9 — the
+// per-step work every lane of a group repeats and the 128/80-register budgets cost more than the extra warps give.
 constexpr double kFarAway = 1.0e8;
 
-template <int POT, int G>
-__device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, double *rs, uint32_t g, uint32_t nm, double rn, double ran) {
+// UNROLL = partners in flight per thread (independent reciprocal chains)
+template <int POT, int UNROLL>
+__device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, double *rs, uint32_t nm, double rn, double ran) {
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
-    constexpr int TILE = kTile / G;
     const double md = (rn - 0.5) * 2 * ch.maxStep;
-    const double rnm = rs[nm * TILE];
+    const double rnm = rs[nm * kTile];
     const double rT = rnm + md;
     if (fabs(rT) > ch.l / 2.0) { ch.cnt[1]++; return kLogWall; }
     const uint32_t N = ch.N;
     const uint32_t lo = (ch.nbn < 0 || (uint32_t) ch.nbn > nm) ? 0u : nm - (uint32_t) ch.nbn;
     const uint32_t hi = (ch.nbn < 0 || nm + (uint32_t) ch.nbn > N - 1) ? N - 1 : nm + (uint32_t) ch.nbn;
-    rs[nm * TILE] = kFarAway;
+    rs[nm * kTile] = kFarAway;
     const long long cb = __double_as_longlong(ch.cutoff);
     double s6 = 0, s12 = 0;
-    const double *rp = rs + (lo + g) * TILE;
-#pragma unroll 4
-    for (uint32_t p = lo + g; p <= hi; p += G, rp += G * TILE) {
+    const double *rp = rs + lo * kTile;
+#pragma unroll (UNROLL)
+    for (uint32_t p = lo; p <= hi; ++p, rp += kTile) {
         const double r = *rp;
         if constexpr (POT == kPotLJcut) {
             // signed distances in the reference's orientation: `d <= cutOff` is a test on the signed d (src/pot.cpp:53)
@@ -98,41 +96,30 @@ __device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, double
             lj_partner<false>(r - rnm, r - rT, cb, s6, s12);      // even powers only: the orientation does not matter
         }
     }
-    // group mask, not the full warp: the other chains of the warp may be in a volume trial or past a wall reject
-#pragma unroll
-    for (int off = 1; off < G; off <<= 1) {
-        s6 += __shfl_xor_sync(ch.gmask, s6, off);
-        s12 += __shfl_xor_sync(ch.gmask, s12, off);
-    }
     const double dE12 = 4 * s12, dE6 = 4 * s6;
     const double dE = dE12 - dE6;
-    if (!metropolis_accept(dE, ch.T, ch.invT, ran)) { rs[nm * TILE] = rnm; ch.cnt[1]++; return 0; }
+    if (!metropolis_accept(dE, ch.T, ch.invT, ran)) { rs[nm * kTile] = rnm; ch.cnt[1]++; return 0; }
     ch.cnt[0]++;
     const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
     ch.tot[0] += dE;  ch.tot[2] += dE12; ch.tot[4] += dE6;
     ch.tot[1] += dV12 - dV6; ch.tot[3] += dV12; ch.tot[5] += dV6;
     ch.tot[6] += dH12 - dH6; ch.tot[7] += dH12; ch.tot[8] += dH6;
-    rs[nm * TILE] = rT;
+    rs[nm * kTile] = rT;
     return kLogAccepted;
 }
 
-// One tile (32/G chains, G lanes each) advanced by `count` steps starting after step sn0 (log rows from log_row0).
+// One tile (32 chains) advanced by `count` steps starting after step sn0 (log rows from log_row0).
+// own = false: a surplus lane of a ragged last tile; it shadows the last chain and stores nothing, so that the
+// warp-wide histogram refill (hist_after_trial) always sees a whole warp.
 // COHERENT: chain state is read with ld.global.cg (L2) because another SM may just have written it
 // (persistent time-sliced launch below).
-template <int POT, int ARITH, bool LOG, bool COHERENT, int G>
+template <int POT, int ARITH, bool LOG, bool COHERENT, int UNROLL>
 __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs &a, const HistDev &H, uint64_t c, double *smem,
                                               uint64_t sn0, uint32_t count, uint64_t log_row0, bool own = true) {
-    static_assert(G == 1 || ARITH == kArithFast, "reference-order sums are serial: one lane per chain");
-    constexpr int TILE = kTile / G;
-    const uint32_t col = threadIdx.x / G, g = threadIdx.x % G;
-    const bool lead = own && g == 0;                         // the lane that owns the chain's global state
+    const bool lead = own;                                   // the lane that owns the chain's global state
     Chain<POT> ch;
-    load_chain<POT, COHERENT>(ch, S, c, smem + col, TILE);   // ch.r -> shared tile (rare paths use it generically)
-    double *rs = smem + col;                                 // same column, known to be shared memory
-    if constexpr (G > 1) {
-        ch.sub = g; ch.nsub = G; ch.gmask = ((1u << G) - 1u) << (threadIdx.x & ~(G - 1));
-        __syncwarp(ch.gmask);                                // the G lanes filled the column with the same values
-    }
+    load_chain<POT, COHERENT>(ch, S, c, smem + threadIdx.x, kTile);   // ch.r -> shared tile (rare paths use it generically)
+    double *rs = smem + threadIdx.x;                         // same column, known to be shared memory
 
     Rng<kRngPhilox> rng;
     rng.k0 = (uint32_t) S.seed; rng.k1 = (uint32_t)(S.seed >> 32); rng.chain = (uint32_t)(S.chain_id0 + c);
@@ -156,7 +143,6 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
     uint64_t hist_u = H.ucount ? ld_state<COHERENT>(H.ucount + c) : 0;
 
     for (uint32_t s = 0; s < count; ++s) {
-        if constexpr (G > 1) __syncwarp(ch.gmask);           // the group's (identical) position writes of the last step
         ++sn;
         rng.begin(sn);
         const uint32_t nm = rng.trial_type(ntt, scale);
@@ -164,14 +150,14 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
         const double maxStep_used = ch.maxStep;
         uint8_t flags;
         if (nm < ch.N) {
-            if constexpr (ARITH == kArithFast) flags = prod_displacement_fast<POT, G>(ch, rs, g, nm, rn, rng.ran());
+            if constexpr (ARITH == kArithFast) flags = prod_displacement_fast<POT, UNROLL>(ch, rs, nm, rn, rng.ran());
             else flags = prod_displacement_ref<POT>(ch, rs, rs, nm, rn, rng.ran());
         } else {
             if constexpr (POT == kPotLJ) {
                 flags = scaling_volume ? volume_trial_scaling<POT, false>(ch, rn, rng) : volume_trial_full<POT, false>(ch, rn, rng);
             } else flags = volume_trial_full<POT, false>(ch, rn, rng);
         }
-        if (H.ucount && lead) hist_after_trial<POT, false>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u);
+        if (H.ucount) hist_after_trial<POT, false>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u, lead, 0xffffffffu);
         if (--eci_left == 0) { energy_check<POT, false>(ch); eci_left = eci32; }
         if (ch.l != l_seen) { l_seen = ch.l; rho = (double) ch.N / ch.l; }
         {   // updateThermo :1941-1961 with the cached N/l
@@ -199,18 +185,15 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
     }
 }
 
-// resident warps per SM the kernels are compiled for: the register budget that goes with the G-times smaller tile
-constexpr int prod_min_ctas(int G) { return G == 1 ? 10 : (G == 2 ? 16 : 24); }
+// 10 one-warp CTAs per SM is what the [80][32] tile of C4 allows: up to 204 registers per thread
+constexpr int kProdMinCtas = 10;
 
-template <int POT, int ARITH, bool LOG, int G>
-__global__ void __launch_bounds__(kTile, prod_min_ctas(G)) k_chains_step_prod(ChainsDev S, StepArgs a, HistDev H) {
+template <int POT, int ARITH, bool LOG, int UNROLL>
+__global__ void __launch_bounds__(kTile, kProdMinCtas) k_chains_step_prod(ChainsDev S, StepArgs a, HistDev H) {
     extern __shared__ double smem[];
-    const uint64_t c = (uint64_t) blockIdx.x * (kTile / G) + threadIdx.x / G;
-    if (G == 1 && c >= S.nchains) return;
-    // a ragged last tile (G > 1): the surplus groups shadow the last chain and store nothing, so that the
-    // full-mask shuffles of the partner loop stay convergent
+    const uint64_t c = (uint64_t) blockIdx.x * kTile + threadIdx.x;
     const bool own = c < S.nchains;
-    prod_run_tile<POT, ARITH, LOG, false, G>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0, (uint32_t) a.nsteps, 0, own);
+    prod_run_tile<POT, ARITH, LOG, false, UNROLL>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0, (uint32_t) a.nsteps, 0, own);
 }
 
 // Persistent, time-sliced variant for launches that would otherwise need a fractional number of waves
@@ -219,8 +202,8 @@ __global__ void __launch_bounds__(kTile, prod_min_ctas(G)) k_chains_step_prod(Ch
 // out by an atomic counter; a tile's chunk k+1 waits for its chunk k through a per-tile progress word
 // (release/acquire).  Every earlier item is held by a running CTA, so the wait always ends.  Chain state goes
 // through L2 between chunks (8N+256 B per chain per chunk: negligible next to `chunk` steps of work).
-template <int POT, int ARITH, bool LOG, int G>
-__global__ void __launch_bounds__(kTile, prod_min_ctas(G)) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, HistDev H, uint32_t chunk, uint32_t ntiles,
+template <int POT, int ARITH, bool LOG, int UNROLL>
+__global__ void __launch_bounds__(kTile, kProdMinCtas) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, HistDev H, uint32_t chunk, uint32_t ntiles,
                                                                    uint32_t nchunks, unsigned int *work, unsigned int *progress) {
     extern __shared__ double smem[];
     for (;;) {
@@ -237,11 +220,11 @@ __global__ void __launch_bounds__(kTile, prod_min_ctas(G)) k_chains_step_prod_sl
             } while (seen < k);
         }
         __syncwarp();
-        const uint64_t c = (uint64_t) tile * (kTile / G) + threadIdx.x / G;
+        const uint64_t c = (uint64_t) tile * kTile + threadIdx.x;
         const uint32_t s0 = k * chunk;
         const uint32_t count = min(chunk, (uint32_t) a.nsteps - s0);
         const bool own = c < S.nchains;
-        if (G > 1 || own) prod_run_tile<POT, ARITH, LOG, true, G>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0 + s0, count, s0, own);
+        prod_run_tile<POT, ARITH, LOG, true, UNROLL>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0 + s0, count, s0, own);
         __threadfence();
         __syncwarp();
         if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(progress + tile), "r"(k + 1) : "memory");

@@ -225,21 +225,32 @@ __global__ void __launch_bounds__(512, 1) k_sweep(SweepDev S, uint64_t step0, in
 
 // JMM_ARITH_FAST variant of k_sweep for the LJ family (fastlj.cuh: one reciprocal per partner, 18 fp64-pipe
 // instructions for the old and the new pair term together; only s6 = sum(b^-6 - a^-6) and s12 are carried).
-// Same staging, same tiling, same random numbers, same trials as k_sweep; what differs is the partner loop:
+// Same staging, same tiling, same random numbers, same trials as k_sweep; what differs:
 //   * G lanes (1, 2, 4, 8, 16, 32) share one particle's trial; lane j takes the partners at index distance
 //     q = j+1, j+1+G, ... on BOTH sides, so one loop iteration holds two independent pair terms and the loop
 //     has no self test, no clamps and (for interior particles) a trip count known to the whole group;
 //   * the orientation of a distance is known statically (left: r[nm]-r[p], right: r[p]-r[nm]), which is all
 //     LJcut's signed `d <= cutOff` test needs (src/pot.cpp:53);
 //   * every lane of a group evaluates the same Philox block (no broadcast shuffles, no divergence);
-//   * the first/last NBN particles of the chain take a bounds-checked copy of the loop.
-// G is chosen by the host so that (trials per half-sweep) x G fills the resident threads (launch_sweep.cu).
+//   * the first/last NBN particles of the chain take a bounds-checked copy of the loop;
+//   * NO block-wide barrier between half-sweeps.  Warp w owns the trials j in [wK, (w+1)K) of every half-sweep
+//     (K = rounds * 32/G consecutive same-colour particles = a contiguous stretch of K*ncol particles), so what it
+//     reads and writes can only collide with warps at most `rad` away (host: rad = 1 + floor((nsub*NBN + ncol +
+//     2 NBN) / (K ncol)), the drift of the colour offsets over the launch).  A warp starts half-sweep t once the
+//     warps within `rad` have published half-sweep t-1 as done (a counter per warp in shared memory, release /
+//     acquire by __threadfence_block): read-after-write and write-after-read are both covered, and a slow warp
+//     only holds up its neighbours.  With the __syncthreads version "barrier" was the second largest stall reason
+//     (profiles/r01_c3_k_sweep_fast.txt).
+//   * per half-sweep every warp writes its two sums to partial[chain][t][tile*nwarps + warp][2]; k_sweep_reduce2
+//     adds them over all slots and expands them to the nine deltas.
+// G, rounds and rad are chosen by the host (jmm_gpu.cu: sweep_shape).
 template <int POT, int G>
-__global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step0, int nsub, int tile, int halo,
-                                                       double *partial /*[nchains][nsub][ntiles][9]*/,
+__global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step0, int nsub, int tile, int halo, int rounds, int rad,
+                                                       double *partial /*[nchains][nsub][ntiles*nwarps][2]*/,
                                                        unsigned long long *counts /*[nchains][2] accepted, trials*/) {
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
     constexpr bool CUT = (POT == kPotLJcut);
+    constexpr int GPW = 32 / G;                                       // groups (trials in flight) per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
     double *w = reinterpret_cast<double *>(smem_raw);                 // window of positions
@@ -251,9 +262,8 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
     const int64_t g1 = min(N, tile_hi + halo);
     const int wlen = (int) (g1 - g0);
     const int wcap = tile + 2 * halo;
-    double *red = w + wcap;                                           // [2][nwarps][9]
-    int *colours = reinterpret_cast<int *>(red + 2 * nwarps * 9);     // [nsub]
-    int *firsts = colours + nsub;                                     // [nsub] window index of the first particle to try
+    int *firsts = reinterpret_cast<int *>(w + wcap);                  // [nsub] window index of the first particle to try
+    volatile int *done = firsts + nsub;                               // [nwarps] half-sweeps completed by each warp
     __shared__ __align__(8) unsigned long long mbar;
 
     const double *src = S.r_in + (uint64_t) chain * S.N + g0;
@@ -262,6 +272,7 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < nwarps) done[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0 && body > 0) {
         const uint32_t bytes = (uint32_t) body * 8u;
@@ -272,15 +283,14 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
     for (int i = body + threadIdx.x; i < wlen; i += blockDim.x) w[i] = src[i];
     for (int t = threadIdx.x; t < nsub; t += blockDim.x) {
         const int col = colour_of(S.seed, (uint32_t)(S.chain_id0 + chain), step0 + t, S.ncol);
-        colours[t] = col;
         const int64_t ulo = (g0 == 0) ? 0 : g0 + (int64_t)(t + 1) * S.nbn;
         firsts[t] = (int) (ulo + (((int64_t) col - ulo % S.ncol) + S.ncol) % S.ncol - g0);
     }
     if (body > 0) {
-        uint32_t done = 0;
-        while (!done) {
+        uint32_t ok = 0;
+        while (!ok) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+                         : "=r"(ok) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
         }
     }
     __syncthreads();
@@ -291,20 +301,33 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
     const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32);
     const uint32_t tag = kTagParticle | (uint32_t)(S.chain_id0 + chain);
     const int nbn = S.nbn, ncol = S.ncol;
-    const int group = threadIdx.x / G, lane = threadIdx.x % G, ngroups = blockDim.x / G;
-    const int warp = threadIdx.x >> 5;
-    // the groups of a warp run different numbers of trials and reject at the wall independently: shuffle within the group only
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+    const int gi = lane32 / G, lane = lane32 % G;
+    // the groups of a warp reject at the wall independently: shuffle within the group only
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane32 & ~(G - 1)));
     const int x_lo = (int) (tile_lo - g0), x_hi = (int) (tile_hi - g0);     // owned window range
     const int x_first_interior = (int) max((int64_t) 0, (int64_t) nbn - g0);   // x >= this: all left partners exist
     const int x_last_interior = (int) (min(g1, N - nbn) - g0) - 1;             // x <= this: all right partners exist
+    const int j0 = warp * rounds * GPW + gi;                                   // this group's first trial of a half-sweep
+    const int w_lo = max(0, warp - rad), w_hi = min(nwarps - 1, warp + rad);
+    const size_t nslots = (size_t) gridDim.x * nwarps;
     uint32_t n_acc = 0, n_try = 0;
 
     for (int t = 0; t < nsub; ++t) {
+        if (t > 0) {
+            // wait until every warp whose stretch can touch ours has finished half-sweep t-1
+            if (lane32 == 0)
+                for (int v = w_lo; v <= w_hi; ++v)
+                    while (done[v] < t) __nanosleep(20);
+            __syncwarp();
+            __threadfence_block();
+        }
         const int x_end = (int) (((g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn) - g0);
         const uint32_t s_lo = (uint32_t)(step0 + t), s_hi = (uint32_t)((step0 + t) >> 32);
         double acc6 = 0, acc12 = 0;
-        for (int x = firsts[t] + group * ncol; x < x_end; x += ngroups * ncol) {
+        int x = firsts[t] + j0 * ncol;
+        for (int r = 0; r < rounds; ++r, x += GPW * ncol) {
+            if (x >= x_end) break;
             const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, k0, k1);
             const double rn = u01(b4.w[0]), ran = u01(b4.w[1]);
             const double rnm = w[x];
@@ -339,23 +362,21 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
                 if (owned) { acc6 += m6; acc12 += m12; if (lane == 0) ++n_acc; }
             }
         }
-        // block-wide sum of this half-sweep's deltas over the owned particles -> partial[chain][t][tile][:]
+        __syncwarp();
+        // this warp's half-sweep is complete: publish it (the position writes above first), then its two sums
+        __threadfence_block();
+        if (lane32 == 0) done[warp] = t + 1;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             acc6 += __shfl_xor_sync(0xffffffffu, acc6, off);
             acc12 += __shfl_xor_sync(0xffffffffu, acc12, off);
         }
-        double *rbuf = red + (t & 1) * nwarps * 9;
-        if ((threadIdx.x & 31) == 0) { rbuf[warp * 9] = acc12; rbuf[warp * 9 + 1] = acc6; }
-        __syncthreads();                       // also orders this half-sweep's position writes before the next reads
-        if (threadIdx.x < 9) {
-            double t12 = 0, t6 = 0;
-            for (int wv = 0; wv < nwarps; ++wv) { t12 += rbuf[wv * 9]; t6 += rbuf[wv * 9 + 1]; }
-            double v[9];
-            lj_nine(t6, t12, v);
-            partial[(((uint64_t) chain * nsub + t) * gridDim.x + blockIdx.x) * 9 + threadIdx.x] = v[threadIdx.x];
+        if (lane32 == 0) {
+            double2 *dst = reinterpret_cast<double2 *>(partial) + ((uint64_t) chain * nsub + t) * nslots + (size_t) blockIdx.x * nwarps + warp;
+            *dst = make_double2(acc12, acc6);
         }
     }
+    __syncthreads();
 
     // ---- write back the owned particles
     double *dst = S.r_out + (uint64_t) chain * S.N;
@@ -371,6 +392,31 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
     }
 }
 
+// Sum of the per-warp (s12, s6) pairs of one half-sweep over all slots, in a fixed order, expanded to the nine
+// deltas -> tsum[chain][t][9].  grid (nsub, nchains), 256 threads.
+static __global__ void __launch_bounds__(256) k_sweep_reduce2(const double *partial, int nsub, size_t nslots, double *tsum) {
+    const int t = blockIdx.x, chain = blockIdx.y;
+    const double2 *p = reinterpret_cast<const double2 *>(partial) + ((uint64_t) chain * nsub + t) * nslots;
+    double s12 = 0, s6 = 0;
+    for (size_t i = threadIdx.x; i < nslots; i += 256) { const double2 v = p[i]; s12 += v.x; s6 += v.y; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s12 += __shfl_xor_sync(0xffffffffu, s12, off);
+        s6 += __shfl_xor_sync(0xffffffffu, s6, off);
+    }
+    __shared__ double red[8][2];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s12; red[threadIdx.x >> 5][1] = s6; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t12 = 0, t6 = 0;
+        for (int wv = 0; wv < 8; ++wv) { t12 += red[wv][0]; t6 += red[wv][1]; }
+        double v[9];
+        lj_nine(t6, t12, v);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) tsum[((uint64_t) chain * nsub + t) * 9 + k] = v[k];
+    }
+}
+
 // After a k_sweep launch: fold the per-tile deltas into the running totals half-sweep by half-sweep
 // (fixed summation order -> reproducible) and sample the twelve sums once per half-sweep
 // (updateThermo :1941-1961 with l constant).
@@ -381,47 +427,45 @@ __device__ __forceinline__ void cb_sample(double (&a)[12], const double *cur, do
     a[10] += HV; a[11] += HV * HV;
 }
 
-// presample != 0: one extra sample of the current totals first (the updateThermo of src/Main.cpp:96).
-// Launched with 9 warps per chain: warp k owns component k; its lanes add the tiles strided and
-// combine with a fixed butterfly, so the result does not depend on scheduling.
-static __global__ void __launch_bounds__(288) k_sweep_finish(const double *partial, int nsub, int ntiles, uint64_t N, const double *l,
-                                                      double *tot /*[nchains][9]*/, double *acc /*[nchains][12]*/, int presample) {
-    const int chain = blockIdx.x;
+// Step 1, grid (nsub, nchains), 9 warps: warp k adds component k of one half-sweep over the tiles (lanes strided,
+// fixed butterfly: the result does not depend on scheduling) -> tsum[chain][t][k].  All half-sweeps of a launch
+// are reduced concurrently; only the running sum over t below is serial.
+static __global__ void __launch_bounds__(288) k_sweep_reduce(const double *partial, int nsub, int ntiles, double *tsum) {
+    const int t = blockIdx.x, chain = blockIdx.y;
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ double cur[9];
-    __shared__ double series[3][64];                     // E, Vir, HV after each half-sweep, 64 at a time
-    if (lane == 0) cur[k] = tot[chain * 9 + k];
-    __syncthreads();
+    const double *p = partial + (((uint64_t) chain * nsub + t) * ntiles) * 9 + k;
+    double s = 0;
+    for (int b = lane; b < ntiles; b += 32) s += p[(uint64_t) b * 9];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) tsum[((uint64_t) chain * nsub + t) * 9 + k] = s;
+}
+
+// Step 2, one warp per chain: running totals over the half-sweeps and one sample of the twelve sums per half-sweep.
+// presample != 0: one extra sample of the current totals first (the updateThermo of src/Main.cpp:96).
+static __global__ void __launch_bounds__(32) k_sweep_finish(const double *tsum, int nsub, uint64_t N, const double *l,
+                                                            double *tot /*[nchains][9]*/, double *acc /*[nchains][12]*/, int presample) {
+    extern __shared__ double ts[];                        // [nsub][9]
+    const int chain = blockIdx.x, lane = threadIdx.x;
+    for (int i = lane; i < nsub * 9; i += 32) ts[i] = tsum[(uint64_t) chain * nsub * 9 + i];
+    __syncwarp();
+    double mine = lane < 9 ? tot[chain * 9 + lane] : 0.0;     // lane k carries component k
     double a[12];
     const double lbox = l[chain];
-    if (threadIdx.x == 0) {
+    if (lane == 0)
         for (int q = 0; q < 12; ++q) a[q] = acc[chain * 12 + q];
-        if (presample) cb_sample(a, cur, (double) N, lbox);
+    double c3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (presample) {
+        c3[0] = __shfl_sync(0xffffffffu, mine, 0); c3[1] = __shfl_sync(0xffffffffu, mine, 1); c3[6] = __shfl_sync(0xffffffffu, mine, 6);
+        if (lane == 0) cb_sample(a, c3, (double) N, lbox);
     }
-    double mine = cur[k];                                 // running total of component k (same in all lanes)
-    for (int t0 = 0; t0 < nsub; t0 += 64) {
-        const int t1 = min(nsub, t0 + 64);
-        for (int t = t0; t < t1; ++t) {
-            const double *p = partial + (((uint64_t) chain * nsub + t) * ntiles) * 9 + k;
-            double s = 0;
-            for (int b = lane; b < ntiles; b += 32) s += p[(uint64_t) b * 9];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            mine += s;
-            if (lane == 0 && (k == 0 || k == 1 || k == 6)) series[k == 0 ? 0 : (k == 1 ? 1 : 2)][t - t0] = mine;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double c3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int t = t0; t < t1; ++t) {
-                c3[0] = series[0][t - t0]; c3[1] = series[1][t - t0]; c3[6] = series[2][t - t0];
-                cb_sample(a, c3, (double) N, lbox);
-            }
-        }
-        __syncthreads();
+    for (int t = 0; t < nsub; ++t) {
+        if (lane < 9) mine += ts[t * 9 + lane];
+        c3[0] = __shfl_sync(0xffffffffu, mine, 0); c3[1] = __shfl_sync(0xffffffffu, mine, 1); c3[6] = __shfl_sync(0xffffffffu, mine, 6);
+        if (lane == 0) cb_sample(a, c3, (double) N, lbox);
     }
-    if (lane == 0) tot[chain * 9 + k] = mine;
-    if (threadIdx.x == 0)
+    if (lane < 9) tot[chain * 9 + lane] = mine;
+    if (lane == 0)
         for (int q = 0; q < 12; ++q) acc[chain * 12 + q] = a[q];
 }
 

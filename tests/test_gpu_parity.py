@@ -195,15 +195,16 @@ def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
         assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
 
 
-@pytest.mark.parametrize("lanes", ["1", "2", "4", "2-sliced"])
+@pytest.mark.parametrize("variant", ["unroll4", "unroll8", "sliced"])
 @pytest.mark.parametrize("name", ["small", "ljcut_nbn", "nlt"])
-def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, lanes, monkeypatch):
-    """JMM_ARITH_FAST (prod.cuh, fastlj.cuh): one reciprocal per partner, r^-6/r^-12 differences only, 1, 2 or 4
-    lanes per chain (40 chains = a ragged last tile for 2 and 4).  Positions and the accept/reject sequence must
-    equal the oracle's exactly; the nine totals and twelve sums agree to 1e-12."""
+def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, variant, monkeypatch):
+    """JMM_ARITH_FAST (prod.cuh, fastlj.cuh): one reciprocal per partner, r^-6/r^-12 differences only, 4 or 8
+    partners in flight, plain and time-sliced launches (40 chains = a ragged last tile).  Positions and the
+    accept/reject sequence must equal the oracle's exactly; the nine totals and twelve sums agree to 1e-12."""
     monkeypatch.setenv("JMM_COOP_G", "0")
-    monkeypatch.setenv("JMM_PROD_G", lanes.split("-")[0])
-    if lanes.endswith("sliced"):
+    if variant == "unroll4":
+        monkeypatch.setenv("JMM_PROD_UNROLL", "4")
+    if variant == "sliced":
         monkeypatch.setenv("JMM_FORCE_SLICE", "1")
         monkeypatch.setenv("JMM_SLICE_CHUNK", "7")
     d = DECKS[name]
@@ -323,12 +324,16 @@ def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C, arith, m
 
 
 @pytest.mark.parametrize("name", ["small", "std", "ljcut_nbn"])
-@pytest.mark.parametrize("engine", ["prod", "generic", "table"])
+@pytest.mark.parametrize("engine", ["prod", "sliced", "generic", "table"])
 def test_histograms_match_oracle_integers(J, O, name, engine, monkeypatch):
-    """rho(x) and g(x) counts (fgrho/qagrho/ugrho) accumulated lazily on the device must equal, integer for integer,
-    the oracle's add-the-whole-histogram-every-step accumulation — at every read-out, for every chain."""
+    """rho(x) and g(x) counts (fgrho/qagrho/ugrho) kept on the device as (count, sum of delta*u) by RED instructions,
+    with warp-cooperative refills, must equal, integer for integer, the oracle's add-the-whole-histogram-every-step
+    accumulation — at every read-out, for every chain (21 chains: owners and helper lanes share a warp)."""
     if engine == "generic":
         monkeypatch.setenv("JMM_NO_PROD", "1")
+    if engine == "sliced":                  # persistent time-sliced launch: a chain changes SM between chunks
+        monkeypatch.setenv("JMM_FORCE_SLICE", "1")
+        monkeypatch.setenv("JMM_SLICE_CHUNK", "7")
     d = DECKS[name]
     C, id0 = 21, 300
     geo = dict(rhonb=48, rbw=0.5, gns=4, gnb=70, gsw=6.0, gbw=0.25)
@@ -365,3 +370,66 @@ def test_histograms_match_oracle_integers(J, O, name, engine, monkeypatch):
         s = h.get_state()
     for c, oc in enumerate(chains):
         assert bits_equal(s["r"][c], oc.r)
+
+
+@pytest.mark.parametrize("case", ["philox-prod", "philox-bond", "taus2-table", "philox-hist", "checkerboard"])
+def test_checkpoint_restart_is_an_exact_continuation(J, O, case, tmp_path, monkeypatch):
+    """jmm_checkpoint_save / jmm_checkpoint_load (N4): a run stopped after n1 steps and resumed in a NEW handle must
+    end in the same bits as the uninterrupted run — positions, box, totals, sums, counters, step sizes, histogram
+    counts.  (The reference's RESTART re-seeds and forgets maxStep/dAcc: src/jmmMCState.cpp:572-765.)"""
+    from jmmonedmc_b200.capi import config
+    ck = tmp_path / "state.jmmckpt"
+    if case == "checkerboard":
+        N = 6000
+        mk = lambda: J.Handle(config(N=N, pot=J.POT_LJCUT, nbn=4, cutoff=5.0, ensemble=J.ENS_NLT, L=N * 1.12, T=0.9, maxStep=0.12,
+                                     seed=92847, nchains=2, chain_id0=3, mode=J.MODE_CHECKERBOARD, arith=J.ARITH_FAST))
+        run = lambda h, n: h.sweep(n)
+        n1, n2 = 7, 9
+    else:
+        if case == "philox-prod":
+            monkeypatch.setenv("JMM_COOP_G", "0")
+        deck = DECKS["std"] if case == "philox-bond" else DECKS["small"]
+        kw = dict(rng_kind=J.RNG_TAUS2, mode=J.MODE_TABLE) if case == "taus2-table" else dict(rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE)
+        mk = lambda: J.Handle(jmm_config_from_deck(J, deck, adapt=J.ADAPT_DEVICE, nchains=45, chain_id0=11, **kw))
+        run = lambda h, n: h.step(n)
+        n1, n2 = 1234, 2345                      # crosses DADJ/VADJ 1000 and an ECheck on both sides of the cut
+    geo = dict(rhonb=48, rbw=0.5, gns=4, gnb=70, gsw=6.0, gbw=0.25)
+    hist = case == "philox-hist"
+
+    def state(h):
+        s = h.get_state()
+        out = [s["r"], s["l"], s["totals"], s["accum"], s["counters"]]
+        if case != "checkerboard":
+            out += list(h.get_step_sizes())
+        if hist:
+            out += list(h.take_histograms())
+        return out
+
+    with mk() as h:                              # the uninterrupted run
+        if hist:
+            h.enable_histograms(**geo)
+        h.start(); run(h, n1); run(h, n2)
+        want = state(h)
+    with mk() as h:                              # first leg, checkpoint
+        if hist:
+            h.enable_histograms(**geo)
+        h.start(); run(h, n1)
+        h.checkpoint_save(ck)
+    with mk() as h:                              # second leg in a fresh handle: no start(), state comes from the file
+        if hist:
+            h.enable_histograms(**geo)
+        h.checkpoint_load(ck)
+        assert h.step_number == n1
+        run(h, n2)
+        got = state(h)
+    for a, b in zip(want, got):
+        a, b = np.asarray(a), np.asarray(b)
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint64) if a.dtype == np.float64 else a,
+                                                     b.view(np.uint64) if b.dtype == np.float64 else b)
+    # a handle with another configuration refuses the file
+    with J.Handle(jmm_config_from_deck(J, DECKS["nlt"], nchains=45)) as h:
+        with pytest.raises(J.JmmError):
+            h.checkpoint_load(ck)
+    with mk() as h:
+        with pytest.raises(J.JmmError):
+            h.checkpoint_load(tmp_path / "missing.jmmckpt")
