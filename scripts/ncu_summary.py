@@ -34,14 +34,19 @@ def main():
         v, u = g(k)
         if v != "":
             print(f"  {k:70s} {v} {u}")
+    stalls = []
     for h in hdr:
-        if "issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+        if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
             try:
-                x = float(d[h][0].replace(",", ""))
+                stalls.append((float(d[h][0].replace(",", "")), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
             except ValueError:
                 continue
-            if x > 2:
-                print(f"  stall {h[len('smsp__warp_issue_stalled_'):-len('_per_warp_active.pct')]:32s} {x:6.1f} %")
+    for x, name in sorted(stalls, reverse=True)[:8]:
+        print(f"  stall {name:32s} {x:6.3f} warps per issue-active cycle")
+    for k in ("sm__cycles_active.avg", "sm__cycles_active.max", "sm__cycles_elapsed.avg", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"):
+        v, u = g(k)
+        if v != "":
+            print(f"  {k:70s} {v} {u}")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     h2 = next(r for r in rows if "Source" in r and "Instructions Executed" in r)
