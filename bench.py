@@ -54,7 +54,7 @@ EXTRA = {
                per_step=64, flop=33 * 8 + 37, bytes_per_trial=16.0),
     "c4": dict(desc="C4: RunJobs-style sweep, 65,536 chains (256x256 P,T grid in [0.1,1]) x N=80, LJ, NBN -1, NPT, RELAX",
                kind="chains", N=80, nchains=65536, pot="LJ", nbn=-1, cutoff=math.inf, maxStep=0.1, maxdl=2.0, eci=10000,
-               mdai=10 ** 6, mvai=10 ** 6, seed=92847, relax=1, per_step=250, flop=33 * 79 + 37,
+               mdai=10 ** 6, mvai=10 ** 6, seed=92847, relax=1, per_step=2000, flop=33 * 79 + 37,
                bytes_per_trial=None),
     "c5": dict(desc="C5: 8 chains x N=262,144, LJ, NBN 64 (128 partners), NLT (L=1.12N), T=0.9, checkerboard half-sweeps",
                kind="sweep", N=1 << 18, nchains=8, pot="LJ", nbn=64, cutoff=math.inf, T=0.9, maxStep=0.12, seed=92847,
@@ -427,7 +427,7 @@ def measure_extra(workload: str, arith: str, hist: bool, steps: int, warmup: int
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": {"workload": w["desc"], "per_step": w["per_step"], "arith": arith, "histograms": bool(hist),
                                                 "l2": "flushed between timed iterations (256 MiB fill)"},
-                "gpu_launches": int(launches), "clocks": clocks,
+                "gpu_launches": int(launches), "clocks": clocks, "ms_steps": [round(a.elapsed_time(b), 4) for a, b in ev],
                 "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": tf / fp64_peak if fp64_peak > 0 else None, "flop_per_trial": w["flop"],
                              "kernel_ms_last_call": k_ms, "traffic": None,

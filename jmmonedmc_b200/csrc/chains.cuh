@@ -425,7 +425,7 @@ __device__ __forceinline__ uint8_t displacement_trial(Chain<POT> &ch, uint32_t n
 
 // qavLJ :1648-1730 (POT LJ and NBN < 0 only: E12 ~ s^-12, E6 ~ s^-6)
 template <int POT, bool TABLE, class RNG>
-__device__ __forceinline__ uint8_t volume_trial_scaling(Chain<POT> &ch, double rn, RNG &rng) {
+__device__ __forceinline__ uint8_t volume_trial_scaling(Chain<POT> &ch, double rn, RNG &rng, double *defer_scale = nullptr) {
     static_assert(PotTraits<POT>::NC == 9, "scaling shortcut is LJ only");
     const double dl = (rn - 0.5) * 2 * ch.maxdl;
     const double lRat1 = (ch.l + dl) / ch.l;
@@ -448,7 +448,8 @@ __device__ __forceinline__ uint8_t volume_trial_scaling(Chain<POT> &ch, double r
     ch.tot[5] = lRat7 * ch.tot[5];
     ch.tot[3] = lRat13 * ch.tot[3];
     ch.tot[1] = (double) ch.N * ch.T / ch.l + ch.tot[3] - ch.tot[5];                 // :1686
-    scale_positions(ch, lRat1);                                                      // :1692
+    if (defer_scale) *defer_scale = lRat1;                                           // the caller scales (prod.cuh: warp-cooperative)
+    else scale_positions(ch, lRat1);                                                 // :1692
     if (TABLE) {
         const uint64_t np = (uint64_t) ch.N * (ch.N - 1) / 2;
         for (uint64_t q = 0; q < np; ++q) ch.rij[q * ch.ts] = lRat1 * ch.rij[q * ch.ts];   // :1699
@@ -458,7 +459,7 @@ __device__ __forceinline__ uint8_t volume_trial_scaling(Chain<POT> &ch, double r
 
 // fav :2161-2293
 template <int POT, bool TABLE, class RNG>
-__device__ __forceinline__ uint8_t volume_trial_full(Chain<POT> &ch, double rn, RNG &rng) {
+__device__ __forceinline__ uint8_t volume_trial_full(Chain<POT> &ch, double rn, RNG &rng, double *defer_scale = nullptr) {
     constexpr int NC = PotTraits<POT>::NC;
     const double dl = (rn - 0.5) * 2 * ch.maxdl;
     const double lnew = ch.l + dl;
@@ -473,7 +474,8 @@ __device__ __forceinline__ uint8_t volume_trial_full(Chain<POT> &ch, double rn, 
     ch.l = ch.l + dl;
 #pragma unroll
     for (int k = 0; k < NC; ++k) ch.tot[k] = t[k];
-    scale_positions(ch, lRat1);
+    if (defer_scale && !TABLE) *defer_scale = lRat1;
+    else scale_positions(ch, lRat1);
     table_from_positions<POT, TABLE>(ch);
     return kLogVolume | kLogAccepted;
 }

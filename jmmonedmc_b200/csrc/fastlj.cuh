@@ -29,23 +29,25 @@ __device__ __forceinline__ double rcp_cubic(double x) {
     return __fma_rn(y, e2, y);
 }
 
-// `d <= cutoff` for cutoff >= 0 without touching the fp64 pipe: for non-NaN doubles the signed 64-bit integer
-// order of the bit patterns agrees with the numeric order whenever the right-hand side is non-negative
-// (every negative double, -0.0 included, has the sign bit set and compares below).
-__device__ __forceinline__ bool le_nonneg(double d, long long cutoff_bits) {
-    return __double_as_longlong(d) <= cutoff_bits;
+// Cutoff of phiLJcut: a pair term counts iff `d <= cutOff` on the SIGNED distance (src/pot.cpp:53).  The test is one
+// DSETP (the fp64 pipe has slack wherever LJcut is used; a 64-bit integer compare is two issue slots), and a term is
+// masked by clearing the HIGH word of its sixth power: what is left is a subnormal < 2^-1042, so that
+// (A - B) inv and (A + B) inv round to exactly the values they have with a true zero whenever the other term is
+// alive, and to (sub)normal noise below 1e-300 when both are masked — one SEL instead of two.
+__device__ __forceinline__ double keep_if(double x, bool keep) {
+    return __hiloint2double(keep ? __double2hiint(x) : 0, __double2loint(x));
 }
 
 // One partner.  a, b = old and new SIGNED distance in the reference's orientation (r[j]-r[i], j > i by index).
 template <bool CUT>
-__device__ __forceinline__ void lj_partner(double a, double b, long long cutoff_bits, double &s6, double &s12) {
+__device__ __forceinline__ void lj_partner(double a, double b, double cutoff, double &s6, double &s12) {
     const double a2 = a * a, b2 = b * b;
     double A = a2 * a2 * a2, B = b2 * b2 * b2;
     const double inv = rcp_cubic(A * B);
     if constexpr (CUT) {
         // new term b^-6 = A inv lives in A, old term a^-6 = B inv lives in B
-        A = le_nonneg(b, cutoff_bits) ? A : 0.0;
-        B = le_nonneg(a, cutoff_bits) ? B : 0.0;
+        A = keep_if(A, b <= cutoff);
+        B = keep_if(B, a <= cutoff);
     }
     const double d6 = (A - B) * inv;
     const double t6 = (A + B) * inv;

@@ -52,6 +52,7 @@ struct jmm_handle {
     double *cb_tot = nullptr, *cb_acc = nullptr;
     unsigned long long *cb_counts = nullptr;
     uint64_t halfsweeps = 0;
+    unsigned int *cb_tile_done = nullptr;   // [nchains] tiles of the running k_sweep_fast launch that have finished
     std::vector<void *> allocs;
 };
 

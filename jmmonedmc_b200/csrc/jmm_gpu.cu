@@ -245,6 +245,7 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
         CKH(dalloc(h, &h->cb_r[0], C * N)); CKH(dalloc(h, &h->cb_r[1], C * N));
         CKH(dalloc(h, &h->cb_tot, C * 9)); CKH(dalloc(h, &h->cb_acc, C * 12));
         CKH(dalloc(h, &h->cb_counts, C * 2));
+        CKH(dalloc(h, &h->cb_tile_done, C));
         // lattice, chain-major: same formula as :561 (k_lattice with nchains = 1 per chain)
         for (uint64_t c = 0; c < C; ++c) {
             k_lattice<<<nblk(N, 256), 256, 0, h->stream>>>(h->cb_r[0] + c * N, S.l + c, 1, N);
@@ -901,25 +902,17 @@ extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *r
 // checkerboard sweeps
 // ------------------------------------------------------------------------------------------------
 
-static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
-    SweepShape s{};
-    const int nbn = h->cfg.nbn, ncol = nbn + 1;
-    const uint64_t N = h->S.N, C = h->S.nchains;
-    // fast-arithmetic kernels fit two CTAs per SM (<= 64 registers): more warps to hide the reciprocal latency
-    const bool fast = h->cfg.arith == JMM_ARITH_FAST && h->cfg.pot != JMM_POT_HARMONIC;
-    if (fast) {
-        // lanes per trial: the largest power of two <= min(NBN, 32) that still leaves every resident thread
-        // (148 SMs x 1024) a trial of its own per half-sweep
-        const uint64_t trials = std::max<uint64_t>(1, C * ((N + ncol - 1) / ncol));
-        int g = 1;
-        while (g * 2 <= std::min(nbn, 32) && trials * (uint64_t) (g * 2) <= 148ull * 1024) g *= 2;
-        if (const char *e = getenv("JMM_SWEEP_G")) { const int v = atoi(e); if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) g = v; }
-        s.G = g;
-    } else s.G = nbn >= 16 ? 32 : 1;
-    const int budget = (fast ? 100 : 200) * 1024 / 8 - 1024;   // doubles of shared memory for the window
-    // k CTAs per SM and ONE wave: tiles per chain = m * floor(148 k / nchains), the smallest m whose tile
-    // (plus halos) fits in shared memory.  152 CTAs on 148 SMs would cost a whole second wave.
-    const uint64_t base = std::max<uint64_t>(1, (fast ? 296 : 148) / C);
+static int env_int(const char *name, int fallback) {
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : fallback;
+}
+
+// Tiling of one launch for a given number k of CTAs per SM: k CTAs per SM and ONE wave (152 CTAs on 148 SMs would
+// cost a whole second wave): tiles per chain = m * floor(148 k / nchains), the smallest m whose tile plus halos fits
+// in `budget` doubles of shared memory; nsub is halved until the redundantly recomputed halo is below ~25 % of the tile.
+static void sweep_tiling(uint64_t N, uint64_t C, int nbn, int ncol, uint64_t ctas, int budget, uint64_t want_sub,
+                         int *tile_out, int *halo_out, int *nsub_out) {
+    const uint64_t base = std::max<uint64_t>(1, ctas / C);
     int nsub = (int) std::min<uint64_t>(want_sub, 64);
     int tile = 0, halo = 0;
     for (;;) {
@@ -931,33 +924,81 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
             t += t & 1;
             if ((int64_t) t + 2 * halo <= budget || t <= (uint64_t) 4 * ncol) { tile = (int) t; break; }
         }
-        // keep the redundantly recomputed halo below ~25 % of the tile
         if (tile >= 8 * halo || nsub == 1) break;
         nsub = std::max(1, nsub / 2);
     }
     if (tile < 2) tile = 2;
-    s.tile = tile; s.halo = halo; s.nsub = nsub;
-    // trials per half-sweep per tile (first half-sweep of a launch: the halos are still tried)
-    const int per_sub = (tile + 2 * std::max(0, halo - nbn) + ncol - 1) / ncol;
+    *tile_out = tile; *halo_out = halo; *nsub_out = nsub;
+}
+
+static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
+    SweepShape s{};
+    const int nbn = h->cfg.nbn, ncol = nbn + 1;
+    const uint64_t N = h->S.N, C = h->S.nchains;
+    const bool fast = h->cfg.arith == JMM_ARITH_FAST && h->cfg.pot != JMM_POT_HARMONIC;
     s.fast = fast ? 1 : 0;
-    if (fast) {
-        // warp w owns the trials [wK, (w+1)K) of every half-sweep, K = rounds * (32/G); a whole number of rounds,
-        // so that no group idles through a last partial round
-        const int gpw = 32 / s.G;
-        const int rounds = std::max(1, (per_sub * s.G + 511) / 512);
-        const int K = rounds * gpw;
-        const int nwarps = std::max(2, std::min(16, (per_sub + K - 1) / K));
-        s.rounds = (per_sub + nwarps * gpw - 1) / (nwarps * gpw);        // >= rounds when nwarps was clipped
-        s.threads = nwarps * 32;
-        // colour offsets drift by at most nsub*NBN + ncol over the launch; reads reach NBN either side
-        s.rad = 1 + (nsub * nbn + ncol + 2 * nbn) / (s.rounds * gpw * ncol);
-        s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) nsub * 4 + (size_t) nwarps * 4 + 32;
+    if (!fast) {
+        s.G = nbn >= 16 ? 32 : 1;
+        sweep_tiling(N, C, nbn, ncol, 148, 200 * 1024 / 8 - 1024, want_sub, &s.tile, &s.halo, &s.nsub);
+        const int per_sub = (s.tile + 2 * std::max(0, s.halo - nbn) + ncol - 1) / ncol;
+        int threads = s.G == 1 ? per_sub : per_sub * 32;
+        threads = std::min(512, std::max(64, ((threads + 31) / 32) * 32));
+        s.threads = threads;
+        s.smem = (size_t) (s.tile + 2 * s.halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) s.nsub * 8 + 16;
         return s;
     }
-    int threads = s.G == 1 ? per_sub : per_sub * 32;
-    threads = std::min(512, std::max(64, ((threads + 31) / 32) * 32));
-    s.threads = threads;
-    s.smem = (size_t) (tile + 2 * halo) * 8 + (size_t) 2 * (threads / 32) * 9 * 8 + (size_t) nsub * 8 + 16;
+    // ---- k_sweep_fast (<= 64 registers, so up to 32 warps per SM whatever the CTA size)
+    // lanes per trial: the largest power of two <= min(NBN, 32) that still leaves every resident thread
+    // (148 SMs x 1024) a trial of its own per half-sweep
+    const uint64_t trials = std::max<uint64_t>(1, C * ((N + ncol - 1) / ncol));
+    int g = 1;
+    while (g * 2 <= std::min(nbn, 32) && trials * (uint64_t) (g * 2) <= 148ull * 1024) g *= 2;
+    {
+        const int v = env_int("JMM_SWEEP_G", 0);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) g = v;
+    }
+    s.G = g;
+    const int gpw = 32 / g;
+    // The warps of a CTA advance in lock-step with their neighbours (sweep.cuh), so the SM runs at the pace of its
+    // fullest sub-partition: warps go to the four sub-partitions round-robin by warp index, hence a CTA gets a
+    // multiple of four warps.  Candidates: k = 1, 2, 4 CTAs per SM x 4, 8, ... warps; score = useful lanes x owned
+    // (non-halo) share x a latency-hiding term in the resident warps per sub-partition x the share of a half-sweep
+    // that is not the neighbour hand-shake.
+    const int k_env = env_int("JMM_SWEEP_K", 0), w_env = env_int("JMM_SWEEP_WARPS", 0);
+    const uint64_t sub_cap = (uint64_t) std::max(1, std::min(64, env_int("JMM_SWEEP_NSUB", 64)));
+    double best = -1.0;
+    for (int k = 1; k <= 4; k *= 2) {
+        if (k_env && k != k_env) continue;
+        int tile, halo, nsub;
+        // shared memory: 200 KB / k, less the per-warp sums [nsub][nwarps][2] and the other small arrays (<= 40 KB / k)
+        sweep_tiling(N, C, nbn, ncol, 148ull * k, (160 / k) * 1024 / 8, std::min(want_sub, sub_cap), &tile, &halo, &nsub);
+        const int per_sub = (tile + 2 * std::max(0, halo - nbn) + ncol - 1) / ncol;    // first half-sweep: halos still tried
+        const double owned = (double) tile / (double) (tile + std::max(0, halo - nbn));   // mean over the half-sweeps
+        const double x = (double) (((N + tile - 1) / tile) * C) / (148.0 * k);            // CTAs / resident CTA slots
+        const double fill = x <= 1.0 ? x : x / ceil(x);
+        for (int nw = 4; nw * k <= 32; nw += 4) {
+            if (w_env && nw != w_env && !(w_env % 4)) continue;
+            const int rounds = (per_sub + nw * gpw - 1) / (nw * gpw);
+            const double lanes = (double) per_sub / (double) (rounds * nw * gpw);
+            const double wps = (double) (nw * k) / 4.0;                               // warps per sub-partition
+            const double hide = wps / (wps + 2.0);
+            const double work = rounds * (120.0 + 40.0 * ((2 * nbn + g - 1) / g));       // warp instructions per half-sweep
+            const double score = fill * lanes * owned * hide * work / (work + 80.0);
+            if (score > best) {
+                best = score;
+                s.tile = tile; s.halo = halo; s.nsub = nsub; s.rounds = rounds; s.threads = nw * 32;
+            }
+        }
+    }
+    if (w_env && (w_env % 4)) {          // experiments: any warp count
+        const int per_sub = (s.tile + 2 * std::max(0, s.halo - nbn) + ncol - 1) / ncol;
+        s.threads = std::min(32, std::max(2, w_env)) * 32;
+        s.rounds = (per_sub + (s.threads / 32) * gpw - 1) / ((s.threads / 32) * gpw);
+    }
+    // colour offsets drift by at most nsub*NBN + ncol over the launch; reads reach NBN either side
+    s.rad = 1 + (s.nsub * nbn + ncol + 2 * nbn) / (s.rounds * gpw * ncol);
+    const size_t nw = (size_t) s.threads / 32;
+    s.smem = (size_t) (s.tile + 2 * s.halo) * 8 + (((size_t) s.nsub + nw + 3) / 4) * 16 + (size_t) s.nsub * nw * 16 + (size_t) s.nsub * 72 + 32;
     return s;
 }
 
@@ -968,14 +1009,14 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
     uint64_t trials = 0;
     h->timed = false;
     uint64_t remaining = n_halfsweeps;
+    tick(h);
     while (remaining) {
         const SweepShape s = sweep_shape(h, remaining);
         const int nsub = (int) std::min<uint64_t>(remaining, (uint64_t) s.nsub);
         const unsigned ntiles = (unsigned) ((N + s.tile - 1) / s.tile);
-        // per-tile deltas [C][nsub][ntiles][9] (k_sweep) or per-warp sums [C][nsub][ntiles*nwarps][2] (k_sweep_fast),
-        // then their sums over the tiles [C][nsub][9]
-        const size_t nslots = (size_t) ntiles * (s.threads / 32);
-        const size_t n_partial = s.fast ? C * (size_t) nsub * nslots * 2 : C * (size_t) nsub * ntiles * 9;
+        // k_sweep: per-tile deltas [C][nsub][ntiles][9], then their sums over the tiles [C][nsub][9] (k_sweep_reduce);
+        // k_sweep_fast: per-tile (s12, s6) [C][nsub][ntiles][2], reduced inside the kernel
+        const size_t n_partial = s.fast ? C * (size_t) nsub * ntiles * 2 : C * (size_t) nsub * ntiles * 9;
         jmm_status st = ensure_partial(h, (n_partial + C * (size_t) nsub * 9) * sizeof(double));
         if (st != JMM_OK) return st;
         double *tsum = h->d_partial + n_partial;
@@ -994,18 +1035,18 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
                 const uint64_t col = ((uint64_t) b.w[0] * (uint64_t) W.ncol) >> 32;
                 if (col < N) trials += (N - col + W.ncol - 1) / W.ncol;
             }
-        tick(h);
         CK(jmm_launch_sweep(h, s, W, h->halfsweeps, nsub, ntiles));
-        if (s.fast) k_sweep_reduce2<<<dim3((unsigned) nsub, (unsigned) C), 256, 0, h->stream>>>(h->d_partial, nsub, nslots, tsum);
-        else k_sweep_reduce<<<dim3((unsigned) nsub, (unsigned) C), 288, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, tsum);
-        k_sweep_finish<<<(unsigned) C, 32, (size_t) nsub * 9 * sizeof(double), h->stream>>>(tsum, nsub, N, h->S.l, h->cb_tot, h->cb_acc, 0);
-        h->launches += 2;
-        CK(cudaGetLastError());
-        tock(h);
+        if (!s.fast) {
+            k_sweep_reduce<<<dim3((unsigned) nsub, (unsigned) C), 288, 0, h->stream>>>(h->d_partial, nsub, (int) ntiles, tsum);
+            k_sweep_finish<<<(unsigned) C, 32, (size_t) nsub * 9 * sizeof(double), h->stream>>>(tsum, nsub, N, h->S.l, h->cb_tot, h->cb_acc, 0);
+            h->launches += 2;
+            CK(cudaGetLastError());
+        }
         h->cb_cur ^= 1;
         h->halfsweeps += nsub;
         remaining -= nsub;
     }
+    tock(h);
     if (trials_out) *trials_out = trials;
     return JMM_OK;
 }

@@ -82,7 +82,7 @@ __device__ __forceinline__ uint8_t prod_displacement_fast(Chain<POT> &ch, double
     const uint32_t lo = (ch.nbn < 0 || (uint32_t) ch.nbn > nm) ? 0u : nm - (uint32_t) ch.nbn;
     const uint32_t hi = (ch.nbn < 0 || nm + (uint32_t) ch.nbn > N - 1) ? N - 1 : nm + (uint32_t) ch.nbn;
     rs[nm * kTile] = kFarAway;
-    const long long cb = __double_as_longlong(ch.cutoff);
+    const double cb = ch.cutoff;
     double s6 = 0, s12 = 0;
     const double *rp = rs + lo * kTile;
 #pragma unroll (UNROLL)
@@ -149,13 +149,30 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
         const double rn = rng.rn();
         const double maxStep_used = ch.maxStep;
         uint8_t flags;
+        double vscale = 0.0;                                  // != 0: an accepted volume move still has to scale the positions
         if (nm < ch.N) {
             if constexpr (ARITH == kArithFast) flags = prod_displacement_fast<POT, UNROLL>(ch, rs, nm, rn, rng.ran());
             else flags = prod_displacement_ref<POT>(ch, rs, rs, nm, rn, rng.ran());
         } else {
             if constexpr (POT == kPotLJ) {
-                flags = scaling_volume ? volume_trial_scaling<POT, false>(ch, rn, rng) : volume_trial_full<POT, false>(ch, rn, rng);
-            } else flags = volume_trial_full<POT, false>(ch, rn, rng);
+                flags = scaling_volume ? volume_trial_scaling<POT, false>(ch, rn, rng, &vscale)
+                                       : volume_trial_full<POT, false>(ch, rn, rng, &vscale);
+            } else flags = volume_trial_full<POT, false>(ch, rn, rng, &vscale);
+        }
+        {   // r *= s of an accepted volume move (qavLJ :1692, fav :2264-2266), done by the whole warp: a third of the
+            // steps have a volume trial in some lane, and one lane walking its N positions alone (N dependent
+            // load-multiply-store round trips while 31 lanes idle) was 10 % of the stall samples of C4
+            // (profiles/r01m_c4_k_chains_step_prod_sliced_fast.txt).  Same products, so the same positions.
+            __syncwarp();
+            unsigned pend = __ballot_sync(0xffffffffu, vscale != 0.0);
+            while (pend) {
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1;
+                const double f = __shfl_sync(0xffffffffu, vscale, src);
+                double *col = smem + src;
+                for (uint32_t i = threadIdx.x; i < ch.N; i += kTile) col[i * kTile] = col[i * kTile] * f;
+            }
+            __syncwarp();
         }
         if (H.ucount) hist_after_trial<POT, false>(H, c, ch, nm, rn, maxStep_used, flags, scaling_volume, hist_u, lead, 0xffffffffu);
         if (--eci_left == 0) { energy_check<POT, false>(ch); eci_left = eci32; }

@@ -37,6 +37,28 @@ JMM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     return r;
 }
 
+// The same block with the ten round keys precomputed (kernel parameters: the xor takes them as constant-bank
+// operands, which removes the twenty key additions per block from the instruction stream).
+struct PhiloxKeys { uint32_t k[20]; };
+
+JMM_HD PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
+    PhiloxKeys K;
+    for (int round = 0; round < 10; ++round) { K.k[2 * round] = k0; K.k[2 * round + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return K;
+}
+
+JMM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &K) {
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ K.k[2 * round], n2 = hi0 ^ c3 ^ K.k[2 * round + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    Philox4 r; r.w[0] = c0; r.w[1] = c1; r.w[2] = c2; r.w[3] = c3;
+    return r;
+}
+
 // stream tags in counter word 3 (keeps the three uses of one (seed) key disjoint)
 constexpr uint32_t kTagTrial = 0u;            // (step, chain): one block per Step()
 constexpr uint32_t kTagParticle = 0x80000000u; // | chain: (half-sweep, particle) in checkerboard mode

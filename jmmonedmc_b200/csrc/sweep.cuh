@@ -223,6 +223,41 @@ __global__ void __launch_bounds__(512, 1) k_sweep(SweepDev S, uint64_t step0, in
     }
 }
 
+// After a k_sweep launch: fold the per-tile deltas into the running totals half-sweep by half-sweep
+// (fixed summation order -> reproducible) and sample the twelve sums once per half-sweep
+// (updateThermo :1941-1961 with l constant).
+__device__ __forceinline__ void cb_sample(double (&a)[12], const double *cur, double N, double lbox) {
+    const double rho = N / lbox, E = cur[0], Vir = cur[1], HV = cur[6];
+    a[0] += rho; a[1] += rho * rho; a[2] += lbox; a[3] += lbox * lbox;
+    a[4] += E; a[5] += E * E; a[6] += lbox * E; a[7] += Vir; a[8] += Vir * Vir; a[9] += E * Vir;
+    a[10] += HV; a[11] += HV * HV;
+}
+
+
+// One warp: running totals over the half-sweeps of a launch (ts[t][9] = the nine deltas of half-sweep t) and one
+// sample of the twelve sums per half-sweep.  presample != 0: one extra sample of the current totals first (the
+// updateThermo of src/Main.cpp:96).  Lane k < 9 carries component k, lane 0 the twelve sums.
+__device__ __forceinline__ void sweep_finish_warp(const double *ts, int nsub, uint64_t N, double lbox, double *tot /*[9]*/,
+                                                  double *acc /*[12]*/, int presample, int lane) {
+    double mine = lane < 9 ? tot[lane] : 0.0;
+    double a[12];
+    if (lane == 0)
+        for (int q = 0; q < 12; ++q) a[q] = acc[q];
+    double c3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (presample) {
+        c3[0] = __shfl_sync(0xffffffffu, mine, 0); c3[1] = __shfl_sync(0xffffffffu, mine, 1); c3[6] = __shfl_sync(0xffffffffu, mine, 6);
+        if (lane == 0) cb_sample(a, c3, (double) N, lbox);
+    }
+    for (int t = 0; t < nsub; ++t) {
+        if (lane < 9) mine += ts[t * 9 + lane];
+        c3[0] = __shfl_sync(0xffffffffu, mine, 0); c3[1] = __shfl_sync(0xffffffffu, mine, 1); c3[6] = __shfl_sync(0xffffffffu, mine, 6);
+        if (lane == 0) cb_sample(a, c3, (double) N, lbox);
+    }
+    if (lane < 9) tot[lane] = mine;
+    if (lane == 0)
+        for (int q = 0; q < 12; ++q) acc[q] = a[q];
+}
+
 // JMM_ARITH_FAST variant of k_sweep for the LJ family (fastlj.cuh: one reciprocal per partner, 18 fp64-pipe
 // instructions for the old and the new pair term together; only s6 = sum(b^-6 - a^-6) and s12 are carried).
 // Same staging, same tiling, same random numbers, same trials as k_sweep; what differs:
@@ -241,13 +276,19 @@ __global__ void __launch_bounds__(512, 1) k_sweep(SweepDev S, uint64_t step0, in
 //     acquire by __threadfence_block): read-after-write and write-after-read are both covered, and a slow warp
 //     only holds up its neighbours.  With the __syncthreads version "barrier" was the second largest stall reason
 //     (profiles/r01_c3_k_sweep_fast.txt).
-//   * per half-sweep every warp writes its two sums to partial[chain][t][tile*nwarps + warp][2]; k_sweep_reduce2
-//     adds them over all slots and expands them to the nine deltas.
+//   * the reductions are part of the kernel (no follow-up launches): per half-sweep every warp leaves its two sums
+//     in shared memory; at the end the CTA adds them over its warps -> partial[chain][t][tile][2], and the LAST CTA
+//     of a chain to finish (a counter per chain) adds the tiles, expands the nine deltas and runs the
+//     totals/twelve-sums recurrence of k_sweep_finish.  Every sum has a fixed order, so results do not depend on
+//     scheduling.
 // G, rounds and rad are chosen by the host (jmm_gpu.cu: sweep_shape).
-template <int POT, int G>
-__global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step0, int nsub, int tile, int halo, int rounds, int rad,
-                                                       double *partial /*[nchains][nsub][ntiles*nwarps][2]*/,
-                                                       unsigned long long *counts /*[nchains][2] accepted, trials*/) {
+// NB > 0: NBN known at compile time (G = 1 only): the partner loop is unrolled completely, 2 NB independent pair terms.
+template <int POT, int G, int NB>
+__global__ void __launch_bounds__(1024, 1) k_sweep_fast(const __grid_constant__ SweepDev S, const __grid_constant__ PhiloxKeys RK, uint64_t step0, int nsub, int tile, int halo, int rounds, int rad,
+                                                       double *partial /*[nchains][nsub][ntiles][2]*/,
+                                                       unsigned long long *counts /*[nchains][2] accepted, trials*/,
+                                                       unsigned int *tile_done /*[nchains], zero between launches*/,
+                                                       double *tot /*[nchains][9]*/, double *acc /*[nchains][12]*/) {
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
     constexpr bool CUT = (POT == kPotLJcut);
     constexpr int GPW = 32 / G;                                       // groups (trials in flight) per warp
@@ -264,7 +305,10 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
     const int wcap = tile + 2 * halo;
     int *firsts = reinterpret_cast<int *>(w + wcap);                  // [nsub] window index of the first particle to try
     volatile int *done = firsts + nsub;                               // [nwarps] half-sweeps completed by each warp
+    double2 *wsum = reinterpret_cast<double2 *>(w + wcap + ((nsub + nwarps + 3) >> 2) * 2);   // [nsub][nwarps] (s12, s6)
+    double *ts = reinterpret_cast<double *>(wsum + nsub * nwarps);    // [nsub][9], last CTA of a chain only
     __shared__ __align__(8) unsigned long long mbar;
+    __shared__ int is_last;
 
     const double *src = S.r_in + (uint64_t) chain * S.N + g0;
     const int body = ((((uintptr_t) src) & 15) == 0) ? (wlen & ~1) : 0;
@@ -297,10 +341,9 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
 
     const double half_l = S.l[chain] / 2.0, T = S.T[chain], step2 = 2 * S.maxStep[chain];
     const double invT = 1.0 / T;
-    const long long cb = __double_as_longlong(S.cutoff);
-    const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32);
+    const double cb = S.cutoff;
     const uint32_t tag = kTagParticle | (uint32_t)(S.chain_id0 + chain);
-    const int nbn = S.nbn, ncol = S.ncol;
+    const int nbn = NB > 0 ? NB : S.nbn, ncol = nbn + 1;
     const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
     const int gi = lane32 / G, lane = lane32 % G;
     // the groups of a warp reject at the wall independently: shuffle within the group only
@@ -310,16 +353,20 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
     const int x_last_interior = (int) (min(g1, N - nbn) - g0) - 1;             // x <= this: all right partners exist
     const int j0 = warp * rounds * GPW + gi;                                   // this group's first trial of a half-sweep
     const int w_lo = max(0, warp - rad), w_hi = min(nwarps - 1, warp + rad);
-    const size_t nslots = (size_t) gridDim.x * nwarps;
     uint32_t n_acc = 0, n_try = 0;
 
+    // The random numbers of a trial depend on (half-sweep, particle) only, so the Philox block of the NEXT trial is
+    // evaluated while the pair terms of the current one are in flight: its ~60 integer instructions go into the
+    // issue slots the fp64 pipe leaves free (an fp64 instruction occupies the pipe for two cycles) instead of
+    // forming a phase of their own, which the lock-step of the warps would line up across the whole CTA.
+    Philox4 nxt = philox4x32_10((uint32_t) step0, (uint32_t)(step0 >> 32), (uint32_t)(g0 + firsts[0] + j0 * ncol), tag, RK);
     for (int t = 0; t < nsub; ++t) {
         if (t > 0) {
-            // wait until every warp whose stretch can touch ours has finished half-sweep t-1
-            if (lane32 == 0)
-                for (int v = w_lo; v <= w_hi; ++v)
-                    while (done[v] < t) __nanosleep(20);
-            __syncwarp();
+            // wait until every warp whose stretch can touch ours has finished half-sweep t-1: lane j watches warp
+            // w_lo + j, one vote per poll, the pause doubling up to 160 ns
+            const int v = min(w_lo + lane32, w_hi);
+            unsigned ns = 20;
+            while (!__all_sync(0xffffffffu, done[v] >= t)) { __nanosleep(ns); ns = min(ns * 2, 160u); }
             __threadfence_block();
         }
         const int x_end = (int) (((g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn) - g0);
@@ -328,24 +375,42 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
         int x = firsts[t] + j0 * ncol;
         for (int r = 0; r < rounds; ++r, x += GPW * ncol) {
             if (x >= x_end) break;
-            const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, k0, k1);
+            const Philox4 b4 = nxt;
+            const uint32_t g_next = (uint32_t)(g0 + x + GPW * ncol);   // (unused after the last round)
             const double rn = u01(b4.w[0]), ran = u01(b4.w[1]);
             const double rnm = w[x];
             const double md = (rn - 0.5) * step2;                                     // qad2 :1182 ((rn-.5)*2*maxStep, 2*maxStep exact)
             const double rT = rnm + md;                                               // :1183
             const bool owned = (x >= x_lo) && (x < x_hi);
             if (owned && lane == 0) ++n_try;
-            if (fabs(rT) > half_l) continue;                                          // :1188 (group-uniform)
+            // :1188: a move through the wall is rejected whatever its energy; only the two ends of a chain can get
+            // there, so it is a predicate on the decision, not a branch around the pair terms
+            const bool inside = !(fabs(rT) > half_l);
             double s6 = 0, s12 = 0;
             if (x >= x_first_interior && x <= x_last_interior) {
-                const double *wl = w + x - 1 - lane, *wr = w + x + 1 + lane;
+                if constexpr (NB > 0) {
+                    static_assert(NB == 0 || G == 1, "compile-time NBN is a G = 1 specialisation");
+                    double t6 = 0, t12 = 0;                   // right partners apart: two independent accumulation chains
+#pragma unroll
+                    for (int q = 1; q <= NB; ++q) {
+                        const double rl = w[x - q], rr = w[x + q];
+                        lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12);
+                        lj_partner<CUT>(rr - rnm, rr - rT, cb, t6, t12);
+                    }
+                    s6 += t6; s12 += t12;
+                    nxt = philox4x32_10(s_lo, s_hi, g_next, tag, RK);       // same basic block as the pair terms
+                } else {
+                    nxt = philox4x32_10(s_lo, s_hi, g_next, tag, RK);
+                    const double *wl = w + x - 1 - lane, *wr = w + x + 1 + lane;
 #pragma unroll 2
-                for (int q = lane; q < nbn; q += G, wl -= G, wr += G) {
-                    const double rl = *wl, rr = *wr;
-                    lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12);
-                    lj_partner<CUT>(rr - rnm, rr - rT, cb, s6, s12);
+                    for (int q = lane; q < nbn; q += G, wl -= G, wr += G) {
+                        const double rl = *wl, rr = *wr;
+                        lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12);
+                        lj_partner<CUT>(rr - rnm, rr - rT, cb, s6, s12);
+                    }
                 }
             } else {
+                nxt = philox4x32_10(s_lo, s_hi, g_next, tag, RK);
                 for (int q = lane + 1; q <= nbn; q += G) {
                     if (g0 + x - q >= 0) { const double rl = w[x - q]; lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12); }
                     if (g0 + x + q < N) { const double rr = w[x + q]; lj_partner<CUT>(rr - rnm, rr - rT, cb, s6, s12); }
@@ -357,7 +422,13 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
                 s6 += __shfl_xor_sync(gmask, s6, off);
                 s12 += __shfl_xor_sync(gmask, s12, off);
             }
-            if (metropolis_accept(4 * s12 - 4 * s6, T, invT, ran)) {                  // :1367-1377
+            // Metropolis rule :1367-1377 (see metropolis_accept, pot.cuh): decided by ran - ea unless that lies within
+            // the band; dE <= 0 gives ea >= 1 > ran.  A NaN fails both tests and is rejected by the exact one.
+            const double dE = 4 * s12 - 4 * s6;
+            const double gap = ran - (double) exp_neg_approx(dE * invT);
+            bool accept = gap < -kMetropolisBand;
+            if (fabs(gap) <= kMetropolisBand) accept = dE <= 0 || exp(-dE / T) > ran;
+            if (accept && inside) {
                 if (lane == 0) w[x] = rT;
                 if (owned) { acc6 += m6; acc12 += m12; if (lane == 0) ++n_acc; }
             }
@@ -366,14 +437,20 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
         // this warp's half-sweep is complete: publish it (the position writes above first), then its two sums
         __threadfence_block();
         if (lane32 == 0) done[warp] = t + 1;
+        // two sums over the warp with one value per lane after the first exchange: even lanes carry s12, odd lanes s6
+        {
+            const bool odd = lane32 & 1;
+            const double give = odd ? acc12 : acc6, keep = odd ? acc6 : acc12;
+            double v = keep + __shfl_xor_sync(0xffffffffu, give, 1);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            acc6 += __shfl_xor_sync(0xffffffffu, acc6, off);
-            acc12 += __shfl_xor_sync(0xffffffffu, acc12, off);
+            for (int off = 2; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            const double other = __shfl_sync(0xffffffffu, v, 1);             // lane 1: the s6 total
+            acc12 = v; acc6 = other;
         }
-        if (lane32 == 0) {
-            double2 *dst = reinterpret_cast<double2 *>(partial) + ((uint64_t) chain * nsub + t) * nslots + (size_t) blockIdx.x * nwarps + warp;
-            *dst = make_double2(acc12, acc6);
+        if (lane32 == 0) wsum[t * nwarps + warp] = make_double2(acc12, acc6);
+        if (t + 1 < nsub) {                                  // first trial of the next half-sweep, ahead of the wait
+            const uint64_t st = step0 + t + 1;
+            nxt = philox4x32_10((uint32_t) st, (uint32_t)(st >> 32), (uint32_t)(g0 + firsts[t + 1] + j0 * ncol), tag, RK);
         }
     }
     __syncthreads();
@@ -390,41 +467,46 @@ __global__ void __launch_bounds__(512, 2) k_sweep_fast(SweepDev S, uint64_t step
         atomicAdd(&counts[2 * chain], (unsigned long long) n_acc);
         atomicAdd(&counts[2 * chain + 1], (unsigned long long) n_try);
     }
-}
 
-// Sum of the per-warp (s12, s6) pairs of one half-sweep over all slots, in a fixed order, expanded to the nine
-// deltas -> tsum[chain][t][9].  grid (nsub, nchains), 256 threads.
-static __global__ void __launch_bounds__(256) k_sweep_reduce2(const double *partial, int nsub, size_t nslots, double *tsum) {
-    const int t = blockIdx.x, chain = blockIdx.y;
-    const double2 *p = reinterpret_cast<const double2 *>(partial) + ((uint64_t) chain * nsub + t) * nslots;
-    double s12 = 0, s6 = 0;
-    for (size_t i = threadIdx.x; i < nslots; i += 256) { const double2 v = p[i]; s12 += v.x; s6 += v.y; }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        s12 += __shfl_xor_sync(0xffffffffu, s12, off);
-        s6 += __shfl_xor_sync(0xffffffffu, s6, off);
+    // ---- this tile's two sums per half-sweep (warps added in index order) -> partial[chain][t][tile]
+    const unsigned ntiles = gridDim.x;
+    double2 *part2 = reinterpret_cast<double2 *>(partial) + (uint64_t) chain * nsub * ntiles;
+    for (int t = threadIdx.x; t < nsub; t += blockDim.x) {
+        double s12 = 0, s6 = 0;
+        for (int v = 0; v < nwarps; ++v) { const double2 q = wsum[t * nwarps + v]; s12 += q.x; s6 += q.y; }
+        part2[(size_t) t * ntiles + blockIdx.x] = make_double2(s12, s6);
     }
-    __shared__ double red[8][2];
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s12; red[threadIdx.x >> 5][1] = s6; }
+    // ---- the last tile of the chain to get here folds the launch into the totals and the twelve sums
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t12 = 0, t6 = 0;
-        for (int wv = 0; wv < 8; ++wv) { t12 += red[wv][0]; t6 += red[wv][1]; }
-        double v[9];
-        lj_nine(t6, t12, v);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) tsum[((uint64_t) chain * nsub + t) * 9 + k] = v[k];
+        const unsigned prev = atomicAdd(&tile_done[chain], 1u);
+        is_last = (prev == ntiles - 1);
+        if (is_last) tile_done[chain] = 0;                 // ready for the next launch
     }
-}
-
-// After a k_sweep launch: fold the per-tile deltas into the running totals half-sweep by half-sweep
-// (fixed summation order -> reproducible) and sample the twelve sums once per half-sweep
-// (updateThermo :1941-1961 with l constant).
-__device__ __forceinline__ void cb_sample(double (&a)[12], const double *cur, double N, double lbox) {
-    const double rho = N / lbox, E = cur[0], Vir = cur[1], HV = cur[6];
-    a[0] += rho; a[1] += rho * rho; a[2] += lbox; a[3] += lbox * lbox;
-    a[4] += E; a[5] += E * E; a[6] += lbox * E; a[7] += Vir; a[8] += Vir * Vir; a[9] += E * Vir;
-    a[10] += HV; a[11] += HV * HV;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int t = warp; t < nsub; t += nwarps) {            // a warp per half-sweep: lanes strided over the tiles + butterfly
+        double s12 = 0, s6 = 0;
+        for (unsigned b = lane32; b < ntiles; b += 32) {
+            const double2 q = __ldcg(&part2[(size_t) t * ntiles + b]);
+            s12 += q.x; s6 += q.y;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s12 += __shfl_xor_sync(0xffffffffu, s12, off);
+            s6 += __shfl_xor_sync(0xffffffffu, s6, off);
+        }
+        if (lane32 == 0) {
+            double v[9];
+            lj_nine(s6, s12, v);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) ts[t * 9 + k] = v[k];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) sweep_finish_warp(ts, nsub, S.N, S.l[chain], tot + chain * 9, acc + chain * 12, 0, lane32);
 }
 
 // Step 1, grid (nsub, nchains), 9 warps: warp k adds component k of one half-sweep over the tiles (lanes strided,
@@ -449,24 +531,7 @@ static __global__ void __launch_bounds__(32) k_sweep_finish(const double *tsum, 
     const int chain = blockIdx.x, lane = threadIdx.x;
     for (int i = lane; i < nsub * 9; i += 32) ts[i] = tsum[(uint64_t) chain * nsub * 9 + i];
     __syncwarp();
-    double mine = lane < 9 ? tot[chain * 9 + lane] : 0.0;     // lane k carries component k
-    double a[12];
-    const double lbox = l[chain];
-    if (lane == 0)
-        for (int q = 0; q < 12; ++q) a[q] = acc[chain * 12 + q];
-    double c3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (presample) {
-        c3[0] = __shfl_sync(0xffffffffu, mine, 0); c3[1] = __shfl_sync(0xffffffffu, mine, 1); c3[6] = __shfl_sync(0xffffffffu, mine, 6);
-        if (lane == 0) cb_sample(a, c3, (double) N, lbox);
-    }
-    for (int t = 0; t < nsub; ++t) {
-        if (lane < 9) mine += ts[t * 9 + lane];
-        c3[0] = __shfl_sync(0xffffffffu, mine, 0); c3[1] = __shfl_sync(0xffffffffu, mine, 1); c3[6] = __shfl_sync(0xffffffffu, mine, 6);
-        if (lane == 0) cb_sample(a, c3, (double) N, lbox);
-    }
-    if (lane < 9) tot[chain * 9 + lane] = mine;
-    if (lane == 0)
-        for (int q = 0; q < 12; ++q) acc[chain * 12 + q] = a[q];
+    sweep_finish_warp(ts, nsub, N, l[chain], tot + chain * 9, acc + chain * 12, presample, lane);
 }
 
 // Parallel configuration totals (SURVEY §3.3 loop): grid (nblocks, nchains), rows i strided over the
