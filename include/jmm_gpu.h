@@ -163,6 +163,11 @@ jmm_status jmm_get_state(jmm_handle *h, double *r, double *l, double *totals, do
 jmm_status jmm_zero_accum(jmm_handle *h);
 /* getStepNum(), :2777 */
 uint64_t   jmm_step_number(const jmm_handle *h);
+/* Continue at a given step number: what a restart does with the step count of the last frame of config.dat.mcs
+ * (setupMCS restart branch, src/jmmMCState.cpp:572-765, `sscanf(... &(mcs->sn) ...)` at :641).  The step number selects the Philox
+ * blocks and decides whether the relaxVolume cadence (every 10 000 steps below 1 000 000, src/Main.cpp:173) is
+ * still active.  Many-chain handles only. */
+jmm_status jmm_set_step_number(jmm_handle *h, uint64_t sn);
 /* ECheck statistics summed over chains: number of checks and of "Energy discrepancy" resets */
 jmm_status jmm_echeck_stats(jmm_handle *h, uint64_t *checks, uint64_t *discrepancies);
 /* words of the recorded stream consumed so far */

@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         "jmm_get_state": (C.c_int32, [H, dp, dp, dp, dp, u64p]),
         "jmm_zero_accum": (C.c_int32, [H]),
         "jmm_step_number": (C.c_uint64, [H]),
+        "jmm_set_step_number": (C.c_int32, [H, C.c_uint64]),
         "jmm_echeck_stats": (C.c_int32, [H, u64p, u64p]),
         "jmm_stream_cursor": (C.c_uint64, [H]),
         "jmm_sweep": (C.c_int32, [H, C.c_uint64, u64p]),
@@ -236,6 +237,9 @@ class Handle:
     @property
     def step_number(self):
         return int(self.L.jmm_step_number(self.h))
+
+    def set_step_number(self, sn):
+        _check(self.L.jmm_set_step_number(self.h, int(sn)))
 
     @property
     def stream_cursor(self):

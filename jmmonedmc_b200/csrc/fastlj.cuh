@@ -34,8 +34,15 @@ __device__ __forceinline__ double rcp_cubic(double x) {
 // masked by clearing the HIGH word of its sixth power: what is left is a subnormal < 2^-1042, so that
 // (A - B) inv and (A + B) inv round to exactly the values they have with a true zero whenever the other term is
 // alive, and to (sub)normal noise below 1e-300 when both are masked — one SEL instead of two.
-__device__ __forceinline__ double keep_if(double x, bool keep) {
-    return __hiloint2double(keep ? __double2hiint(x) : 0, __double2loint(x));
+// In place: one DSETP and one predicated move of RZ into the high word (written with SEL on a copy, the compiler
+// spends two more moves per term on rebuilding the register pair).
+__device__ __forceinline__ void mask_beyond(double &x, double d, double cutoff) {
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
+        "setp.gtu.f64 p, %1, %2;\n\t"            // !(d <= cutoff): beyond the cutoff, or NaN
+        "mov.b64 {lo, hi}, %0;\n\t"
+        "@p mov.b32 hi, 0;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "+d"(x) : "d"(d), "d"(cutoff));
 }
 
 // One partner.  a, b = old and new SIGNED distance in the reference's orientation (r[j]-r[i], j > i by index).
@@ -46,8 +53,8 @@ __device__ __forceinline__ void lj_partner(double a, double b, double cutoff, do
     const double inv = rcp_cubic(A * B);
     if constexpr (CUT) {
         // new term b^-6 = A inv lives in A, old term a^-6 = B inv lives in B
-        A = keep_if(A, b <= cutoff);
-        B = keep_if(B, a <= cutoff);
+        mask_beyond(A, b, cutoff);
+        mask_beyond(B, a, cutoff);
     }
     const double d6 = (A - B) * inv;
     const double t6 = (A + B) * inv;

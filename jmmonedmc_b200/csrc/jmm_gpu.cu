@@ -471,6 +471,13 @@ extern "C" jmm_status jmm_zero_accum(jmm_handle *h) {
 }
 
 extern "C" uint64_t jmm_step_number(const jmm_handle *h) { return h ? (is_cb(h) ? h->halfsweeps : h->sn) : 0; }
+
+extern "C" jmm_status jmm_set_step_number(jmm_handle *h, uint64_t sn) {
+    if (!h) return fail(JMM_ERR_INVALID, "null handle");
+    if (is_cb(h)) return fail(JMM_ERR_INVALID, "jmm_set_step_number: many-chain handles only");
+    h->sn = sn;
+    return JMM_OK;
+}
 extern "C" uint64_t jmm_stream_cursor(const jmm_handle *h) { return h ? h->cursor : 0; }
 extern "C" uint64_t jmm_kernel_launches(const jmm_handle *h) { return h ? h->launches : 0; }
 
@@ -948,11 +955,12 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
         return s;
     }
     // ---- k_sweep_fast (<= 64 registers, so up to 32 warps per SM whatever the CTA size)
-    // lanes per trial: the largest power of two <= min(NBN, 32) that still leaves every resident thread
-    // (148 SMs x 1024) a trial of its own per half-sweep
+    // lanes per trial: the largest power of two <= min(NBN, 32) that keeps a half-sweep at 2-3 rounds of the
+    // resident threads (148 SMs x JMM_SWEEP_MAXT).  Measured on C5 (NBN 64): G = 8 3.87e9, G = 4 3.54e9, G = 2
+    // 2.9e9 trials/s; on C3 (NBN 4): G = 1 5.3e10, G = 2 3.5e10.
     const uint64_t trials = std::max<uint64_t>(1, C * ((N + ncol - 1) / ncol));
     int g = 1;
-    while (g * 2 <= std::min(nbn, 32) && trials * (uint64_t) (g * 2) <= 148ull * 1024) g *= 2;
+    while (g * 2 <= std::min(nbn, 32) && trials * (uint64_t) (g * 2) * 10 <= 148ull * JMM_SWEEP_MAXT * 24) g *= 2;
     {
         const int v = env_int("JMM_SWEEP_G", 0);
         if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) g = v;
@@ -976,8 +984,8 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
         const double owned = (double) tile / (double) (tile + std::max(0, halo - nbn));   // mean over the half-sweeps
         const double x = (double) (((N + tile - 1) / tile) * C) / (148.0 * k);            // CTAs / resident CTA slots
         const double fill = x <= 1.0 ? x : x / ceil(x);
-        for (int nw = 4; nw * k <= 32; nw += 4) {
-            if (w_env && nw != w_env && !(w_env % 4)) continue;
+        for (int nw = 2; nw * k * 32 <= JMM_SWEEP_MAXT; ++nw) {          // registers: 65536 / MAXT per thread
+            if (w_env && nw != w_env) continue;
             const int rounds = (per_sub + nw * gpw - 1) / (nw * gpw);
             const double lanes = (double) per_sub / (double) (rounds * nw * gpw);
             const double wps = (double) (nw * k) / 4.0;                               // warps per sub-partition
@@ -990,13 +998,9 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
             }
         }
     }
-    if (w_env && (w_env % 4)) {          // experiments: any warp count
-        const int per_sub = (s.tile + 2 * std::max(0, s.halo - nbn) + ncol - 1) / ncol;
-        s.threads = std::min(32, std::max(2, w_env)) * 32;
-        s.rounds = (per_sub + (s.threads / 32) * gpw - 1) / ((s.threads / 32) * gpw);
-    }
-    // colour offsets drift by at most nsub*NBN + ncol over the launch; reads reach NBN either side
-    s.rad = 1 + (s.nsub * nbn + ncol + 2 * nbn) / (s.rounds * gpw * ncol);
+    // how far (in warps) a stretch can collide: 1 whenever a stretch holds >= 5 trials (sweep.cuh: "Interior first");
+    // for shorter stretches the conservative bound on the drift of the colour offsets over the whole launch
+    s.rad = (s.rounds * gpw >= 5) ? 1 : 1 + (s.nsub * nbn + ncol + 2 * nbn) / (s.rounds * gpw * ncol);
     const size_t nw = (size_t) s.threads / 32;
     s.smem = (size_t) (s.tile + 2 * s.halo) * 8 + (((size_t) s.nsub + nw + 3) / 4) * 16 + (size_t) s.nsub * nw * 16 + (size_t) s.nsub * 72 + 32;
     return s;

@@ -23,7 +23,17 @@
 #include "pot.cuh"
 #include "fastlj.cuh"
 
+// build-time shape of k_sweep_fast (defaults = the measured best)
+#ifndef JMM_SWEEP_UNROLL
+#define JMM_SWEEP_UNROLL 2        // iterations of the run-time partner loop in flight (two pair terms each)
+#endif
+#ifndef JMM_SWEEP_MAXT
+#define JMM_SWEEP_MAXT 768        // __launch_bounds__ of k_sweep_fast (register cap = 65536 / MAXT)
+#endif
+
 namespace jmm {
+
+constexpr int kSweepUnroll = JMM_SWEEP_UNROLL;
 
 struct SweepDev {
     uint64_t nchains, N;
@@ -284,7 +294,7 @@ __device__ __forceinline__ void sweep_finish_warp(const double *ts, int nsub, ui
 // G, rounds and rad are chosen by the host (jmm_gpu.cu: sweep_shape).
 // NB > 0: NBN known at compile time (G = 1 only): the partner loop is unrolled completely, 2 NB independent pair terms.
 template <int POT, int G, int NB>
-__global__ void __launch_bounds__(1024, 1) k_sweep_fast(const __grid_constant__ SweepDev S, const __grid_constant__ PhiloxKeys RK, uint64_t step0, int nsub, int tile, int halo, int rounds, int rad,
+__global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_constant__ SweepDev S, const __grid_constant__ PhiloxKeys RK, uint64_t step0, int nsub, int tile, int halo, int rounds, int rad,
                                                        double *partial /*[nchains][nsub][ntiles][2]*/,
                                                        unsigned long long *counts /*[nchains][2] accepted, trials*/,
                                                        unsigned int *tile_done /*[nchains], zero between launches*/,
@@ -351,32 +361,40 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_fast(const __grid_constant__ 
     const int x_lo = (int) (tile_lo - g0), x_hi = (int) (tile_hi - g0);     // owned window range
     const int x_first_interior = (int) max((int64_t) 0, (int64_t) nbn - g0);   // x >= this: all left partners exist
     const int x_last_interior = (int) (min(g1, N - nbn) - g0) - 1;             // x <= this: all right partners exist
-    const int j0 = warp * rounds * GPW + gi;                                   // this group's first trial of a half-sweep
     const int w_lo = max(0, warp - rad), w_hi = min(nwarps - 1, warp + rad);
     uint32_t n_acc = 0, n_try = 0;
 
-    // The random numbers of a trial depend on (half-sweep, particle) only, so the Philox block of the NEXT trial is
-    // evaluated while the pair terms of the current one are in flight: its ~60 integer instructions go into the
-    // issue slots the fp64 pipe leaves free (an fp64 instruction occupies the pipe for two cycles) instead of
-    // forming a phase of their own, which the lock-step of the warps would line up across the whole CTA.
-    Philox4 nxt = philox4x32_10((uint32_t) step0, (uint32_t)(step0 >> 32), (uint32_t)(g0 + firsts[0] + j0 * ncol), tag, RK);
+    // Interior first.  A trial at offset o of this warp's stretch (o = 0 .. K-1, K = rounds * GPW) touches particles
+    // within NBN of its own; the stretch of half-sweep t is shifted against that of t-1 by -NBN .. 2 NBN particles
+    // (the halo shrinks by NBN — not in the first tile of a chain — and the colour changes by less than ncol).  So
+    // for 2 <= o <= K-3 everything the trial reads or overwrites was last touched, at t-1, by THIS warp; only
+    // o = 0, 1, K-2 and K-1 can collide with a neighbour's stretch (and never with a stretch further away, however
+    // far that warp lags: it is (d-1)K+3 trials off after d half-sweeps of drift of at most 2 NBN each).  The trials
+    // are therefore taken in the order o = 2, 3, ..., K-1, 0, 1 and the wait for the two neighbours comes right before
+    // the first round that holds one of the last four: the hand-shake latency hides behind the interior rounds.
+    // (K < 5, or a stretch so short that the host asks for rad > 1: wait before round 0, as a barrier would.)
+    const int K = rounds * GPW;
+    const bool interior_first = rad == 1 && K >= 5;
+    const int r_wait = interior_first ? (K - 4) / GPW : 0, rot = interior_first ? 2 : 0;
     for (int t = 0; t < nsub; ++t) {
-        if (t > 0) {
-            // wait until every warp whose stretch can touch ours has finished half-sweep t-1: lane j watches warp
-            // w_lo + j, one vote per poll, the pause doubling up to 160 ns
-            const int v = min(w_lo + lane32, w_hi);
-            unsigned ns = 20;
-            while (!__all_sync(0xffffffffu, done[v] >= t)) { __nanosleep(ns); ns = min(ns * 2, 160u); }
-            __threadfence_block();
-        }
         const int x_end = (int) (((g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn) - g0);
         const uint32_t s_lo = (uint32_t)(step0 + t), s_hi = (uint32_t)((step0 + t) >> 32);
         double acc6 = 0, acc12 = 0;
-        int x = firsts[t] + j0 * ncol;
-        for (int r = 0; r < rounds; ++r, x += GPW * ncol) {
-            if (x >= x_end) break;
-            const Philox4 b4 = nxt;
-            const uint32_t g_next = (uint32_t)(g0 + x + GPW * ncol);   // (unused after the last round)
+        const int x_base = firsts[t] + warp * K * ncol;
+        for (int r = 0; r < rounds; ++r) {
+            if (t > 0 && r == r_wait) {
+                // every warp whose stretch can touch ours must have finished half-sweep t-1: lane j watches warp
+                // w_lo + j, one vote per poll, the pause doubling up to 160 ns
+                const int v = min(w_lo + lane32, w_hi);
+                unsigned ns = 20;
+                while (!__all_sync(0xffffffffu, done[v] >= t)) { __nanosleep(ns); ns = min(ns * 2, 160u); }
+                __threadfence_block();
+            }
+            int o = r * GPW + gi + rot;
+            if (o >= K) o -= K;
+            const int x = x_base + o * ncol;
+            if (x >= x_end) continue;
+            const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, RK);
             const double rn = u01(b4.w[0]), ran = u01(b4.w[1]);
             const double rnm = w[x];
             const double md = (rn - 0.5) * step2;                                     // qad2 :1182 ((rn-.5)*2*maxStep, 2*maxStep exact)
@@ -398,11 +416,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_fast(const __grid_constant__ 
                         lj_partner<CUT>(rr - rnm, rr - rT, cb, t6, t12);
                     }
                     s6 += t6; s12 += t12;
-                    nxt = philox4x32_10(s_lo, s_hi, g_next, tag, RK);       // same basic block as the pair terms
                 } else {
-                    nxt = philox4x32_10(s_lo, s_hi, g_next, tag, RK);
                     const double *wl = w + x - 1 - lane, *wr = w + x + 1 + lane;
-#pragma unroll 2
+#pragma unroll (kSweepUnroll)
                     for (int q = lane; q < nbn; q += G, wl -= G, wr += G) {
                         const double rl = *wl, rr = *wr;
                         lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12);
@@ -410,7 +426,6 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_fast(const __grid_constant__ 
                     }
                 }
             } else {
-                nxt = philox4x32_10(s_lo, s_hi, g_next, tag, RK);
                 for (int q = lane + 1; q <= nbn; q += G) {
                     if (g0 + x - q >= 0) { const double rl = w[x - q]; lj_partner<CUT>(rnm - rl, rT - rl, cb, s6, s12); }
                     if (g0 + x + q < N) { const double rr = w[x + q]; lj_partner<CUT>(rr - rnm, rr - rT, cb, s6, s12); }
@@ -422,8 +437,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_fast(const __grid_constant__ 
                 s6 += __shfl_xor_sync(gmask, s6, off);
                 s12 += __shfl_xor_sync(gmask, s12, off);
             }
-            // Metropolis rule :1367-1377 (see metropolis_accept, pot.cuh): decided by ran - ea unless that lies within
-            // the band; dE <= 0 gives ea >= 1 > ran.  A NaN fails both tests and is rejected by the exact one.
+            // Metropolis rule :1367-1377 (see metropolis_accept, pot.cuh) without the early-out branches: decided by
+            // ran - ea unless that lies within the band; dE <= 0 gives ea >= 1 > ran.  A NaN fails both tests and is
+            // rejected by the exact one.
             const double dE = 4 * s12 - 4 * s6;
             const double gap = ran - (double) exp_neg_approx(dE * invT);
             bool accept = gap < -kMetropolisBand;
@@ -448,10 +464,6 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_fast(const __grid_constant__ 
             acc12 = v; acc6 = other;
         }
         if (lane32 == 0) wsum[t * nwarps + warp] = make_double2(acc12, acc6);
-        if (t + 1 < nsub) {                                  // first trial of the next half-sweep, ahead of the wait
-            const uint64_t st = step0 + t + 1;
-            nxt = philox4x32_10((uint32_t) st, (uint32_t)(st >> 32), (uint32_t)(g0 + firsts[t + 1] + j0 * ncol), tag, RK);
-        }
     }
     __syncthreads();
 

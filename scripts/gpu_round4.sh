@@ -26,7 +26,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ch
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_prod -s 1 -c 1 -f -o $OUT/prof_c4fast_$TAG \
     python bench.py --workload c4 --arith fast --steps 1 --warmup 3 > $OUT/ncu_c4fast_$TAG.log 2>&1; tail -1 $OUT/ncu_c4fast_$TAG.log | cut -c1-200
 for w in c3 c5; do
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_sweep_fast -s 2 -c 1 -f -o $OUT/prof_${w}fast_$TAG \
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_sweep_fast -s 4 -c 1 -f -o $OUT/prof_${w}fast_$TAG \
       python bench.py --workload $w --arith fast --steps 1 --warmup 3 > $OUT/ncu_${w}fast_$TAG.log 2>&1; tail -1 $OUT/ncu_${w}fast_$TAG.log | cut -c1-200
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_${w}fast_$TAG.csv \
       python bench.py --workload $w --arith fast --steps 1 --warmup 3 > /dev/null 2>&1

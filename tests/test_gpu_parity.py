@@ -323,6 +323,40 @@ def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C, arith, m
     assert trials == sum(int(x) for x in s["counters"].sum(axis=1))
 
 
+@pytest.mark.parametrize("shape", ["K=1,WARPS=4,G=8", "K=1,WARPS=3,G=4", "K=2,WARPS=5,G=2", "K=4,WARPS=2,G=1", "K=1,WARPS=24,G=8",
+                                   "K=2,WARPS=7,G=16,NSUB=32"])
+@pytest.mark.parametrize("pot,nbn,cutoff,N,C", [("LJcut", 4, 5.0, 60000, 1), ("LJ", 24, math.inf, 40000, 2)])
+def test_checkerboard_launch_shapes_match_oracle(J, O, pot, nbn, cutoff, N, C, shape, monkeypatch):
+    """k_sweep_fast under forced launch shapes (CTAs per SM, warps per CTA, lanes per trial, half-sweeps per launch):
+    many rounds per warp, so that the interior-first order and the deferred neighbour hand-shake (sweep.cuh) are what
+    runs.  Positions must be bit-identical to the oracle whatever the shape; a race between warps would show here."""
+    from jmmonedmc_b200.capi import config
+    for kv in shape.split(","):
+        k, v = kv.split("=")
+        monkeypatch.setenv("JMM_SWEEP_" + k, v)
+    seed, id0, T, ms, nhs = 4711, 3, 0.9, 0.12, 40
+    L = N * 1.12
+    cfg = config(N=N, pot={"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT}[pot], nbn=nbn, cutoff=cutoff, ensemble=J.ENS_NLT, L=L, T=T,
+                 maxStep=ms, seed=seed, nchains=C, chain_id0=id0, mode=J.MODE_CHECKERBOARD, arith=J.ARITH_FAST)
+    with J.Handle(cfg) as h:
+        h.start()
+        trials = h.sweep(nhs)
+        s = h.get_state()
+        fresh = h.energy()
+    ncol = nbn + 1
+    for c in range(C):
+        r = ((np.arange(N) + 0.5) / N - 0.5) * L
+        nacc = ntry = 0
+        for t in range(nhs):
+            col = O.colour_of_step(seed, id0 + c, t, ncol)
+            a, _ = O.colour_halfsweep(r, L, nbn, O.POT[pot], cutoff, T, ms, seed, id0 + c, t, ncol, col)
+            nacc += a; ntry += len(range(col, N, ncol))
+        assert bits_equal(s["r"][c], r), f"chain {c}: positions after {nhs} half-sweeps with {shape}"
+        assert int(s["counters"][c][0]) == nacc and int(s["counters"][c].sum()) == ntry
+        assert totals_close(s["totals"][c], fresh[c], 1e-11)
+    assert trials == sum(int(x) for x in s["counters"].sum(axis=1))
+
+
 @pytest.mark.parametrize("name", ["small", "std", "ljcut_nbn"])
 @pytest.mark.parametrize("engine", ["prod", "sliced", "generic", "table"])
 def test_histograms_match_oracle_integers(J, O, name, engine, monkeypatch):
