@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
         double acc6 = 0, acc12 = 0;
         const int x_base = firsts[t] + warp * K * ncol;
         for (int r = 0; r < rounds; ++r) {
+#ifndef JMM_ABL_NOSYNC
             if (t > 0 && r == r_wait) {
                 // every warp whose stretch can touch ours must have finished half-sweep t-1: lane j watches warp
                 // w_lo + j, one vote per poll, the pause doubling up to 160 ns
@@ -390,11 +391,16 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
                 while (!__all_sync(0xffffffffu, done[v] >= t)) { __nanosleep(ns); ns = min(ns * 2, 160u); }
                 __threadfence_block();
             }
+#endif
             int o = r * GPW + gi + rot;
             if (o >= K) o -= K;
             const int x = x_base + o * ncol;
             if (x >= x_end) continue;
+#ifdef JMM_ABL_NOPHILOX
+            Philox4 b4; b4.w[0] = (s_lo * 2654435761u) ^ ((uint32_t)(g0 + x) * 2246822519u); b4.w[1] = b4.w[0] * 3266489917u + tag;
+#else
             const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, RK);
+#endif
             const double rn = u01(b4.w[0]), ran = u01(b4.w[1]);
             const double rnm = w[x];
             const double md = (rn - 0.5) * step2;                                     // qad2 :1182 ((rn-.5)*2*maxStep, 2*maxStep exact)
@@ -441,9 +447,13 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
             // ran - ea unless that lies within the band; dE <= 0 gives ea >= 1 > ran.  A NaN fails both tests and is
             // rejected by the exact one.
             const double dE = 4 * s12 - 4 * s6;
+#ifdef JMM_ABL_NOMET
+            bool accept = dE * invT < ran * 2.0;
+#else
             const double gap = ran - (double) exp_neg_approx(dE * invT);
             bool accept = gap < -kMetropolisBand;
             if (fabs(gap) <= kMetropolisBand) accept = dE <= 0 || exp(-dE / T) > ran;
+#endif
             if (accept && inside) {
                 if (lane == 0) w[x] = rT;
                 if (owned) { acc6 += m6; acc12 += m12; if (lane == 0) ++n_acc; }

@@ -14,7 +14,7 @@ from bench import EXTRA
 wl = sys.argv[1]
 w = EXTRA[wl]
 pot = {"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT}[w["pot"]]
-KEYS = ("K", "WARPS", "G", "NSUB")
+KEYS = ("K", "WARPS", "G", "NSUB", "STAGGER")
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 peak = J.lib().jmm_fp64_peak_tflops(0)
 print(f"{wl}: fp64 peak {peak:.1f} TFLOP/s")
