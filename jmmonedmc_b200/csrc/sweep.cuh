@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
         const uint32_t s_lo = (uint32_t)(step0 + t), s_hi = (uint32_t)((step0 + t) >> 32);
         double acc6 = 0, acc12 = 0;
         const int x_base = firsts[t] + warp * K * ncol;
+        Philox4 ahead{};
         for (int r = 0; r < rounds; ++r) {
 #ifndef JMM_ABL_NOSYNC
             if (t > 0 && r == r_wait) {
@@ -395,13 +396,30 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
             int o = r * GPW + gi + rot;
             if (o >= K) o -= K;
             const int x = x_base + o * ncol;
+            uint32_t w0, w1;
+            if constexpr (G > 1) {
+                // the G lanes of a group need the same block; evaluated by all of them it is G-1 times redundant.
+                // Instead lane j evaluates the block of the group's trial j rounds ahead, once every G rounds, and
+                // each round fetches its two words from the lane that holds them.
+                const int rb = r % G;
+                if (rb == 0) {
+                    int oj = (r + lane) * GPW + gi + rot;
+                    if (oj >= K) oj -= K;                    // (rounds past the last one: an unused block)
+                    ahead = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x_base + oj * ncol), tag, RK);
+                }
+                w0 = __shfl_sync(gmask, ahead.w[0], rb, G);
+                w1 = __shfl_sync(gmask, ahead.w[1], rb, G);
+            }
             if (x >= x_end) continue;
+            if constexpr (G == 1) {
 #ifdef JMM_ABL_NOPHILOX
-            Philox4 b4; b4.w[0] = (s_lo * 2654435761u) ^ ((uint32_t)(g0 + x) * 2246822519u); b4.w[1] = b4.w[0] * 3266489917u + tag;
+                w0 = (s_lo * 2654435761u) ^ ((uint32_t)(g0 + x) * 2246822519u); w1 = w0 * 3266489917u + tag;
 #else
-            const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, RK);
+                const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, RK);
+                w0 = b4.w[0]; w1 = b4.w[1];
 #endif
-            const double rn = u01(b4.w[0]), ran = u01(b4.w[1]);
+            }
+            const double rn = u01(w0), ran = u01(w1);
             const double rnm = w[x];
             const double md = (rn - 0.5) * step2;                                     // qad2 :1182 ((rn-.5)*2*maxStep, 2*maxStep exact)
             const double rT = rnm + md;                                               // :1183
