@@ -967,11 +967,8 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
     }
     s.G = g;
     const int gpw = 32 / g;
-    // The warps of a CTA advance in lock-step with their neighbours (sweep.cuh), so the SM runs at the pace of its
-    // fullest sub-partition: warps go to the four sub-partitions round-robin by warp index, hence a CTA gets a
-    // multiple of four warps.  Candidates: k = 1, 2, 4 CTAs per SM x 4, 8, ... warps; score = useful lanes x owned
-    // (non-halo) share x a latency-hiding term in the resident warps per sub-partition x the share of a half-sweep
-    // that is not the neighbour hand-shake.
+    // Candidates: k = 1, 2, 4 CTAs per SM x 2, 3, ... warps; score = modelled trials per unit time x owned
+    // (non-halo) share x the share of a half-sweep that is not the neighbour hand-shake.
     const int k_env = env_int("JMM_SWEEP_K", 0), w_env = env_int("JMM_SWEEP_WARPS", 0);
     const uint64_t sub_cap = (uint64_t) std::max(1, std::min(64, env_int("JMM_SWEEP_NSUB", 64)));
     double best = -1.0;
@@ -980,29 +977,32 @@ static SweepShape sweep_shape(const jmm_handle *h, uint64_t want_sub) {
         int tile, halo, nsub;
         // shared memory: 200 KB / k, less the per-warp sums [nsub][nwarps][2] and the other small arrays (<= 40 KB / k)
         sweep_tiling(N, C, nbn, ncol, 148ull * k, (160 / k) * 1024 / 8, std::min(want_sub, sub_cap), &tile, &halo, &nsub);
-        const int per_sub = (tile + 2 * std::max(0, halo - nbn) + ncol - 1) / ncol;    // first half-sweep: halos still tried
+        // first half-sweep: halos still tried; + 1: the base of a stretch moves down to an even trial index (sweep.cuh)
+        const int per_sub = (tile + 2 * std::max(0, halo - nbn) + ncol - 1) / ncol + 1;
         const double owned = (double) tile / (double) (tile + std::max(0, halo - nbn));   // mean over the half-sweeps
         const double x = (double) (((N + tile - 1) / tile) * C) / (148.0 * k);            // CTAs / resident CTA slots
         const double fill = x <= 1.0 ? x : x / ceil(x);
         for (int nw = 2; nw * k * 32 <= JMM_SWEEP_MAXT; ++nw) {          // registers: 65536 / MAXT per thread
             if (w_env && nw != w_env) continue;
             const int rounds = (per_sub + nw * gpw - 1) / (nw * gpw);
-            const double lanes = (double) per_sub / (double) (rounds * nw * gpw);
+            // trials per SM and half-sweep over the time of its rounds; a round of w warps per sub-partition takes
+            // ~ w^0.7 (measured, profiles/r01t_sweep_shapes_*: more warps keep the fp64 pipe busier, so idle lanes in
+            // the last round cost less than a warp count that divides the trials evenly but is smaller)
             const double wps = (double) (nw * k) / 4.0;                               // warps per sub-partition
-            const double hide = wps / (wps + 2.0);
             const double work = rounds * (120.0 + 40.0 * ((2 * nbn + g - 1) / g));       // warp instructions per half-sweep
-            const double score = fill * lanes * owned * hide * work / (work + 80.0);
+            // launch ramp, window load and the closing reduction cost about one half-sweep per launch
+            const double score = fill * owned * ((double) per_sub * k) / (rounds * pow(wps, 0.7)) * work / (work + 80.0) * nsub / (nsub + 1.0);
             if (score > best) {
                 best = score;
                 s.tile = tile; s.halo = halo; s.nsub = nsub; s.rounds = rounds; s.threads = nw * 32;
             }
         }
     }
-    // how far (in warps) a stretch can collide: 1 whenever a stretch holds >= 5 trials (sweep.cuh: "Interior first");
+    // how far (in warps) a stretch can collide: 1 whenever a stretch holds >= 6 trials (sweep.cuh: "Interior first");
     // for shorter stretches the conservative bound on the drift of the colour offsets over the whole launch
-    s.rad = (s.rounds * gpw >= 5) ? 1 : 1 + (s.nsub * nbn + ncol + 2 * nbn) / (s.rounds * gpw * ncol);
+    s.rad = (s.rounds * gpw >= 6) ? 1 : 1 + (s.nsub * nbn + ncol + 2 * nbn) / (s.rounds * gpw * ncol);
     const size_t nw = (size_t) s.threads / 32;
-    s.smem = (size_t) (s.tile + 2 * s.halo) * 8 + (((size_t) s.nsub + nw + 3) / 4) * 16 + (size_t) s.nsub * nw * 16 + (size_t) s.nsub * 72 + 32;
+    s.smem = (size_t) (s.tile + 2 * s.halo) * 8 + ((3 * (size_t) s.nsub + nw + 3) / 4) * 16 + (size_t) s.nsub * nw * 16 + (size_t) s.nsub * 72 + 32;
     return s;
 }
 

@@ -125,11 +125,13 @@ __global__ void __launch_bounds__(512, 1) k_sweep(SweepDev S, uint64_t step0, in
         double dacc[NA];
 #pragma unroll
         for (int k = 0; k < NA; ++k) dacc[k] = 0;
-        for (int64_t g = first + (int64_t) group * ncol; g < uhi; g += (int64_t) ngroups * ncol) {
+        // trial index within the half-sweep (particle = colour + j ncol): one Philox block serves the trials 2m, 2m+1
+        int64_t j = first / ncol + group;
+        for (int64_t g = first + (int64_t) group * ncol; g < uhi; g += (int64_t) ngroups * ncol, j += ngroups) {
             uint32_t w0, w1;
             if (G == 1 || lane == 0) {
-                const Philox4 b = philox4x32_10((uint32_t)(step0 + t), (uint32_t)((step0 + t) >> 32), (uint32_t) g, tag, k0, k1);
-                w0 = b.w[0]; w1 = b.w[1];
+                const Philox4 b = philox4x32_10((uint32_t)(step0 + t), (uint32_t)((step0 + t) >> 32), (uint32_t)(j >> 1), tag, k0, k1);
+                w0 = b.w[2 * (j & 1)]; w1 = b.w[2 * (j & 1) + 1];
             }
             if constexpr (G > 1) { w0 = __shfl_sync(0xffffffffu, w0, 0); w1 = __shfl_sync(0xffffffffu, w1, 0); }
             const double rn = u01(w0), ran = u01(w1);
@@ -314,8 +316,10 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
     const int wlen = (int) (g1 - g0);
     const int wcap = tile + 2 * halo;
     int *firsts = reinterpret_cast<int *>(w + wcap);                  // [nsub] window index of the first particle to try
-    volatile int *done = firsts + nsub;                               // [nwarps] half-sweeps completed by each warp
-    double2 *wsum = reinterpret_cast<double2 *>(w + wcap + ((nsub + nwarps + 3) >> 2) * 2);   // [nsub][nwarps] (s12, s6)
+    int *bases = firsts + nsub;                                       // [nsub] the same, moved down to an EVEN trial index
+    uint32_t *jbs = reinterpret_cast<uint32_t *>(bases + nsub);       // [nsub] that (even) trial index within the half-sweep
+    volatile int *done = bases + 2 * nsub;                            // [nwarps] half-sweeps completed by each warp
+    double2 *wsum = reinterpret_cast<double2 *>(w + wcap + ((3 * nsub + nwarps + 3) >> 2) * 2);   // [nsub][nwarps] (s12, s6)
     double *ts = reinterpret_cast<double *>(wsum + nsub * nwarps);    // [nsub][9], last CTA of a chain only
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ int is_last;
@@ -338,7 +342,11 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
     for (int t = threadIdx.x; t < nsub; t += blockDim.x) {
         const int col = colour_of(S.seed, (uint32_t)(S.chain_id0 + chain), step0 + t, S.ncol);
         const int64_t ulo = (g0 == 0) ? 0 : g0 + (int64_t)(t + 1) * S.nbn;
-        firsts[t] = (int) (ulo + (((int64_t) col - ulo % S.ncol) + S.ncol) % S.ncol - g0);
+        const int64_t first = ulo + (((int64_t) col - ulo % S.ncol) + S.ncol) % S.ncol;
+        const int64_t jf = first / S.ncol;                            // trial index of `first` in its half-sweep
+        firsts[t] = (int) (first - g0);
+        bases[t] = (int) (first - (jf & 1) * S.ncol - g0);            // trials 2m, 2m+1 share a Philox block
+        jbs[t] = (uint32_t) (jf & ~(int64_t) 1);
     }
     if (body > 0) {
         uint32_t ok = 0;
@@ -365,22 +373,26 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
     uint32_t n_acc = 0, n_try = 0;
 
     // Interior first.  A trial at offset o of this warp's stretch (o = 0 .. K-1, K = rounds * GPW) touches particles
-    // within NBN of its own; the stretch of half-sweep t is shifted against that of t-1 by -NBN .. 2 NBN particles
-    // (the halo shrinks by NBN — not in the first tile of a chain — and the colour changes by less than ncol).  So
-    // for 2 <= o <= K-3 everything the trial reads or overwrites was last touched, at t-1, by THIS warp; only
-    // o = 0, 1, K-2 and K-1 can collide with a neighbour's stretch (and never with a stretch further away, however
-    // far that warp lags: it is (d-1)K+3 trials off after d half-sweeps of drift of at most 2 NBN each).  The trials
-    // are therefore taken in the order o = 2, 3, ..., K-1, 0, 1 and the wait for the two neighbours comes right before
-    // the first round that holds one of the last four: the hand-shake latency hides behind the interior rounds.
-    // (K < 5, or a stretch so short that the host asks for rad > 1: wait before round 0, as a barrier would.)
+    // within NBN of its own; the stretch of half-sweep t is shifted against that of t-1 by -NBN-ncol .. 2 NBN+ncol
+    // particles (the halo shrinks by NBN — not in the first tile of a chain —, the colour changes by less than ncol,
+    // and the base moves down by one trial when the first trial index is odd).  So for 2 <= o <= K-4 everything the
+    // trial reads or overwrites was last touched, at t-1, by THIS warp; only o = 0, 1, K-3, K-2 and K-1 can collide
+    // with a neighbour's stretch (and never with a stretch further away, however far that warp lags: it is at least
+    // (d-1)K+2 trials off after d half-sweeps of drift of at most 2 NBN + ncol each).  The trials are therefore taken
+    // in the order o = 2, 3, ..., K-1, 0, 1 and the wait for the two neighbours comes right before the first round
+    // that holds one of the last five: the hand-shake latency hides behind the interior rounds.
+    // (K < 6, or a stretch so short that the host asks for rad > 1: wait before round 0, as a barrier would.)
     const int K = rounds * GPW;
-    const bool interior_first = rad == 1 && K >= 5;
-    const int r_wait = interior_first ? (K - 4) / GPW : 0, rot = interior_first ? 2 : 0;
+    const bool high = lane32 >= 16;                                   // G = 1: lanes 16-31 take the odd trials of a round
+    const int lane_o = 2 * (lane32 & 15) + (lane32 >> 4);
+    const bool interior_first = rad == 1 && K >= 6;
+    const int r_wait = interior_first ? (K - 5) / GPW : 0, rot = interior_first ? 2 : 0;
     for (int t = 0; t < nsub; ++t) {
         const int x_end = (int) (((g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn) - g0);
         const uint32_t s_lo = (uint32_t)(step0 + t), s_hi = (uint32_t)((step0 + t) >> 32);
         double acc6 = 0, acc12 = 0;
-        const int x_base = firsts[t] + warp * K * ncol;
+        const int x_valid = firsts[t], x_base = bases[t] + warp * K * ncol;
+        const uint32_t j_base = jbs[t] + (uint32_t) (warp * K);       // trial index of offset 0 (even for G = 1: K is)
         Philox4 ahead{};
         for (int r = 0; r < rounds; ++r) {
 #ifndef JMM_ABL_NOSYNC
@@ -393,32 +405,50 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
                 __threadfence_block();
             }
 #endif
-            int o = r * GPW + gi + rot;
-            if (o >= K) o -= K;
-            const int x = x_base + o * ncol;
+            // One Philox block serves the trials 2m and 2m+1 of a half-sweep (words 0,1 and 2,3).
             uint32_t w0, w1;
-            if constexpr (G > 1) {
-                // the G lanes of a group need the same block; evaluated by all of them it is G-1 times redundant.
-                // Instead lane j evaluates the block of the group's trial j rounds ahead, once every G rounds, and
-                // each round fetches its two words from the lane that holds them.
+            int o;
+            if constexpr (G == 1) {
+                // Two rounds = 64 consecutive offsets = 32 blocks, one per lane, evaluated in the even round.  Lanes
+                // 0-15 take the even trials of a round and lanes 16-31 the odd ones, so that in the even round
+                // (blocks 0-15) a low lane owns its words and a high lane fetches words 2,3 from lane - 16, and in the
+                // odd round (blocks 16-31) a high lane owns its words and a low lane fetches words 0,1 from lane + 16.
+                const int o_pair = (r >> 1) * 64 + rot;                                   // first offset of the round pair
+                if ((r & 1) == 0) {
+                    int op = o_pair + 2 * lane32;
+                    if (op >= K) op -= K;
+                    ahead = philox4x32_10(s_lo, s_hi, (j_base + (uint32_t) op) >> 1, tag, RK);
+                }
+                const bool odd_round = r & 1;
+                const uint32_t give0 = odd_round ? ahead.w[0] : ahead.w[2], give1 = odd_round ? ahead.w[1] : ahead.w[3];
+                const uint32_t got0 = __shfl_xor_sync(0xffffffffu, give0, 16), got1 = __shfl_xor_sync(0xffffffffu, give1, 16);
+                const bool own = high == odd_round;
+                w0 = own ? (high ? ahead.w[2] : ahead.w[0]) : got0;
+                w1 = own ? (high ? ahead.w[3] : ahead.w[1]) : got1;
+                o = o_pair + 32 * (r & 1) + lane_o;
+                if (o >= K) o -= K;
+            } else {
+                // the G lanes of a group need the same two words; evaluated by all of them the block is G-1 times
+                // redundant.  Instead lane j evaluates the block of the group's trial j rounds ahead, once every G
+                // rounds, and each round fetches its words from the lane that holds them.
+                o = r * GPW + gi + rot;
+                if (o >= K) o -= K;
                 const int rb = r % G;
                 if (rb == 0) {
                     int oj = (r + lane) * GPW + gi + rot;
                     if (oj >= K) oj -= K;                    // (rounds past the last one: an unused block)
-                    ahead = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x_base + oj * ncol), tag, RK);
+                    const uint32_t jj = j_base + (uint32_t) oj;
+                    const Philox4 b4 = philox4x32_10(s_lo, s_hi, jj >> 1, tag, RK);
+                    ahead.w[0] = b4.w[2 * (jj & 1)]; ahead.w[1] = b4.w[2 * (jj & 1) + 1];
                 }
                 w0 = __shfl_sync(gmask, ahead.w[0], rb, G);
                 w1 = __shfl_sync(gmask, ahead.w[1], rb, G);
             }
-            if (x >= x_end) continue;
-            if constexpr (G == 1) {
+            const int x = x_base + o * ncol;
+            if (x < x_valid || x >= x_end) continue;
 #ifdef JMM_ABL_NOPHILOX
-                w0 = (s_lo * 2654435761u) ^ ((uint32_t)(g0 + x) * 2246822519u); w1 = w0 * 3266489917u + tag;
-#else
-                const Philox4 b4 = philox4x32_10(s_lo, s_hi, (uint32_t)(g0 + x), tag, RK);
-                w0 = b4.w[0]; w1 = b4.w[1];
+            w0 = (s_lo * 2654435761u) ^ ((uint32_t)(g0 + x) * 2246822519u); w1 = w0 * 3266489917u + tag;
 #endif
-            }
             const double rn = u01(w0), ran = u01(w1);
             const double rnm = w[x];
             const double md = (rn - 0.5) * step2;                                     // qad2 :1182 ((rn-.5)*2*maxStep, 2*maxStep exact)

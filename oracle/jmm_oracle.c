@@ -656,7 +656,8 @@ uint64_t jmo_relax_calls(const jmo_state *s) { return s->relax_calls; }
  * Not in the reference (it moves one particle per step and cannot allocate N > ~1e4).  With NBN = k,
  * particles i and j interact iff |i-j| <= k (src/jmmMCState.cpp:1217,1312), so all particles of one
  * colour i mod (k+1) are mutually independent and their qad2 trials commute.  Each trial is exactly
- * displacement_trial() in RECOMPUTE mode; the Philox block is keyed per (sweep step, particle). */
+ * displacement_trial() in RECOMPUTE mode; the Philox block is keyed per (sweep step, pair of consecutive same-colour
+ * particles): all four words of a block are used. */
 int jmo_colour_of_step(uint64_t seed, uint64_t chain_id, uint64_t sweep_step, int ncolours) {
     uint32_t ctr[4] = { (uint32_t) sweep_step, (uint32_t)(sweep_step >> 32), 0xFFFFFFFFu, 0x40000000u | (uint32_t) chain_id };
     uint32_t key[2] = { (uint32_t) seed, (uint32_t)(seed >> 32) }, w[4];
@@ -671,9 +672,12 @@ uint64_t jmo_colour_halfsweep(double *r, uint64_t N, double l, int nbn, int pot,
     uint32_t key[2] = { (uint32_t) seed, (uint32_t)(seed >> 32) };
     for (int k = 0; k < 9; k++) dtot[k] = 0;
     for (uint64_t nm = (uint64_t) colour; nm < N; nm += (uint64_t) ncolours) {
-        uint32_t ctr[4] = { (uint32_t) sweep_step, (uint32_t)(sweep_step >> 32), (uint32_t) nm, 0x80000000u | (uint32_t) chain_id }, w[4];
+        /* one Philox block serves two trials: trial j = nm / ncolours of this half-sweep (nm = colour + j ncolours)
+         * takes words 0,1 (j even) or 2,3 (j odd) of the block keyed by (sweep step, j / 2) */
+        uint64_t j = nm / (uint64_t) ncolours;
+        uint32_t ctr[4] = { (uint32_t) sweep_step, (uint32_t)(sweep_step >> 32), (uint32_t)(j >> 1), 0x80000000u | (uint32_t) chain_id }, w[4];
         jmo_philox4x32_10(ctr, key, w);
-        double rn = w[0] / 4294967296.0, ran = w[1] / 4294967296.0;
+        double rn = w[2 * (j & 1)] / 4294967296.0, ran = w[2 * (j & 1) + 1] / 4294967296.0;
         double md = (rn - 0.5) * 2 * maxStep;
         double rT = r[nm] + md;
         if (fabs(rT) > l / 2.0) continue;
