@@ -11,6 +11,7 @@
 //   ECheck :1965-2095, updateThermo :1941-1961, maxDisAdjust :2100-2115, maxDVAdjust :2120-2139,
 //   relaxVolume :2396-2679, calculateEnergyOfTrialVolumeChange :2783-2827, moveVolume :2831-2916.
 #pragma once
+#include <type_traits>
 #include <math.h>
 #include "pot.cuh"
 
@@ -362,6 +363,11 @@ template <> struct Rng<kRngRecorded> {
     __device__ __forceinline__ double ran() { return u01(next()); }
 };
 
+// Philox stream outside the lock-step (TABLE) mode: the acceptance word of a step exists whether or not the
+// reference would have drawn it, so the banded decisions of pot.cuh apply.
+template <class RNG, bool TABLE>
+constexpr bool kPhiloxProduction = std::is_same<RNG, Rng<kRngPhilox>>::value && !TABLE;
+
 // ---------------------------------------------------------------- trial moves
 
 constexpr uint8_t kLogAccepted = 1, kLogVolume = 2, kLogWall = 4;
@@ -435,10 +441,16 @@ __device__ __forceinline__ uint8_t volume_trial_scaling(Chain<POT> &ch, double r
     const double E12Trial = lRat12 * ch.tot[2];
     const double E6Trial = lRat6 * ch.tot[4];
     const double dE = E12Trial - E6Trial - ch.tot[0];
-    const double bf = exp(-(dE + ch.P * dl) / ch.T + (double) ch.N * log(lRat1));
-    double ran = 0;
-    if (bf < 1.0) ran = rng.ran();
-    if (!(bf >= 1.0 || bf > ran)) { ch.cnt[3]++; return kLogVolume; }
+    bool accepted;
+    if constexpr (kPhiloxProduction<RNG, TABLE>) {                // banded decision (pot.cuh), same outcome
+        accepted = volume_accept(dE + ch.P * dl, ch.T, ch.invT, (double) ch.N, lRat1, rng.ran());
+    } else {
+        const double bf = exp(-(dE + ch.P * dl) / ch.T + (double) ch.N * log(lRat1));
+        double ran = 0;
+        if (bf < 1.0) ran = rng.ran();                            // :1667: drawn only when needed
+        accepted = bf >= 1.0 || bf > ran;
+    }
+    if (!accepted) { ch.cnt[3]++; return kLogVolume; }
     ch.cnt[2]++;
     ch.tot[0] = ch.tot[0] + dE;
     ch.tot[2] = E12Trial;
@@ -466,10 +478,16 @@ __device__ __forceinline__ uint8_t volume_trial_full(Chain<POT> &ch, double rn, 
     const double lRat1 = lnew / ch.l;
     double t[NC];
     full_totals<POT, true, true>(ch, lRat1, lnew, t);
-    const double bf = exp(-(t[0] - ch.tot[0] + ch.P * dl) / ch.T + (double) ch.N * log(lRat1));   // :2249
-    double ran = 0;
-    if (bf < 1.0) ran = rng.ran();
-    if (!(bf >= 1.0 || bf > ran)) { ch.cnt[3]++; return kLogVolume; }
+    bool accepted;
+    if constexpr (kPhiloxProduction<RNG, TABLE>) {
+        accepted = volume_accept(t[0] - ch.tot[0] + ch.P * dl, ch.T, ch.invT, (double) ch.N, lRat1, rng.ran());
+    } else {
+        const double bf = exp(-(t[0] - ch.tot[0] + ch.P * dl) / ch.T + (double) ch.N * log(lRat1));   // :2249
+        double ran = 0;
+        if (bf < 1.0) ran = rng.ran();                            // :2251: drawn only when needed
+        accepted = bf >= 1.0 || bf > ran;
+    }
+    if (!accepted) { ch.cnt[3]++; return kLogVolume; }
     ch.cnt[2]++;
     ch.l = ch.l + dl;
 #pragma unroll

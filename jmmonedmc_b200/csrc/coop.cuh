@@ -330,8 +330,7 @@ __device__ __forceinline__ uint8_t coop_volume_scaling(Coop<POT, G> &c, double r
     const double E12Trial = lRat12 * c.tot[2];
     const double E6Trial = lRat6 * c.tot[4];
     const double dE = E12Trial - E6Trial - c.tot[0];
-    const double bf = exp(-(dE + c.P * dl) / c.T + (double) c.N * log(lRat1));
-    if (!(bf >= 1.0 || bf > ran)) { c.cnt[3]++; return kLogVolume; }
+    if (!volume_accept(dE + c.P * dl, c.T, c.invT, (double) c.N, lRat1, ran)) { c.cnt[3]++; return kLogVolume; }   // :1666-1672
     c.cnt[2]++;
     c.tot[0] = c.tot[0] + dE;
     c.tot[2] = E12Trial;
@@ -353,8 +352,7 @@ __device__ __forceinline__ uint8_t coop_volume_full(Coop<POT, G> &c, double rn, 
     const double lRat1 = lnew / c.l;
     double t[NC];
     coop_full_totals<POT, G, true>(c, lRat1, 2 / lnew, t);
-    const double bf = exp(-(t[0] - c.tot[0] + c.P * dl) / c.T + (double) c.N * log(lRat1));
-    if (!(bf >= 1.0 || bf > ran)) { c.cnt[3]++; return kLogVolume; }
+    if (!volume_accept(t[0] - c.tot[0] + c.P * dl, c.T, c.invT, (double) c.N, lRat1, ran)) { c.cnt[3]++; return kLogVolume; }   // :2249-2255
     c.cnt[2]++;
     c.set_l(c.l + dl);
 #pragma unroll

@@ -73,6 +73,10 @@ __device__ __forceinline__ float exp_neg_approx(double x) {
 }
 constexpr double kMetropolisBand = 1e-5;     // > 30 x the error bound of exp_neg_approx
 
+// Exact Metropolis test, out of line: the band makes it a 2e-5 event, and inlined the compiler hoists its IEEE
+// division and part of exp() above the branch (6 % of the instructions of the C2 kernel, profiles/r02b_c2_*).
+static __device__ __noinline__ bool metropolis_exact(double dE, double T, double ran) { return dE <= 0 || exp(-dE / T) > ran; }
+
 // Metropolis rule of qad2, src/jmmMCState.cpp:1367-1377: accept iff dE <= 0 || exp(-dE/T) > ran.
 // exp() and the IEEE division are ~70 instructions; ran is uniform, so the decision is settled by a cheap
 // approximation ea of exp(-dE/T) unless ran falls within 1e-5 of it (2e-5 of the trials):
@@ -87,7 +91,35 @@ __device__ __forceinline__ bool metropolis_accept(double dE, double T, double in
     const double ea = (double) exp_neg_approx(dE * invT);
     if (ran > ea + kMetropolisBand) return false;
     if (ran < ea - kMetropolisBand) return true;
-    return exp(-dE / T) > ran;
+    return metropolis_exact(dE, T, ran);
+}
+
+// Acceptance of a volume trial, qavLJ :1666-1672 / fav :2249-2255:  bf = exp(-(dE + P dl)/T + N log(lRat1)),
+// accept iff bf >= 1.0 || bf > ran — which is bf > ran, because ran < 1.  (Philox streams only: ran is word 2 of the
+// step's block whether or not the reference would have drawn it; the lock-step kernels draw it only if bf < 1.)
+// exp and log in double precision are ~150 instructions that a warp executes whenever ANY of its chains makes a
+// volume trial (17 % of the steps of C2), so the decision is taken on an approximation b of bf with a rigorous band:
+//   log(s): lg2.approx.ftz.f32 of (float) s — input rounding 2^-24 relative, result within 2^-22.6 absolute (PTX ISA),
+//           float result rounding <= 2^-24 |log2 s|: |error of ln s| <= 1.8e-7 for s in (0.5, 2);
+//   exp(A): exp_neg_approx above, relative error <= 1.6e-7 |A| + 2.4e-7;
+// so |b - bf| <= bf (1.8e-7 N + 1.6e-7 |A| + 2.4e-7).  Four times that is the band; inside it (<= ~1e-5 of the volume
+// trials) the reference expression is evaluated.  NaN fails both comparisons and reaches the exact test, like every
+// s outside (0.5, 2).
+static __device__ __noinline__ bool volume_accept_exact(double x, double T, double n, double s, double ran) {
+    const double bf = exp(-x / T + n * log(s));
+    return bf >= 1.0 || bf > ran;
+}
+
+__device__ __forceinline__ bool volume_accept(double x /* dE + P dl */, double T, double invT, double n, double s, double ran) {
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float) s));
+    const double A = n * ((double) lg * 0.6931471805599453) - x * invT;
+    const double b = (double) exp_neg_approx(-A);
+    const double band = 4.0 * (1.8e-7 * n + 1.6e-7 * fabs(A) + 2.4e-7);
+    const bool narrow = s > 0.5 && s < 2.0;
+    if (narrow && ran < b * (1.0 - band)) return true;
+    if (narrow && ran > b * (1.0 + band)) return false;
+    return volume_accept_exact(x, T, n, s, ran);
 }
 
 }  // namespace jmm
