@@ -225,6 +225,12 @@ const char *jmm_version(void);
  * taus_out[0..n-1] with the first n taus2 words for `seed`, computed ON THE GPU */
 jmm_status jmm_rng_selftest(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4],
                             uint64_t seed, uint32_t *taus_out, uint32_t n, int32_t device);
+/* device-side self-test of the banded acceptance rules (pot.cuh): n random cases each of the Metropolis rule
+ * (src/jmmMCState.cpp:1367-1377) and of the volume rule (:1666-1672, :2249-2255), half of them with the random
+ * number placed within a few ulp .. 1e-4 of the exact acceptance probability, decided both by the banded fast path
+ * and by the reference expression.  counts[0] = Metropolis mismatches, [1] = volume mismatches, [2] / [3] = cases
+ * that reached the exact expression.  A correct build returns counts[0] = counts[1] = 0. */
+jmm_status jmm_accept_selftest(uint64_t n, uint64_t seed, uint64_t counts[4], int32_t device);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         "jmm_last_error": (C.c_char_p, []),
         "jmm_version": (C.c_char_p, []),
         "jmm_rng_selftest": (C.c_int32, [u32p, u32p, u32p, C.c_uint64, u32p, C.c_uint32, C.c_int32]),
+        "jmm_accept_selftest": (C.c_int32, [C.c_uint64, C.c_uint64, u64p, C.c_int32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -146,6 +147,13 @@ def read_input(path) -> tuple[Config, Deck]:
     cfg, deck = Config(), Deck()
     _check(lib().jmm_read_input(str(path).encode(), C.byref(cfg), C.byref(deck)))
     return cfg, deck
+
+
+def accept_selftest(n, seed=1, device=0):
+    """(Metropolis mismatches, volume mismatches, Metropolis cases decided exactly, volume cases decided exactly)."""
+    out = np.zeros(4, dtype=np.uint64)
+    _check(lib().jmm_accept_selftest(int(n), int(seed), out.ctypes.data_as(C.POINTER(C.c_uint64)), int(device)))
+    return tuple(int(x) for x in out)
 
 
 def rng_selftest(ctr, key, seed, n, device=0):

@@ -1111,6 +1111,72 @@ extern "C" double jmm_fp64_peak_tflops(int32_t device) {
     return best;
 }
 
+// ---- self-test of the banded acceptance rules ---------------------------------------------------------------
+__global__ void k_accept_selftest(uint64_t n, uint64_t seed, unsigned long long *counts) {
+    const uint64_t i0 = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad_m = 0, bad_v = 0, ex_m = 0, ex_v = 0;
+    for (uint64_t i = i0; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const Philox4 a = philox4x32_10((uint32_t) i, (uint32_t)(i >> 32), 0x5e1f7e57u, 1u, (uint32_t) seed, (uint32_t)(seed >> 32));
+        const Philox4 b = philox4x32_10((uint32_t) i, (uint32_t)(i >> 32), 0x5e1f7e57u, 2u, (uint32_t) seed, (uint32_t)(seed >> 32));
+        const double T = 0.1 + 1.9 * u01(a.w[0]);
+        // energy changes from -5 T to +30 T, log-uniform magnitudes included through the square
+        const double u = u01(a.w[1]) * 2 - 0.3;
+        const double dE = T * 18.0 * u * fabs(u);
+        double ran = u01(a.w[2]);
+        if (i & 1) {                                   // adversarial: ran next to the exact probability
+            const double p = exp(-dE / T);
+            const double eps = ldexp(1.0, -(int) (a.w[3] % 40) - 13) * ((a.w[3] >> 8 & 1) ? 1.0 : -1.0);    // 1e-4 .. 1e-16
+            ran = p * (1.0 + eps);
+            if (!(ran >= 0.0 && ran < 1.0)) ran = u01(a.w[2]);
+        }
+        const bool want = dE <= 0 || exp(-dE / T) > ran;                              // :1377
+        const double ea = (double) exp_neg_approx(dE * (1.0 / T));
+        if (!(dE <= 0) && !(ran > ea + kMetropolisBand) && !(ran < ea - kMetropolisBand)) ++ex_m;
+        if (metropolis_accept(dE, T, 1.0 / T, ran) != want) ++bad_m;
+
+        // volume rule: N from 2 to 2000, box ratio within +-20 %, x = dE + P dl of either sign
+        const double N = 2.0 + floor(1998.0 * u01(b.w[0]) * u01(b.w[0]));
+        const double s = 0.8 + 0.4 * u01(b.w[1]);
+        const double v = u01(b.w[2]) * 2 - 1;
+        const double x = T * (N * log(s) + 12.0 * v * fabs(v));                        // keeps bf in a useful range
+        double ran2 = u01(b.w[3]);
+        const double bf = exp(-x / T + N * log(s));
+        if (i & 2) {
+            const double eps = ldexp(1.0, -(int) (a.w[3] >> 16 & 31) - 13) * ((a.w[3] >> 9 & 1) ? 1.0 : -1.0);
+            ran2 = bf * (1.0 + eps);
+            if (!(ran2 >= 0.0 && ran2 < 1.0)) ran2 = u01(b.w[3]);
+        }
+        const bool want_v = bf >= 1.0 || bf > ran2;                                   // :1672, :2255
+        if (volume_accept(x, T, 1.0 / T, N, s, ran2) != want_v) ++bad_v;
+        {   // the same band arithmetic as volume_accept, to count how often the exact expression is reached
+            float lg;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float) s));
+            const double A = N * ((double) lg * 0.6931471805599453) - x * (1.0 / T);
+            const double bb = (double) exp_neg_approx(-A);
+            const double band = 4.0 * (1.8e-7 * N + 1.6e-7 * fabs(A) + 2.4e-7);
+            if (!(ran2 < bb * (1.0 - band)) && !(ran2 > bb * (1.0 + band))) ++ex_v;
+        }
+    }
+    atomicAdd(&counts[0], bad_m); atomicAdd(&counts[1], bad_v); atomicAdd(&counts[2], ex_m); atomicAdd(&counts[3], ex_v);
+}
+
+extern "C" jmm_status jmm_accept_selftest(uint64_t n, uint64_t seed, uint64_t counts[4], int32_t device) {
+    if (!counts) return fail(JMM_ERR_INVALID, "jmm_accept_selftest: null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(JMM_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    CK(cudaSetDevice(device));
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc((void **) &d, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+    k_accept_selftest<<<148 * 4, 256>>>(n, seed, d);
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) le = cudaMemcpy(counts, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (le != cudaSuccess) return fail(JMM_ERR_CUDA, cudaGetErrorString(le));
+    return JMM_OK;
+}
+
 extern "C" jmm_status jmm_rng_selftest(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], uint64_t seed,
                                        uint32_t *taus_out, uint32_t n, int32_t device) {
     int ndev = 0;

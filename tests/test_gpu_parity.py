@@ -282,6 +282,16 @@ def test_energy_bookkeeping_stays_consistent(J, O):
     assert abs(np.mean(acc[:, 2] / 5001) - np.mean(s["l"])) < 0.2 * np.mean(s["l"])   # ensemble <L> ~ current L
 
 
+def test_banded_acceptance_rules_decide_like_the_reference_expressions(J):
+    """pot.cuh settles the Metropolis rule (:1367-1377) and the volume rule (:1666-1672, :2249-2255) by cheap
+    approximations with an error band and evaluates the reference expression only inside the band.  40 million random
+    cases each, half with the random number within 1e-4 .. 1e-16 (relative) of the exact acceptance probability: the
+    decision must be the reference's every time, and the exact path must actually be exercised."""
+    bad_m, bad_v, exact_m, exact_v = J.accept_selftest(40_000_000, seed=20261017)
+    assert bad_m == 0 and bad_v == 0
+    assert exact_m > 1000 and exact_v > 1000
+
+
 @pytest.mark.parametrize("arith", ["reference", "fast", "fast-g1", "fast-g8", "fast-g32"])
 @pytest.mark.parametrize("pot,nbn,cutoff,N,C", [("LJcut", 4, 5.0, 20000, 2), ("LJ", 2, math.inf, 5001, 1),
                                                  ("HARMONIC", 1, math.inf, 8192, 3), ("LJ", 24, math.inf, 6000, 2)])
