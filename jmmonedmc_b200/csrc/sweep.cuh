@@ -366,9 +366,13 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
     const int gi = lane32 / G, lane = lane32 % G;
     // the groups of a warp reject at the wall independently: shuffle within the group only
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane32 & ~(G - 1)));
-    const int x_lo = (int) (tile_lo - g0), x_hi = (int) (tile_hi - g0);     // owned window range
+    // range tests as one unsigned compare each: (unsigned)(x - lo) < span
+    const int x_lo = (int) (tile_lo - g0);                                       // owned window range [x_lo, x_lo + own_span)
+    const unsigned own_span = (unsigned) (tile_hi - tile_lo);
     const int x_first_interior = (int) max((int64_t) 0, (int64_t) nbn - g0);   // x >= this: all left partners exist
     const int x_last_interior = (int) (min(g1, N - nbn) - g0) - 1;             // x <= this: all right partners exist
+    const unsigned interior_span = (unsigned) max(0, x_last_interior - x_first_interior + 1);
+    const int x_end0 = (int) (((g1 == N) ? N : g1 - nbn) - g0), x_end_step = (g1 == N) ? 0 : nbn;   // x_end of half-sweep t
     const int w_lo = max(0, warp - rad), w_hi = min(nwarps - 1, warp + rad);
     uint32_t n_acc = 0, n_try = 0;
 
@@ -388,10 +392,11 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
     const bool interior_first = rad == 1 && K >= 6;
     const int r_wait = interior_first ? (K - 5) / GPW : 0, rot = interior_first ? 2 : 0;
     for (int t = 0; t < nsub; ++t) {
-        const int x_end = (int) (((g1 == N) ? N : g1 - (int64_t)(t + 1) * nbn) - g0);
+        const int x_end = x_end0 - t * x_end_step;
         const uint32_t s_lo = (uint32_t)(step0 + t), s_hi = (uint32_t)((step0 + t) >> 32);
         double acc6 = 0, acc12 = 0;
         const int x_valid = firsts[t], x_base = bases[t] + warp * K * ncol;
+        const unsigned valid_span = (unsigned) max(0, x_end - x_valid);
         const uint32_t j_base = jbs[t] + (uint32_t) (warp * K);       // trial index of offset 0 (even for G = 1: K is)
         Philox4 ahead{};
         for (int r = 0; r < rounds; ++r) {
@@ -445,21 +450,21 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
                 w1 = __shfl_sync(gmask, ahead.w[1], rb, G);
             }
             const int x = x_base + o * ncol;
-            if (x < x_valid || x >= x_end) continue;
+            if ((unsigned) (x - x_valid) >= valid_span) continue;
 #ifdef JMM_ABL_NOPHILOX
             w0 = (s_lo * 2654435761u) ^ ((uint32_t)(g0 + x) * 2246822519u); w1 = w0 * 3266489917u + tag;
 #endif
-            const double rn = u01(w0), ran = u01(w1);
+            const double ran = u01_shifted(w1, 1.0);                                  // = w1 / 2^32 exactly
             const double rnm = w[x];
-            const double md = (rn - 0.5) * step2;                                     // qad2 :1182 ((rn-.5)*2*maxStep, 2*maxStep exact)
+            const double md = u01_shifted(w0, 1.5) * step2;                           // qad2 :1182 ((rn-.5)*2*maxStep; rn-.5 and 2*maxStep exact)
             const double rT = rnm + md;                                               // :1183
-            const bool owned = (x >= x_lo) && (x < x_hi);
+            const bool owned = (unsigned) (x - x_lo) < own_span;
             if (owned && lane == 0) ++n_try;
             // :1188: a move through the wall is rejected whatever its energy; only the two ends of a chain can get
             // there, so it is a predicate on the decision, not a branch around the pair terms
             const bool inside = !(fabs(rT) > half_l);
             double s6 = 0, s12 = 0;
-            if (x >= x_first_interior && x <= x_last_interior) {
+            if ((unsigned) (x - x_first_interior) < interior_span) {
                 if constexpr (NB > 0) {
                     static_assert(NB == 0 || G == 1, "compile-time NBN is a G = 1 specialisation");
                     double t6 = 0, t12 = 0;                   // right partners apart: two independent accumulation chains
