@@ -641,6 +641,9 @@ void jmo_set_r(jmo_state *s, const double *r, double l) {
             for (uint64_t j = i + 1; j < s->N; j++) s->rij[pair_index(s->N, i, j)] = s->r[j] - s->r[i];
     full_recompute_into_state(s);
 }
+/* continue at a given step number: what the restart branch of setupMCS does with the step count of the last frame
+ * (src/jmmMCState.cpp:641); the print/histogram marks follow as at :692,711,739 */
+void jmo_set_sn(jmo_state *s, uint64_t sn) { s->sn = sn; s->sltp = sn; s->slrho = sn; s->slg = sn; }
 void jmo_get_totals(const jmo_state *s, double out[9]) { memcpy(out, s->tot, sizeof s->tot); }
 void jmo_get_accum(const jmo_state *s, double out[12]) { memcpy(out, s->acc, sizeof s->acc); }
 void jmo_zero_accum(jmo_state *s) { memset(s->acc, 0, sizeof s->acc); }

@@ -116,6 +116,7 @@ void jmo_run_deck_hist(jmo_state *s, uint64_t numsteps, uint64_t tpi, uint64_t c
 uint64_t jmo_colour_halfsweep(double *r, uint64_t N, double l, int nbn, int pot, double cutoff,
                               double T, double maxStep, uint64_t seed, uint64_t chain_id,
                               uint64_t sweep_step, int ncolours, int colour, double dtot[9]);
+void     jmo_set_sn(jmo_state *s, uint64_t sn);
 int      jmo_colour_of_step(uint64_t seed, uint64_t chain_id, uint64_t sweep_step, int ncolours);
 
 #ifdef __cplusplus

@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
         for name in ("jmo_N", "jmo_sn", "jmo_relax_calls"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_uint64
+        L.jmo_set_sn.argtypes = [C.c_void_p, C.c_uint64]
+        L.jmo_set_sn.restype = None
         L.jmo_l.argtypes = [C.c_void_p]
         L.jmo_l.restype = C.c_double
         L.jmo_get_r.argtypes = [C.c_void_p, dp]
@@ -186,6 +188,9 @@ class Chain:
     def N(self): return int(self.L.jmo_N(self.h))
     @property
     def sn(self): return int(self.L.jmo_sn(self.h))
+    def set_step_number(self, sn): self.L.jmo_set_sn(self.h, int(sn))
+    @property
+    def relax_calls(self): return int(self.L.jmo_relax_calls(self.h))
     @property
     def l(self): return float(self.L.jmo_l(self.h))
 

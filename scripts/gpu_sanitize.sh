@@ -24,6 +24,10 @@ cases = {
  "prod": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), run(config(nchains=70, **lj)), run(config(nchains=70, arith=J.ARITH_FAST, **ljc))),
  "sliced": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), os.environ.__setitem__("JMM_FORCE_SLICE", "1"), os.environ.__setitem__("JMM_SLICE_CHUNK", "7"), run(config(nchains=70, **lj))),
  "generic": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), os.environ.__setitem__("JMM_NO_PROD", "1"), run(config(nchains=40, **ljc)), run(config(nchains=3, mode=J.MODE_TABLE, rng_kind=J.RNG_TAUS2, adapt=J.ADAPT_HOST, **lj))),
+ "sweep_shapes": lambda: (os.environ.__setitem__("JMM_SWEEP_G", "8"), os.environ.__setitem__("JMM_SWEEP_WARPS", "4"), os.environ.__setitem__("JMM_SWEEP_K", "1"),
+                   run(config(N=30000, pot=J.POT_LJ, nbn=20, ensemble=J.ENS_NLT, L=33600.0, T=0.9, maxStep=0.12, seed=3, nchains=1, mode=J.MODE_CHECKERBOARD, arith=J.ARITH_FAST), 12, True),
+                   os.environ.__setitem__("JMM_SWEEP_G", "1"), os.environ.__setitem__("JMM_SWEEP_WARPS", "3"),
+                   run(config(N=60000, pot=J.POT_LJCUT, nbn=4, cutoff=5.0, ensemble=J.ENS_NLT, L=67200.0, T=0.9, maxStep=0.12, seed=3, nchains=1, mode=J.MODE_CHECKERBOARD, arith=J.ARITH_FAST), 12, True)),
  "sweep": lambda: (run(config(N=3000, pot=J.POT_LJCUT, nbn=4, cutoff=5.0, ensemble=J.ENS_NLT, L=3360.0, T=0.9, maxStep=0.12, seed=3, nchains=2, mode=J.MODE_CHECKERBOARD), 11, True),
                    run(config(N=3000, pot=J.POT_LJ, nbn=20, ensemble=J.ENS_NLT, L=3360.0, T=0.9, maxStep=0.12, seed=3, nchains=2, mode=J.MODE_CHECKERBOARD, arith=J.ARITH_FAST), 25, True)),
 }
@@ -31,7 +35,7 @@ for k, f in cases.items():
     if which in ("all", k): f(); print("case", k, "ok")
 PY
 for tool in memcheck racecheck; do
-  for c in bond coop prod sliced generic sweep; do
+  for c in ${SAN_CASES:-bond coop prod sliced generic sweep sweep_shapes}; do
     echo "== $tool $c"
     SAN_CASE=$c timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|case|Error|error|hazard|Invalid" | head -8
   done

@@ -195,6 +195,38 @@ def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
         assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
 
 
+@pytest.mark.parametrize("engine", ["coop", "prod", "sliced"])
+def test_continue_at_a_step_number_matches_oracle(J, O, engine, monkeypatch):
+    """jmm_set_step_number (restart at the step count of a frame, src/jmmMCState.cpp:641): the Philox blocks and the
+    relaxVolume cadence (every 10 000 steps below 1 000 000, src/Main.cpp:173) follow the step number.  From step
+    989 500 a run of 12 000 steps relaxes at 990 000 and must not at 1 000 000; every chain equals the oracle."""
+    for k, v in ENGINES[engine].items():
+        monkeypatch.setenv(k, v)
+    d = dict(DECKS["small"], ENGCHECK=5000, DADJ=4000, VADJ=6000)
+    C, sn0, nsteps, id0 = 33, 989_500, 12_000, 40
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C, chain_id0=id0)
+    with J.Handle(cfg) as h:
+        h.start()
+        h.set_step_number(sn0)
+        assert h.step_number == sn0
+        h.step(nsteps)
+        assert h.step_number == sn0 + nsteps
+        s = h.get_state()
+        ms, mv = h.get_step_sizes()
+    for c in (0, 7, 32):
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=id0 + c))
+        oc.start()
+        oc.set_step_number(sn0)
+        relax0 = oc.relax_calls
+        for _ in range(nsteps):
+            oc.step(); oc.cadence()
+        assert oc.relax_calls == relax0 + 1                       # 990 000 only
+        assert bits_equal(s["r"][c], oc.r) and bits_equal(s["l"][c:c + 1], [oc.l])
+        assert np.array_equal(s["counters"][c], oc.counters)
+        assert bits_equal(s["totals"][c], oc.totals) and bits_equal(s["accum"][c], oc.accum)
+        assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
+
+
 @pytest.mark.parametrize("variant", ["unroll4", "unroll8", "sliced"])
 @pytest.mark.parametrize("name", ["small", "ljcut_nbn", "nlt"])
 def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, variant, monkeypatch):
@@ -362,6 +394,36 @@ def test_checkerboard_launch_shapes_match_oracle(J, O, pot, nbn, cutoff, N, C, s
             a, _ = O.colour_halfsweep(r, L, nbn, O.POT[pot], cutoff, T, ms, seed, id0 + c, t, ncol, col)
             nacc += a; ntry += len(range(col, N, ncol))
         assert bits_equal(s["r"][c], r), f"chain {c}: positions after {nhs} half-sweeps with {shape}"
+        assert int(s["counters"][c][0]) == nacc and int(s["counters"][c].sum()) == ntry
+        assert totals_close(s["totals"][c], fresh[c], 1e-11)
+    assert trials == sum(int(x) for x in s["counters"].sum(axis=1))
+
+
+@pytest.mark.parametrize("pot,nbn,cutoff,N,C,nhs", [("LJcut", 4, 5.0, 1 << 20, 1, 150), ("LJ", 64, math.inf, 1 << 18, 8, 60)])
+def test_checkerboard_at_bench_size_matches_oracle(J, O, pot, nbn, cutoff, N, C, nhs):
+    """BASELINE.json configs C3 and C5 at their FULL size and with the launch shape bench.py runs (one 24-warp CTA
+    per SM, neighbour hand-shakes instead of block barriers, in-kernel reductions, more than one launch): positions
+    bit-identical to the oracle, counters equal, totals equal to a fresh evaluation.  compute-sanitizer's racecheck
+    cannot follow the flag protocol of sweep.cuh (profiles/r02g_sanitizer.txt); this is the check that it holds."""
+    from jmmonedmc_b200.capi import config
+    seed, id0, T, ms = 92847, 0, 0.9, 0.12
+    L = N * 1.12
+    cfg = config(N=N, pot={"LJ": J.POT_LJ, "LJcut": J.POT_LJCUT}[pot], nbn=nbn, cutoff=cutoff, ensemble=J.ENS_NLT, L=L, T=T,
+                 maxStep=ms, seed=seed, nchains=C, chain_id0=id0, mode=J.MODE_CHECKERBOARD, arith=J.ARITH_FAST)
+    with J.Handle(cfg) as h:
+        h.start()
+        trials = h.sweep(nhs)
+        s = h.get_state()
+        fresh = h.energy()
+    ncol = nbn + 1
+    for c in range(C):
+        r = ((np.arange(N) + 0.5) / N - 0.5) * L
+        nacc = ntry = 0
+        for t in range(nhs):
+            col = O.colour_of_step(seed, id0 + c, t, ncol)
+            a, _ = O.colour_halfsweep(r, L, nbn, O.POT[pot], cutoff, T, ms, seed, id0 + c, t, ncol, col)
+            nacc += a; ntry += len(range(col, N, ncol))
+        assert bits_equal(s["r"][c], r), f"chain {c}: positions after {nhs} half-sweeps"
         assert int(s["counters"][c][0]) == nacc and int(s["counters"][c].sum()) == ntry
         assert totals_close(s["totals"][c], fresh[c], 1e-11)
     assert trials == sum(int(x) for x in s["counters"].sum(axis=1))
