@@ -81,12 +81,25 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def run_reference_sample(numsteps: int, nproc: int) -> dict:
+def deck_text_c4(numsteps: int, seed: int) -> str:
+    """One chain of the C4 sweep (scripts/RunJobs.bash:40-62 deck, P = T = 0.5) for the reference binary: prints pushed
+    out, histograms reduced to one bin."""
+    big = 10 ** 12
+    return (f"N          80\nP          0.5\nT          0.5\nNUMSTEPS   {numsteps}\nPOT        LJ\nNBN        -1\nRELAX\n"
+            f"MAXSTEP    0.1\nMAXDV      2.0\nCPI        {big}\nTPI        {big}\nRBW        0.1\nRHONB      1\n"
+            f"RHOPI      {big}\nGSW        200\nGNS        1\nGBW        0.1\nGNB        1\nGPI        {big}\n"
+            f"SEED       {seed}\nENGCHECK   10000\nDADJ       1000000\nVADJ       1000000\n")
+
+
+def run_reference_sample(numsteps: int, nproc: int, deck=None, what: str = "C2") -> dict:
     """nproc independent single-threaded copies of the compiled reference, one deck each."""
+    deck = deck or deck_text
     from oracle import oracle as O
     if not O.REF_BIN.exists():
         O.build()
     if not O.REF_BIN.exists():
+        if what != "C2":
+            raise RuntimeError("oracle/_ref/jmmOneDMC_ref is missing")
         return run_port_sample(numsteps, nproc)
     with tempfile.TemporaryDirectory() as tmp:
         procs = []
@@ -95,7 +108,7 @@ def run_reference_sample(numsteps: int, nproc: int) -> dict:
         for p in range(nproc):
             d = Path(tmp) / f"p{p}"
             d.mkdir()
-            (d / "INPUT").write_text(deck_text(numsteps, 125 + p))
+            (d / "INPUT").write_text(deck(numsteps, 125 + p))
         t0 = time.perf_counter()
         for p in range(nproc):
             procs.append(subprocess.Popen([str(O.REF_BIN)], cwd=Path(tmp) / f"p{p}", env=env,
@@ -106,7 +119,7 @@ def run_reference_sample(numsteps: int, nproc: int) -> dict:
         raise RuntimeError(f"reference binary failed: {rcs}")
     return {"seconds": dt, "trials": numsteps * nproc, "kind": "reference", "cores": nproc,
             "sample": f"{nproc} independent single-thread processes of oracle/_ref/jmmOneDMC_ref (reference Main.cpp "
-                      f"-O3, OMP_NUM_THREADS=1) x {numsteps} steps of the C2 deck, stdout to /dev/null, set-up included"}
+                      f"-O3, OMP_NUM_THREADS=1) x {numsteps} steps of the {what} deck, stdout to /dev/null, set-up included"}
 
 
 def run_port_sample(numsteps: int, nproc: int) -> dict:
@@ -124,6 +137,51 @@ def run_port_sample(numsteps: int, nproc: int) -> dict:
     return {"seconds": dt, "trials": numsteps * nproc, "kind": "port", "cores": nproc,
             "sample": f"{nproc} processes of the C restatement (oracle/jmm_oracle.c, table mode) x {numsteps} steps, "
                       "interpreter start-up included"}
+
+
+def run_sweep_port_sample(w: dict, nhs: int, nproc: int) -> dict:
+    """C3/C5 on the CPU: the reference cannot allocate these sizes (232 B x N^2/2 of pair tables), so the
+    O(N x neighbours) C restatement of the colour half-sweep (oracle/jmm_oracle.c) is timed, one chain per process."""
+    code = ("import sys, numpy as np; sys.path.insert(0, %r)\nfrom oracle import oracle as O\n"
+            "N, nbn, nhs, cid = %d, %d, %d, int(sys.argv[1]); L = 1.12 * N; ncol = nbn + 1\n"
+            "r = ((np.arange(N) + 0.5) / N - 0.5) * L; n = 0\n"
+            "for t in range(nhs):\n"
+            "    col = O.colour_of_step(%d, cid, t, ncol)\n"
+            "    O.colour_halfsweep(r, L, nbn, O.POT[%r], %r, %r, %r, %d, cid, t, ncol, col)\n"
+            "    n += len(range(col, N, ncol))\n"
+            "print(n)\n") % (str(ROOT), w["N"], w["nbn"], nhs, w["seed"], w["pot"],
+                             float(w["cutoff"]) if math.isfinite(w["cutoff"]) else 1e300, w["T"], w["maxStep"], w["seed"])
+    from oracle import oracle as O
+    O.build()
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(p)], stdout=subprocess.PIPE, text=True) for p in range(nproc)]
+    outs = [p.communicate()[0] for p in procs]
+    dt = time.perf_counter() - t0
+    if any(p.returncode for p in procs):
+        raise RuntimeError("oracle port failed")
+    return {"seconds": dt, "trials": sum(int(o.strip().splitlines()[-1]) for o in outs), "kind": "port", "cores": nproc,
+            "sample": f"{nproc} process(es) of the C restatement of the colour half-sweep (oracle/jmm_oracle.c, reference "
+                      f"arithmetic) x {nhs} half-sweeps of one N={w['N']} chain each, interpreter start-up included; the "
+                      "reference itself cannot allocate this N"}
+
+
+def cpu_baseline_extra(workload: str, w: dict) -> dict:
+    """Bounded CPU sample of a secondary workload on the box's host cores (SURVEY §8d side-by-side)."""
+    cores = host_cores()
+    try:
+        if w["kind"] == "chains":
+            smp = run_reference_sample(int(os.environ.get("JMM_BENCH_CPU_STEPS", "400000")), cores, deck_text_c4, "C4 (one chain)")
+        else:
+            nhs = {"c3": 80, "c5": 300}.get(workload, 40)
+            smp = run_sweep_port_sample(w, nhs, cores)
+            one = run_sweep_port_sample(w, max(1, nhs // 4), 1)
+            smp["single_core_value"] = one["trials"] / one["seconds"]
+        out = {"value": smp["trials"] / smp["seconds"], "unit": UNIT, "cores": smp["cores"], "kind": smp["kind"], "sample": smp["sample"]}
+        if "single_core_value" in smp:
+            out["single_core_value"] = smp["single_core_value"]
+        return out
+    except Exception as e:                      # the baseline is reported, never required
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
 
 def reference_arm(args) -> None:
@@ -347,7 +405,7 @@ def gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
-def measure_extra(workload: str, arith: str, hist: bool, steps: int, warmup: int, rank: int, world: int, local: int):
+def measure_extra(workload: str, arith: str, hist: bool, steps: int, warmup: int, rank: int, world: int, local: int, cpu: bool = False):
     """One secondary workload on an initialised device/process group; returns the JSON line on rank 0 (None elsewhere)."""
     import numpy as np
     import torch
@@ -442,7 +500,7 @@ def measure_extra(workload: str, arith: str, hist: bool, steps: int, warmup: int
                                  "peak": float(peaks.get("hbm_gbs", 6650.0)),
                                  "frac": per_gpu * w["bytes_per_trial"] / 1e9 / float(peaks.get("hbm_gbs", 6650.0))}},
                 "acceptance": float(st["counters"][:, 0].sum() / max(1, st["counters"][:, :2].sum())),
-                "e2e": None, "cpu_baseline": None}
+                "e2e": None, "cpu_baseline": cpu_baseline_extra(workload, w) if cpu else None}
     h.close()
     del flush
     return line
@@ -462,7 +520,7 @@ def extra_arm(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     J.build()
-    line = measure_extra(args.workload, args.arith, args.hist, args.steps, args.warmup, rank, world, local)
+    line = measure_extra(args.workload, args.arith, args.hist, args.steps, args.warmup, rank, world, local, cpu=not args.no_cpu)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -479,6 +537,7 @@ def main():
     ap.add_argument("--arith", default="reference", choices=["reference", "fast"], help="c3/c4/c5: JMM_ARITH_*")
     ap.add_argument("--hist", action="store_true", help="c4 only: rho(x)/g(x) histograms with the RunJobs geometry")
     ap.add_argument("--no-extras", action="store_true", help="c2: skip the short C3/C4/C5 runs reported as other_workloads")
+    ap.add_argument("--no-cpu", action="store_true", help="c3/c4/c5: skip the CPU side-by-side sample (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

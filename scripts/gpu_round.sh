@@ -18,17 +18,18 @@ for k,v in d["other_workloads"].items(): print(k, v.get("value"), v.get("fp64_fr
 EOF
 tail -3 $OUT/bench_$TAG.err
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 2>> $OUT/bench_$TAG.err | tee $OUT/bench_ref_$TAG.json | cut -c1-300
+bash scripts/bench_workloads.sh $TAG
 # launch list (cold-cache, serialised: shares only)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_launches_$TAG.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step -s 3 -c 1 -f -o $OUT/prof_c2_$TAG \
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_c2_$TAG.log 2>&1; tail -1 $OUT/ncu_c2_$TAG.log | cut -c1-200
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_prod -s 1 -c 1 -f -o $OUT/prof_c4fast_$TAG \
-    python bench.py --workload c4 --arith fast --steps 1 --warmup 3 > $OUT/ncu_c4fast_$TAG.log 2>&1; tail -1 $OUT/ncu_c4fast_$TAG.log | cut -c1-200
+    python bench.py --workload c4 --arith fast --steps 1 --warmup 3 --no-cpu > $OUT/ncu_c4fast_$TAG.log 2>&1; tail -1 $OUT/ncu_c4fast_$TAG.log | cut -c1-200
 for w in c3 c5; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_sweep_fast -s 4 -c 1 -f -o $OUT/prof_${w}fast_$TAG \
-      python bench.py --workload $w --arith fast --steps 1 --warmup 3 > $OUT/ncu_${w}fast_$TAG.log 2>&1; tail -1 $OUT/ncu_${w}fast_$TAG.log | cut -c1-200
+      python bench.py --workload $w --arith fast --steps 1 --warmup 3 --no-cpu > $OUT/ncu_${w}fast_$TAG.log 2>&1; tail -1 $OUT/ncu_${w}fast_$TAG.log | cut -c1-200
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_${w}fast_$TAG.csv \
-      python bench.py --workload $w --arith fast --steps 1 --warmup 3 > /dev/null 2>&1
+      python bench.py --workload $w --arith fast --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
 done
 ls -la $OUT | tail -20
