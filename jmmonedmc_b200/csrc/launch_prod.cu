@@ -11,23 +11,29 @@ static cudaError_t launch_step_prod_u(jmm_handle *h, const StepArgs &a) {
     auto kern = a.accept_log ? k_chains_step_prod<POT, ARITH, true, UNROLL> : k_chains_step_prod<POT, ARITH, false, UNROLL>;
     auto sliced = a.accept_log ? k_chains_step_prod_sliced<POT, ARITH, true, UNROLL> : k_chains_step_prod_sliced<POT, ARITH, false, UNROLL>;
     cudaError_t e;
-    const size_t smem = h->smem;                          // [N][32] doubles
+    const size_t tile_bytes = h->smem;                    // [N][32] doubles
+    const unsigned ntiles = nblk(h->S.nchains, kTile);
+    // warps (= tiles) per CTA: as many tiles as fit in the 227 KB of one CTA, at most kProdMaxWarps (registers)
+    int nw = (int) std::min<size_t>(kProdMaxWarps<ARITH>, (227 * 1024 - 1024) / tile_bytes);
+    if (const char *ev = getenv("JMM_PROD_WARPS")) nw = std::max(1, std::min(nw, atoi(ev)));
+    nw = std::max(1, std::min<int>(nw, (int) ntiles));
+    const size_t smem = tile_bytes * nw;
     if (smem > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(sliced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
     }
-    const unsigned ntiles = nblk(h->S.nchains, kTile);
-    // how many CTAs of the sliced kernel are co-resident on this device
+    // how many warps of the sliced kernel are co-resident on this device
     int per_sm = 0, nsm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sliced, kTile, smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sliced, nw * kTile, smem)) != cudaSuccess) return e;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    const unsigned slots = (unsigned) std::max(1, per_sm * nsm);
+    const unsigned ctas = (unsigned) std::max(1, per_sm * nsm);
+    const unsigned slots = ctas * (unsigned) nw;
     const double waves = (double) ntiles / slots;
     // (histogram bins are only touched by REDs and L2 reads, so a chain may change SM between chunks)
     const bool slice = getenv("JMM_FORCE_SLICE") ||
                        (!getenv("JMM_NO_SLICE") && ntiles > slots && (waves - floor(waves)) < 0.85 && a.nsteps >= 16);
     if (!slice) {
-        kern<<<ntiles, kTile, smem, h->stream>>>(h->S, a, h->H);
+        kern<<<nblk(ntiles, nw), nw * kTile, smem, h->stream>>>(h->S, a, h->H, ntiles);
         h->launches++;
         return cudaGetLastError();
     }
@@ -42,7 +48,8 @@ static cudaError_t launch_step_prod_u(jmm_handle *h, const StepArgs &a) {
         h->work_words = (size_t) ntiles + 1;
     }
     if ((e = cudaMemsetAsync(h->d_work, 0, ((size_t) ntiles + 1) * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
-    sliced<<<std::min(slots, ntiles * nchunks), kTile, smem, h->stream>>>(h->S, a, h->H, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
+    const unsigned grid = std::min(ctas, nblk((uint64_t) ntiles * nchunks, nw));
+    sliced<<<grid, nw * kTile, smem, h->stream>>>(h->S, a, h->H, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
     h->launches++;
     return cudaGetLastError();
 }

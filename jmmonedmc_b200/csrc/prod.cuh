@@ -118,8 +118,9 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
                                               uint64_t sn0, uint32_t count, uint64_t log_row0, bool own = true) {
     const bool lead = own;                                   // the lane that owns the chain's global state
     Chain<POT> ch;
-    load_chain<POT, COHERENT>(ch, S, c, smem + threadIdx.x, kTile);   // ch.r -> shared tile (rare paths use it generically)
-    double *rs = smem + threadIdx.x;                         // same column, known to be shared memory
+    const uint32_t lane = threadIdx.x & 31;                  // a tile belongs to ONE warp; a CTA holds several tiles
+    load_chain<POT, COHERENT>(ch, S, c, smem + lane, kTile);   // ch.r -> shared tile (rare paths use it generically)
+    double *rs = smem + lane;                                // same column, known to be shared memory
 
     Rng<kRngPhilox> rng;
     rng.k0 = (uint32_t) S.seed; rng.k1 = (uint32_t)(S.seed >> 32); rng.chain = (uint32_t)(S.chain_id0 + c);
@@ -170,7 +171,7 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
                 pend &= pend - 1;
                 const double f = __shfl_sync(0xffffffffu, vscale, src);
                 double *col = smem + src;
-                for (uint32_t i = threadIdx.x; i < ch.N; i += kTile) col[i * kTile] = col[i * kTile] * f;
+                for (uint32_t i = lane; i < ch.N; i += kTile) col[i * kTile] = col[i * kTile] * f;
             }
             __syncwarp();
         }
@@ -202,34 +203,43 @@ __device__ __forceinline__ void prod_run_tile(const ChainsDev &S, const StepArgs
     }
 }
 
-// 10 one-warp CTAs per SM is what the [80][32] tile of C4 allows: up to 204 registers per thread
-constexpr int kProdMinCtas = 10;
+// One CTA per SM, one tile per WARP: the [80][32] tile of C4 is 20 KB, and ten one-warp CTAs were all that fit
+// (every CTA also reserves 1 KB of shared memory), but one CTA of eleven warps holds eleven tiles in 220 KB of its
+// 227 KB.  The warps of a CTA never synchronise with each other.  Fast arithmetic: <= 12 warps (65536 / (12 x 32) =
+// 170 registers, it needs 164); reference arithmetic: <= 10 warps (204 registers, as with the one-warp CTAs).
+template <int ARITH> constexpr int kProdMaxWarps = ARITH == kArithFast ? 12 : 10;
 
 template <int POT, int ARITH, bool LOG, int UNROLL>
-__global__ void __launch_bounds__(kTile, kProdMinCtas) k_chains_step_prod(ChainsDev S, StepArgs a, HistDev H) {
+__global__ void __launch_bounds__(kProdMaxWarps<ARITH> * kTile, 1) k_chains_step_prod(ChainsDev S, StepArgs a, HistDev H, uint32_t ntiles) {
     extern __shared__ double smem[];
-    const uint64_t c = (uint64_t) blockIdx.x * kTile + threadIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const uint32_t tile = blockIdx.x * nwarps + warp;
+    if (tile >= ntiles) return;                              // (a whole warp)
+    const uint64_t c = (uint64_t) tile * kTile + lane;
     const bool own = c < S.nchains;
-    prod_run_tile<POT, ARITH, LOG, false, UNROLL>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0, (uint32_t) a.nsteps, 0, own);
+    prod_run_tile<POT, ARITH, LOG, false, UNROLL>(S, a, H, own ? c : S.nchains - 1, smem + (size_t) warp * S.N * kTile, a.sn0,
+                                                  (uint32_t) a.nsteps, 0, own);
 }
 
 // Persistent, time-sliced variant for launches that would otherwise need a fractional number of waves
-// (65 536 chains = 2048 tiles on 1480 resident CTAs = 1.38 waves: the last 0.38 wave leaves most SMs idle).
+// (65 536 chains = 2048 tiles on 1628 resident warps = 1.26 waves: the last 0.26 wave leaves most SMs idle).
 // The grid is exactly the number of co-resident CTAs.  Work items are (chunk, tile) pairs, chunk-major, handed
-// out by an atomic counter; a tile's chunk k+1 waits for its chunk k through a per-tile progress word
-// (release/acquire).  Every earlier item is held by a running CTA, so the wait always ends.  Chain state goes
+// out to the WARPS by an atomic counter; a tile's chunk k+1 waits for its chunk k through a per-tile progress word
+// (release/acquire).  Every earlier item is held by a running warp, so the wait always ends.  Chain state goes
 // through L2 between chunks (8N+256 B per chain per chunk: negligible next to `chunk` steps of work).
 template <int POT, int ARITH, bool LOG, int UNROLL>
-__global__ void __launch_bounds__(kTile, kProdMinCtas) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, HistDev H, uint32_t chunk, uint32_t ntiles,
+__global__ void __launch_bounds__(kProdMaxWarps<ARITH> * kTile, 1) k_chains_step_prod_sliced(ChainsDev S, StepArgs a, HistDev H, uint32_t chunk, uint32_t ntiles,
                                                                    uint32_t nchunks, unsigned int *work, unsigned int *progress) {
     extern __shared__ double smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *tile_smem = smem + (size_t) warp * S.N * kTile;
     for (;;) {
         unsigned int item = 0;
-        if (threadIdx.x == 0) item = atomicAdd(work, 1u);
+        if (lane == 0) item = atomicAdd(work, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= ntiles * nchunks) return;
         const uint32_t tile = item % ntiles, k = item / ntiles;
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             unsigned int seen;
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
@@ -237,14 +247,14 @@ __global__ void __launch_bounds__(kTile, kProdMinCtas) k_chains_step_prod_sliced
             } while (seen < k);
         }
         __syncwarp();
-        const uint64_t c = (uint64_t) tile * kTile + threadIdx.x;
+        const uint64_t c = (uint64_t) tile * kTile + lane;
         const uint32_t s0 = k * chunk;
         const uint32_t count = min(chunk, (uint32_t) a.nsteps - s0);
         const bool own = c < S.nchains;
-        prod_run_tile<POT, ARITH, LOG, true, UNROLL>(S, a, H, own ? c : S.nchains - 1, smem, a.sn0 + s0, count, s0, own);
+        prod_run_tile<POT, ARITH, LOG, true, UNROLL>(S, a, H, own ? c : S.nchains - 1, tile_smem, a.sn0 + s0, count, s0, own);
         __threadfence();
         __syncwarp();
-        if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(progress + tile), "r"(k + 1) : "memory");
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(progress + tile), "r"(k + 1) : "memory");
     }
 }
 
