@@ -389,9 +389,9 @@ def gpu_arm(args) -> None:
                                         "MEASURED_PEAKS.json has no fp64 entry",
                          "flop_per_trial": FLOP_PER_TRIAL, "kernel_ms": k_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed
-                         # ncu --set full capture (profiles/r02f_c2_k_chains_step_bond.txt); the 2.75 MB of state
+                         # ncu --set full capture (profiles/r02p_c2_k_chains_step_bond.txt); the 2.75 MB of state
                          # (algorithmic bytes) mostly stay in the 126 MB L2 between launches
-                         "traffic": 1259008,
+                         "traffic": 1240320,
                          "note": "serial Markov chains: latency-bound, see DESIGN.md §roofline",
                          "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,

@@ -29,8 +29,11 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
     const bool inf = std::isinf(h->S.cutoff);
     auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
                              : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
-    const unsigned per_block = 128 / kB2G;
-    kern<<<nblk(h->S.nchains, per_block), 128, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
+    // threads per CTA: 128 (a warp per sub-partition); JMM_BOND_BLOCK = 32, 64 or 96 for wave-quantisation experiments
+    unsigned threads = 128;
+    if (const char *e = getenv("JMM_BOND_BLOCK")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) threads = (unsigned) v; }
+    const unsigned per_block = threads / kB2G;
+    kern<<<nblk(h->S.nchains, per_block), threads, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
     h->launches++;
     return cudaGetLastError();
 }
