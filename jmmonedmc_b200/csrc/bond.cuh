@@ -154,13 +154,7 @@ __device__ __forceinline__ void b2_adapt(B2Chain &c, const StepArgs &a, bool dis
     }
 }
 
-// ECI1: ENGCHECK 1 (the INPUTstd deck): every step ends with an ECheck, so its bond energies are evaluated at the
-// START of the step, beside the displacement trial (two independent dependent chains instead of one after the other),
-// from the positions before the move; the two bonds of the moved particle are then replaced by the new bond energies
-// the trial has just evaluated: ETest(after) = sum_i e_i(before) + (accepted ? dE : 0), every term a fresh evaluation
-// from positions.  ETest is only compared with the running E to 1e-4 (:1998) and a discrepancy is re-decided on the
-// reference-order sum (coop_energy_check), so its order of summation is free.
-template <bool LOG, bool INF, bool ECI1>
+template <bool LOG, bool INF>
 __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs a, int npad) {
     extern __shared__ double smem[];
     const uint32_t gib = threadIdx.x / kB2G, lane = threadIdx.x % kB2G;
@@ -211,29 +205,19 @@ __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs 
         ++batch_pos;
 
         uint8_t fA;
-        double eA = 0;
-        bool have_e = false;
         if (nmA < N) {
-            if constexpr (ECI1) {
-                eA = b2_etest_partial<INF>(A);         // bonds of the configuration BEFORE the move
-#pragma unroll
-                for (int o = kB2G / 2; o > 0; o >>= 1) eA += __shfl_xor_sync(gmask, eA, o, kB2G);
-            }
             B2Trial tA = b2_displacement<INF>(A, nmA, rnA, ranA);
             if (!(tA.decided | tA.wall)) b2_resolve(A, tA, ranA);
             __syncwarp(gmask);                         // every lane has read the positions
             fA = b2_commit(A, tA);
             __syncwarp(gmask);
-            if constexpr (ECI1) { eA += (fA & kLogAccepted) ? tA.dE : 0.0; have_e = true; }
         } else {
             fA = coop_volume_full(A, rnA, ranA);       // fav :2161-2293
         }
-        if (ECI1 || eci32 == 1 || --eci_left == 0) {   // ECheck :1965-2095
-            if (!have_e) {
-                eA = b2_etest_partial<INF>(A);
+        if (eci32 == 1 || --eci_left == 0) {           // ECheck :1965-2095
+            double eA = b2_etest_partial<INF>(A);
 #pragma unroll
-                for (int o = kB2G / 2; o > 0; o >>= 1) eA += __shfl_xor_sync(gmask, eA, o, kB2G);
-            }
+            for (int o = kB2G / 2; o > 0; o >>= 1) eA += __shfl_xor_sync(gmask, eA, o, kB2G);
             A.echecks++;
             if (fabs(eA - A.tot[0]) > 0.0001) { A.echecks--; coop_energy_check(A); }
             eci_left = eci32;

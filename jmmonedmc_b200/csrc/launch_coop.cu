@@ -27,11 +27,8 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
     int npad = (int) h->S.N;
     npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
     const bool inf = std::isinf(h->S.cutoff);
-    const bool eci1 = a.eci == 1 && getenv("JMM_BOND_EARLY_ECHECK");      // opt-in until verified on the GPU
-    auto kern = eci1 ? (a.accept_log ? (inf ? k_chains_step_bond<true, true, true> : k_chains_step_bond<true, false, true>)
-                                     : (inf ? k_chains_step_bond<false, true, true> : k_chains_step_bond<false, false, true>))
-                     : (a.accept_log ? (inf ? k_chains_step_bond<true, true, false> : k_chains_step_bond<true, false, false>)
-                                     : (inf ? k_chains_step_bond<false, true, false> : k_chains_step_bond<false, false, false>));
+    auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
+                             : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
     // threads per CTA: 128 (a warp per sub-partition); JMM_BOND_BLOCK = 32, 64 or 96 for wave-quantisation experiments
     unsigned threads = 128;
     if (const char *e = getenv("JMM_BOND_BLOCK")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) threads = (unsigned) v; }
