@@ -94,3 +94,25 @@ def test_product_never_imports_the_oracle(J):
     assert "oracle" not in deps
     syms = subprocess.run(["nm", "-D", str(J.lib_path())], capture_output=True, text=True).stdout
     assert "jmo_" not in syms
+
+
+def test_bench_cpu_decks_are_the_gpu_workloads(J, tmp_path):
+    """bench.py times the reference binary on INPUT decks it writes itself (C2 for the headline line, one chain of
+    the C4 sweep for --workload c4): parsed by jmm_read_input they must give the configuration the GPU arm runs."""
+    import sys
+    sys.path.insert(0, str(ROOT))
+    import bench
+    p = tmp_path / "INPUT"
+    p.write_text(bench.deck_text(12345, 125))
+    cfg, dk = J.read_input(p)
+    c2 = bench.C2
+    assert (cfg.N, cfg.pot, cfg.nbn, cfg.ensemble, cfg.relax) == (c2["N"], J.POT_HARMONIC, c2["nbn"], J.ENS_NPT, 0)
+    assert (cfg.P, cfg.T, cfg.maxStep, cfg.maxdl, cfg.eci, cfg.mdai, cfg.mvai) == (c2["P"], c2["T"], c2["maxStep"], c2["maxdl"],
+                                                                                c2["eci"], c2["mdai"], c2["mvai"])
+    assert math.isinf(cfg.cutoff) and dk.numsteps == 12345
+    p.write_text(bench.deck_text_c4(777, 9))
+    cfg, dk = J.read_input(p)
+    c4 = bench.EXTRA["c4"]
+    assert (cfg.N, cfg.pot, cfg.nbn, cfg.ensemble, cfg.relax) == (c4["N"], J.POT_LJ, c4["nbn"], J.ENS_NPT, c4["relax"])
+    assert (cfg.maxStep, cfg.maxdl, cfg.eci, cfg.mdai, cfg.mvai) == (c4["maxStep"], c4["maxdl"], c4["eci"], c4["mdai"], c4["mvai"])
+    assert (cfg.P, cfg.T, cfg.seed, dk.numsteps) == (0.5, 0.5, 9, 777)

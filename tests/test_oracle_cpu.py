@@ -153,3 +153,31 @@ def test_oracle_histograms_reproduce_reference_files(O, gold, tmp_path, name):
     for f in files:
         assert (tmp_path / f).read_bytes() == (g["dir"] / f).read_bytes(), f
     assert [int(x) for x in c.counters] == g["summary"]["counters"]
+
+
+def test_oracle_continues_at_a_step_number(O):
+    """jmo_set_sn (the restart branch of setupMCS takes the step count from the last frame, src/jmmMCState.cpp:641):
+    the Philox stream and the relaxVolume cadence (every 10 000 steps below 1 000 000, src/Main.cpp:173) follow it."""
+    d = dict(N=10, POT="LJ", NBN=-1, CUTOFF=float("inf"), ENSEMBLE="NPT", P=1.0, T=0.9, MAXSTEP=0.1, MAXDV=0.1,
+             ENGCHECK=5000, DADJ=4000, VADJ=6000, SEED=92847, RELAX=1)
+
+    def run(sn0, n):
+        c = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=3))
+        c.start()
+        if sn0 is not None:
+            c.set_step_number(sn0)
+        r0 = c.relax_calls
+        for _ in range(n):
+            c.step(); c.cadence()
+        return c, c.relax_calls - r0
+
+    a, _ = run(None, 300)
+    b, _ = run(0, 300)
+    assert np.array_equal(a.r.view(np.uint64), b.r.view(np.uint64)) and a.sn == b.sn == 300
+    c, _ = run(5000, 300)
+    assert c.sn == 5300 and not np.array_equal(a.r.view(np.uint64), c.r.view(np.uint64))     # other Philox blocks
+    e, relaxes = run(989_500, 12_000)
+    assert e.sn == 1_001_500 and relaxes == 1                                              # 990 000 yes, 1 000 000 no
+    f, relaxes = run(1_000_000, 25_000)
+    assert relaxes == 0
+    assert int(f.counters.sum()) == 25_001
