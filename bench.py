@@ -189,7 +189,7 @@ def reference_arm(args) -> None:
     if rank != 0:
         return
     cores = host_cores()
-    per_step = 400_000                      # ~4 s of CPU work per process per bench step
+    per_step = int(os.environ.get("JMM_BENCH_REF_STEPS", "400000"))     # ~4 s of CPU work per process per bench step
     for _ in range(args.warmup if args.warmup < 2 else 1):
         run_reference_sample(50_000, cores)
     t, trials, last = 0.0, 0, None

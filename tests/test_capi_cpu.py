@@ -116,3 +116,20 @@ def test_bench_cpu_decks_are_the_gpu_workloads(J, tmp_path):
     assert (cfg.N, cfg.pot, cfg.nbn, cfg.ensemble, cfg.relax) == (c4["N"], J.POT_LJ, c4["nbn"], J.ENS_NPT, c4["relax"])
     assert (cfg.maxStep, cfg.maxdl, cfg.eci, cfg.mdai, cfg.mvai) == (c4["maxStep"], c4["maxdl"], c4["eci"], c4["mdai"], c4["mvai"])
     assert (cfg.P, cfg.T, cfg.seed, dk.numsteps) == (0.5, 0.5, 9, 777)
+
+
+def test_bench_reference_arm_prints_the_contract_line(tmp_path):
+    """bench.py --impl reference: the compiled reference on the host cores, one JSON line with the keys the driver
+    reads (a short sample here; the default is 400 000 steps per process and bench step)."""
+    import json, os, sys
+    env = dict(os.environ, JMM_BENCH_REF_STEPS="20000")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "MC trial moves/sec" and line["unit"] == "trial moves/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    assert line["config"]["workload"].startswith("C2:")
