@@ -343,7 +343,7 @@ def gpu_arm(args) -> None:
         for wl in ("c3", "c4", "c5"):
             for ar in ("fast", "reference"):
                 try:
-                    ln = measure_extra(wl, ar, False, 3, 3, rank, world, local)
+                    ln = measure_extra(wl, ar, False, 3 if wl == "c4" else 10, 3, rank, world, local)
                     if ln:
                         others[f"{wl}_{ar}"] = {"workload": ln["config"]["workload"], "arith": ar, "value": ln["value"], "unit": UNIT,
                                                 "ms_per_step": ln["ms_per_step"], "gpu_launches": ln["gpu_launches"],
@@ -449,6 +449,15 @@ def measure_extra(workload: str, arith: str, hist: bool, steps: int, warmup: int
         return h.sweep(w["per_step"]) if w["kind"] == "sweep" else (h.step(w["per_step"]) or C * w["per_step"])
 
     for _ in range(max(warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    # a step of the sweep workloads is a fraction of a millisecond: keep warming up (untimed) until the device has
+    # been busy for ~50 ms, so that the timed steps do not run on clocks that are still ramping
+    t_w = time.perf_counter()
+    one()
+    torch.cuda.synchronize()
+    t_one = max(time.perf_counter() - t_w, 1e-5)
+    for _ in range(min(2000, int(0.05 / t_one))):          # back to back, one synchronisation at the end
         one()
     torch.cuda.synchronize()
     if world > 1:
