@@ -44,6 +44,7 @@ struct Coop {
     uint32_t lane;                                // 0..G-1 inside the group
     uint32_t gmask;                               // lanes of this group inside the warp
     bool chain_of_bonds;                          // NBN == 1 and N-1 <= G: one nearest-neighbour pair per lane
+    bool lean;                                    // scratch is [G][NC] only: ordered sums spread over the lanes (lanes.cuh)
 
     __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
     __device__ __forceinline__ void set_l(double lnew) {
@@ -97,6 +98,44 @@ __device__ __forceinline__ void coop_pair_sum(const Coop<POT, G> &c, F term, dou
     const uint32_t total = c.npairs_included();
     // per-lane cursor over pairs q = lane, lane+G, ... : (i, off) with j = i+1+off
     uint32_t i = 0, off = c.lane;
+    if (c.lean) {
+        // G pairs at a time through a [G][NCX] scratch; the NCX ordered sums are SPREAD over the lanes (lane k adds
+        // component k, k+G, ... of the G terms in pair order), so a chunk costs G loads + G additions per lane instead
+        // of G*NCX, and the scratch is G*NCX doubles instead of kCoopChunk*2*NC.  Same order of addition per component.
+        constexpr int M = (NCX + G - 1) / G;
+        double mine[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) mine[m] = 0;
+        for (uint32_t base = 0; base < total; base += G) {
+            const uint32_t n = min((uint32_t) G, total - base);
+            if (c.lane < n) {
+                while (off >= c.rowlen(i)) { off -= c.rowlen(i); ++i; }
+                double t[NCX];
+                term(i, i + 1 + off, t);
+                double *dst = c.sc + c.lane * NCX;
+#pragma unroll
+                for (int k = 0; k < NCX; ++k) dst[k] = t[k];
+                off += G;
+            }
+            c.sync();
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const uint32_t comp = c.lane + m * G;
+                if (comp < NCX) {
+                    if (n == G) {
+#pragma unroll
+                        for (int q = 0; q < G; ++q) mine[m] += c.sc[q * NCX + comp];
+                    } else {
+                        for (uint32_t q = 0; q < n; ++q) mine[m] += c.sc[q * NCX + comp];
+                    }
+                }
+            }
+            c.sync();
+        }
+#pragma unroll
+        for (int k = 0; k < NCX; ++k) out[k] = __shfl_sync(c.gmask, mine[k / G], k % G, G);
+        return;
+    }
     for (uint32_t base = 0; base < total; base += kCoopChunk) {
         const uint32_t end = min(total, base + kCoopChunk);
         for (uint32_t q = base + c.lane; q < end; q += G) {
@@ -140,6 +179,19 @@ __device__ __forceinline__ double coop_full_energy(const Coop<POT, G> &c, double
         t[0] = phi_energy<POT>(rj - ri, c.cutoff);
     }, e);
     return e[0];
+}
+
+// EUp and EDown of one relaxVolume iteration in ONE pass over the pairs (two independent ordered sums: the same
+// doubles as two coop_full_energy calls, half the cursor arithmetic and two dependent addition chains in flight)
+template <int POT, int G>
+__device__ __forceinline__ void coop_full_energy2(const Coop<POT, G> &c, double scale_a, double scale_b, double &ea, double &eb) {
+    double e[2];
+    coop_pair_sum<POT, G, 2>(c, [&](uint32_t i, uint32_t j, double (&t)[2]) {
+        const double ri = c.r[i], rj = c.r[j];
+        t[0] = phi_energy<POT>(rj * scale_a - ri * scale_a, c.cutoff);
+        t[1] = phi_energy<POT>(rj * scale_b - ri * scale_b, c.cutoff);
+    }, e);
+    ea = e[0]; eb = e[1];
 }
 
 // ECheck's ETest (:1974-1993): only compared against 1e-4, so lane partial sums + butterfly
@@ -190,8 +242,8 @@ __device__ __forceinline__ int coop_relax_volume(Coop<POT, G> &c) {             
     double lTryMin = 0, lTryMax = 1E10;
     for (int count = 0; count < 20; ++count) {
         const double h = 0.1;
-        const double EUp = coop_full_energy<POT, G, true>(c, (c.l + h) / c.l);
-        const double EDown = coop_full_energy<POT, G, true>(c, (c.l + (-h)) / c.l);
+        double EUp, EDown;
+        coop_full_energy2<POT, G>(c, (c.l + h) / c.l, (c.l + (-h)) / c.l, EUp, EDown);
         const double first = (EUp - EDown) / (2 * h);
         const double second = (EUp - 2.0 * c.tot[0] + EDown) / (h * h);
         double dlEstimate = -(c.P - ((double) c.N / c.l) * c.T + first) / second;
@@ -372,6 +424,25 @@ __device__ __forceinline__ void coop_energy_check(Coop<POT, G> &c) {            
     }
 }
 
+// maxDisAdjust :2100-2115, maxDVAdjust :2120-2139 (device variant)
+template <int POT, int G>
+__device__ __forceinline__ void coop_adjust_max_step(Coop<POT, G> &c, double log_ideal) {
+    const double actualRatio = (double) c.cnt[0] / (double)(c.cnt[0] + c.cnt[1]);
+    c.maxStep = c.maxStep * log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+    if (c.maxStep < 0.002) c.maxStep = 0.002;
+    else if (c.maxStep > 0.5) c.maxStep = 0.5;
+}
+template <int POT, int G>
+__device__ __forceinline__ void coop_adjust_max_dl(Coop<POT, G> &c, double log_ideal) {
+    if ((c.cnt[2] + c.cnt[3] - c.vAErr) > 0) {
+        c.vAErr = c.cnt[2] + c.cnt[3];
+        const double actualRatio = (double) c.cnt[2] / (double)(c.cnt[2] + c.cnt[3]);
+        c.maxdl = c.maxdl * log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+        if (c.maxdl < 0.002 * (double) c.N) c.maxdl = 0.002 * (double) c.N;
+        else if (c.maxdl > 0.10 * (double) c.N) c.maxdl = 0.50 * (double) c.N;
+    }
+}
+
 // nsteps x Step() :1758-1811, G lanes per chain, Philox stream, positions from shared memory
 template <int POT, int G, bool LOG>
 __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs a, int npad) {
@@ -387,6 +458,7 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
     c.lane = threadIdx.x % G;
     c.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     c.chain_of_bonds = (S.nbn == 1) && (S.N - 1 <= (uint64_t) G);
+    c.lean = false;
     const size_t per_group = (size_t) npad + (size_t) kCoopChunk * 2 * NC;
     c.r = smem + gib * per_group;
     c.sc = c.r + npad;
@@ -453,23 +525,8 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
         coop_update_thermo(c);
         if (LOG && c.lane == 0) a.accept_log[(uint64_t) s * C + chain] = flags;
         if (a.adapt_device) {
-            if (--mdai_left == 0) {
-                const double actualRatio = (double) c.cnt[0] / (double)(c.cnt[0] + c.cnt[1]);
-                c.maxStep = c.maxStep * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
-                if (c.maxStep < 0.002) c.maxStep = 0.002;
-                else if (c.maxStep > 0.5) c.maxStep = 0.5;
-                mdai_left = mdai32;
-            }
-            if (--mvai_left == 0) {
-                if ((c.cnt[2] + c.cnt[3] - c.vAErr) > 0) {
-                    c.vAErr = c.cnt[2] + c.cnt[3];
-                    const double actualRatio = (double) c.cnt[2] / (double)(c.cnt[2] + c.cnt[3]);
-                    c.maxdl = c.maxdl * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
-                    if (c.maxdl < 0.002 * (double) c.N) c.maxdl = 0.002 * (double) c.N;
-                    else if (c.maxdl > 0.10 * (double) c.N) c.maxdl = 0.50 * (double) c.N;
-                }
-                mvai_left = mvai32;
-            }
+            if (--mdai_left == 0) { coop_adjust_max_step(c, a.log_ideal); mdai_left = mdai32; }
+            if (--mvai_left == 0) { coop_adjust_max_dl(c, a.log_ideal); mvai_left = mvai32; }
             if (--relax_left == 0) { if (sn < 1000000ull) coop_relax_volume(c); relax_left = 10000; }
         }
     }

@@ -30,9 +30,14 @@ struct jmm_handle {
     int coop_g = 0;                 // lanes per chain of the cooperative kernel (0 = one chain per thread)
     int coop_npad = 0;
     size_t coop_smem = 0;
+    // lanes.cuh (JMM_ARITH_FAST, G lanes per chain): lanes per chain (0 = not this kernel), unrolled slots per lane
+    // (0 = run-time loop), row length incl. pads, doubles per group in shared memory
+    int lanes_g = 0, lanes_npl = 0, lanes_npad = 0, lanes_stride = 0;
     // recorded stream
     uint32_t *d_stream = nullptr;
-    uint64_t stream_cap = 0;
+    uint64_t stream_cap = 0;               // allocated words
+    uint64_t stream_len = 0;               // words of the stream loaded last (<= stream_cap)
+    bool keep_cursor = false;              // set by jmm_checkpoint_load: the next stream load keeps the restored cursor
     uint64_t *d_cursor = nullptr;
     int *d_err = nullptr;
     uint64_t cursor = 0;
@@ -73,6 +78,9 @@ struct SweepShape {
 JMM_INTERNAL cudaError_t jmm_launch_prod(jmm_handle *h, const jmm::StepArgs &a);
 // coop.cuh / bond.cuh: few chains, G lanes per chain
 JMM_INTERNAL cudaError_t jmm_launch_coop(jmm_handle *h, const jmm::StepArgs &a);
+// lanes.cuh: a moderate number of chains, G lanes per chain, fast arithmetic
+JMM_INTERNAL cudaError_t jmm_launch_lanes(jmm_handle *h, const jmm::StepArgs &a);
+JMM_INTERNAL void jmm_lanes_shape(jmm_handle *h, int g);
 // sweep.cuh: nsub colour half-sweeps of every chain of a checkerboard handle
 JMM_INTERNAL cudaError_t jmm_launch_sweep(jmm_handle *h, const SweepShape &s, const jmm::SweepDev &W, uint64_t step0, int nsub,
                                           unsigned ntiles);

@@ -58,6 +58,16 @@ struct MCState {
         _Pragma("omp barrier")       \
     } while (0)
 
+// Functions the reference calls from `omp sections` / `omp single` (src/Main.cpp:77-106,128-165) can run on different
+// threads AT THE SAME TIME (printCoords, printRho, updateThermo + printThermo at step 0).  A jmm_handle is a
+// one-host-thread object (include/jmm_gpu.h) and `m->r/tot/acc` are shared, so every such function runs its body
+// under one named critical section.
+#define GPU_LOCKED(...)                     \
+    do {                                    \
+        _Pragma("omp critical(jmm_gpu)")    \
+        { __VA_ARGS__ }                     \
+    } while (0)
+
 static void die(const char *what) {
     fprintf(stderr, "jmm compat: %s failed: %s\n", what, jmm_last_error());
     exit(2);
@@ -167,19 +177,22 @@ int relaxVolume(struct MCState *m) {                                           /
 }
 
 int updateThermo(struct MCState *m) {                                          // :1941-1961 (step-0 call, Main.cpp:96)
-    JCK(jmm_start_parts(m->h, 0, 0, 1));
+    GPU_LOCKED(JCK(jmm_start_parts(m->h, 0, 0, 1)););
     return 0;
 }
 
 int printCoords(struct MCState *m) {                                           // :1007-1017
-    pull(m);
-    fprintf(m->cf, "%lu\nStep no.: %lu  Box length: %.5f\n", m->N, m->sn, m->l);
-    for (unsigned long int i = 0; i < m->N; i++) fprintf(m->cf, "%lu  0.0  0.0  %.8G\n", i + 1, m->r[i]);
-    fflush(m->cf);
+    GPU_LOCKED(
+        pull(m);
+        fprintf(m->cf, "%lu\nStep no.: %lu  Box length: %.5f\n", m->N, m->sn, m->l);
+        for (unsigned long int i = 0; i < m->N; i++) fprintf(m->cf, "%lu  0.0  0.0  %.8G\n", i + 1, m->r[i]);
+        fflush(m->cf);
+    );
     return 0;
 }
 
 int printThermo(struct MCState *m) {                                           // :1896-1937
+    GPU_LOCKED(
     pull(m);
     const unsigned long int ss = m->sn - m->sltp;
     const double *a = m->acc;
@@ -191,10 +204,12 @@ int printThermo(struct MCState *m) {                                           /
     fflush(stdout);
     JCK(jmm_zero_accum(m->h));
     m->sltp = m->sn;
+    );
     return 0;
 }
 
 int printRho(struct MCState *m) {                                              // :1021-1038
+    GPU_LOCKED(
     m->hist.resize(m->rhonb);
     JCK(jmm_take_histograms(m->h, m->hist.data(), NULL));
     const unsigned long int ns = m->sn - m->slrho;
@@ -203,6 +218,7 @@ int printRho(struct MCState *m) {                                              /
     fprintf(m->rhof, "\n");
     fflush(m->rhof);
     m->slrho = m->sn;
+    );
     return 0;
 }
 
@@ -245,25 +261,29 @@ int isMaxDisAdjust(struct MCState *m) { return m->sn % m->mdai == 0; }         /
 int isMaxDVAdjust(struct MCState *m) { return m->sn % m->mvai == 0; }          // :1883
 
 int maxDisAdjust(struct MCState *m) {                                          // :2100-2115
-    JCK(jmm_adjust_step_sizes(m->h, 1, 0));
-    double ms, mv;
-    JCK(jmm_get_step_sizes(m->h, &ms, &mv));
-    pull(m);
-    printf("Step: %lu  Updating max Step...dAcc: %lu,%lu   new maxStep: %.5G\n", m->sn, (unsigned long) m->cnt[0],
-           (unsigned long) m->cnt[1], ms);
+    GPU_LOCKED(
+        JCK(jmm_adjust_step_sizes(m->h, 1, 0));
+        double ms, mv;
+        JCK(jmm_get_step_sizes(m->h, &ms, &mv));
+        pull(m);
+        printf("Step: %lu  Updating max Step...dAcc: %lu,%lu   new maxStep: %.5G\n", m->sn, (unsigned long) m->cnt[0],
+               (unsigned long) m->cnt[1], ms);
+    );
     return 0;
 }
 
 int maxDVAdjust(struct MCState *m) {                                           // :2120-2139
-    JCK(jmm_adjust_step_sizes(m->h, 0, 1));
+    GPU_LOCKED(JCK(jmm_adjust_step_sizes(m->h, 0, 1)););
     return 0;
 }
 
-int printE(struct MCState *m) { pull(m); printf("\nE = %.8G\n", m->tot[JMM_E]); return 0; }   // :2143
+int printE(struct MCState *m) { GPU_LOCKED(pull(m); printf("\nE = %.8G\n", m->tot[JMM_E]);); return 0; }   // :2143
 int printAcc(struct MCState *m) {                                              // :2151
-    pull(m);
-    printf("Accepted/Rejected: Displacements VolumeChanges\n              \
+    GPU_LOCKED(
+        pull(m);
+        printf("Accepted/Rejected: Displacements VolumeChanges\n              \
           %lu/%lu          %lu/%lu\n", (unsigned long) m->cnt[0], (unsigned long) m->cnt[1], (unsigned long) m->cnt[2],
-           (unsigned long) m->cnt[3]);
+               (unsigned long) m->cnt[3]);
+    );
     return 0;
 }

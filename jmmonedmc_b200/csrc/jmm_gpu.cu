@@ -64,6 +64,8 @@ extern "C" jmm_status jmm_read_input(const char *path, jmm_config *cfg, jmm_deck
     memset(&dk, 0, sizeof dk);
     memset(cfg, 0, sizeof *cfg);
     cfg->cutoff = INFINITY;
+    cfg->nbn = -1;                                     // no NBN line = no neighbour limit (the reference leaves nbn
+                                                       // uninitialised, src/readInput.cpp:103; 0 would exclude every pair)
     cfg->ensemble = JMM_ENS_NPT;                       // default "NPT", :57
     cfg->nchains = 1;
     cfg->rng_kind = JMM_RNG_PHILOX;
@@ -151,6 +153,8 @@ static jmm_status validate(const jmm_config *c) {
     if (c->N < 2) return fail(JMM_ERR_INVALID, "N must be >= 2");
     if (c->N > 0x7fffffffull) return fail(JMM_ERR_INVALID, "N too large");
     if (c->nchains < 1) return fail(JMM_ERR_INVALID, "nchains must be >= 1");
+    if (c->nbn == 0) return fail(JMM_ERR_INVALID, "NBN 0 excludes every pair (use NBN -1 for no neighbour limit)");
+    if (!(c->T > 0)) return fail(JMM_ERR_INVALID, "T must be > 0");
     if (c->pot < JMM_POT_LJ || c->pot > JMM_POT_HARMONIC)
         return fail(JMM_ERR_UNKNOWN_POT, "FATAL ERROR: Unknown potential.");
     if (c->ensemble != JMM_ENS_NPT && c->ensemble != JMM_ENS_NLT)
@@ -297,6 +301,18 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
                 const size_t bytes = (size_t) (128 / g) * (npad + scratch) * sizeof(double);
                 if (bytes <= 200 * 1024) { h->coop_g = g; h->coop_npad = npad; h->coop_smem = bytes; }
             }
+            // JMM_ARITH_FAST with too few chains for one chain per thread (prod.cuh wants >= ~2048 warps = 65 536
+            // chains): G lanes per chain with the same arithmetic (lanes.cuh), G = the power of two that brings the
+            // launch to ~2048 warps, at most one lane per ~partner.  (A sweep of 65 536 state points sharded over 8
+            // GPUs is 8192 chains per GPU: G = 8.)
+            if (cfg->arith == JMM_ARITH_FAST && cfg->pot != JMM_POT_HARMONIC) {
+                const uint64_t partners = cfg->nbn < 0 ? N - 1 : std::min<uint64_t>(2 * (uint64_t) cfg->nbn, N - 1);
+                int lg = 1;
+                while (lg < 32 && (uint64_t) (2 * lg) * C <= 65536 && (uint64_t) (2 * lg) <= std::max<uint64_t>(2, partners)) lg *= 2;
+                if (const char *e = getenv("JMM_LANES_G")) lg = atoi(e);
+                h->coop_g = 0;                                       // never the reference-arithmetic kernel for a FAST handle
+                if (lg == 2 || lg == 4 || lg == 8 || lg == 16 || lg == 32) jmm_lanes_shape(h, lg);
+            }
             // nearest-neighbour bond chains (the INPUTstd shape): branch-free kernel, one chain per 16 lanes
             const char *eb = getenv("JMM_BOND");
             if (h->coop_g && cfg->pot == JMM_POT_HARMONIC && cfg->nbn == 1 && N - 1 <= 16 && !(h->cfg.relax > 0) &&
@@ -340,6 +356,7 @@ static cudaError_t launch_step_rng(jmm_handle *h, const StepArgs &a) {
 template <int POT, bool TABLE>
 static cudaError_t launch_step_table(jmm_handle *h, const StepArgs &a) {
     if constexpr (!TABLE) {
+        if (h->lanes_g) return jmm_launch_lanes(h, a);
         if (h->coop_g) return jmm_launch_coop(h, a);
         if (h->cfg.rng_kind == JMM_RNG_PHILOX && h->pos_in_smem && h->block == 32 && !getenv("JMM_NO_PROD"))
             return jmm_launch_prod(h, a);
@@ -537,7 +554,7 @@ extern "C" jmm_status jmm_enable_histograms(jmm_handle *h, uint64_t rhonb, doubl
     CK(dalloc(h, &H.rho, C * rhonb)); CK(dalloc(h, &H.g, C * ng));
     CK(dalloc(h, &H.ucount, C));
     h->H = H;
-    h->coop_g = 0; h->bond = 0;                    // the per-thread kernels carry the histogram hooks
+    h->coop_g = 0; h->bond = 0; h->lanes_g = 0;    // the per-thread kernels carry the histogram hooks
     k_hist_init<<<nblk(C, 32), 32, 0, h->stream>>>(h->S, h->H);
     h->launches++;
     CK(cudaGetLastError());
@@ -575,11 +592,15 @@ static jmm_status totals_parallel(jmm_handle *h, const double *r, uint64_t ps, u
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct CkptHeader {
-    char magic[8];                 // "JMMCKPT1"
+    char magic[8];                 // "JMMCKPT2"
     uint64_t N, nchains, seed, chain_id0, sn, halfsweeps, cursor;
     int32_t mode, pot, nbn, ensemble, rng_kind, cb_cur, hist, gns;
     uint64_t rhonb, gnb;
     double rbw, gsw, gbw;
+    // (format 2) what decides the cadence and the arithmetic of the continuation
+    double cutoff;
+    uint64_t eci, mdai, mvai;
+    int32_t adapt, arith, relax, pad_;
 };
 
 // the device arrays of a handle, in file order
@@ -605,12 +626,14 @@ jmm_status ckpt_arrays(jmm_handle *h, F &&io) {
 
 CkptHeader ckpt_header(const jmm_handle *h) {
     CkptHeader k{};
-    memcpy(k.magic, "JMMCKPT1", 8);
+    memcpy(k.magic, "JMMCKPT2", 8);
     k.N = h->S.N; k.nchains = h->S.nchains; k.seed = h->cfg.seed; k.chain_id0 = h->cfg.chain_id0;
     k.sn = h->sn; k.halfsweeps = h->halfsweeps; k.cursor = h->cursor;
     k.mode = h->cfg.mode; k.pot = h->cfg.pot; k.nbn = h->cfg.nbn; k.ensemble = h->cfg.ensemble; k.rng_kind = h->cfg.rng_kind;
     k.cb_cur = 0; k.hist = h->H.ucount ? 1 : 0; k.gns = h->H.gns; k.rhonb = h->H.rhonb; k.gnb = h->H.gnb;
     k.rbw = h->H.rbw; k.gsw = h->H.gsw; k.gbw = h->H.gbw;
+    k.cutoff = h->cfg.cutoff; k.eci = h->cfg.eci; k.mdai = h->cfg.mdai; k.mvai = h->cfg.mvai;
+    k.adapt = h->cfg.adapt; k.arith = h->cfg.arith; k.relax = h->cfg.relax; k.pad_ = 0;
     return k;
 }
 }  // namespace
@@ -642,7 +665,7 @@ extern "C" jmm_status jmm_checkpoint_load(jmm_handle *h, const char *path) {
     FILE *f = fopen(path, "rb");
     if (!f) return fail(JMM_ERR_IO, std::string("cannot read ") + path);
     CkptHeader k{};
-    if (fread(&k, sizeof(k), 1, f) != 1 || memcmp(k.magic, "JMMCKPT1", 8) != 0) {
+    if (fread(&k, sizeof(k), 1, f) != 1 || memcmp(k.magic, "JMMCKPT2", 8) != 0) {
         fclose(f);
         return fail(JMM_ERR_IO, std::string(path) + " is not a jmm checkpoint");
     }
@@ -653,25 +676,39 @@ extern "C" jmm_status jmm_checkpoint_load(jmm_handle *h, const char *path) {
         return fail(JMM_ERR_INVALID, "checkpoint was written by a handle with a different configuration "
                                      "(N, nchains, mode, pot, NBN, ensemble, generator, seed or chain_id0)");
     }
+    if (memcmp(&k.cutoff, &me.cutoff, sizeof(double)) != 0 || k.eci != me.eci || k.mdai != me.mdai || k.mvai != me.mvai ||
+        k.adapt != me.adapt || k.arith != me.arith || k.relax != me.relax) {
+        fclose(f);
+        return fail(JMM_ERR_INVALID, "checkpoint was written by a handle with a different cadence or arithmetic "
+                                     "(cutoff, ENGCHECK, DADJ, VADJ, adapt, arith or RELAX): the continuation would not be exact");
+    }
     if (k.hist != me.hist || (k.hist && (k.rhonb != me.rhonb || k.gnb != me.gnb || k.gns != me.gns || k.rbw != me.rbw ||
                                          k.gsw != me.gsw || k.gbw != me.gbw))) {
         fclose(f);
         return fail(JMM_ERR_INVALID, "checkpoint and handle disagree about the histograms (call jmm_enable_histograms "
                                      "with the same geometry before jmm_checkpoint_load, or not at all)");
     }
-    std::vector<char> buf;
-    bool ok = true;
+    // read and size-check the whole file before any device state is touched: a truncated file leaves the handle as it was
+    size_t need = 0;
+    ckpt_arrays(h, [&](void *, size_t bytes) -> jmm_status { need += bytes; return JMM_OK; });
+    std::vector<char> buf(need);
+    const size_t got = need ? fread(buf.data(), 1, need, f) : 0;
+    const bool trailing = fgetc(f) != EOF;
+    fclose(f);
+    if (got != need || trailing) return fail(JMM_ERR_IO, std::string(got != need ? "truncated checkpoint " : "checkpoint longer than this handle's state: ") + path);
+    size_t off = 0;
     jmm_status st = ckpt_arrays(h, [&](void *d, size_t bytes) -> jmm_status {
-        buf.resize(bytes);
-        if (fread(buf.data(), 1, bytes, f) != bytes) { ok = false; return fail(JMM_ERR_IO, std::string("truncated checkpoint ") + path); }
-        CK(cudaMemcpy(d, buf.data(), bytes, cudaMemcpyHostToDevice));
+        // on the handle's own stream (non-blocking: the legacy stream does not order against it), then one synchronise
+        CK(cudaMemcpyAsync(d, buf.data() + off, bytes, cudaMemcpyHostToDevice, h->stream));
+        off += bytes;
         return JMM_OK;
     });
-    fclose(f);
     if (st != JMM_OK) return st;
     h->sn = k.sn; h->halfsweeps = k.halfsweeps; h->cursor = k.cursor;
-    if (h->d_cursor) CK(cudaMemcpy(h->d_cursor, &h->cursor, sizeof(uint64_t), cudaMemcpyHostToDevice));
-    return ok ? JMM_OK : JMM_ERR_IO;
+    if (h->d_cursor) CK(cudaMemcpyAsync(h->d_cursor, &h->cursor, sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->keep_cursor = h->cfg.rng_kind == JMM_RNG_RECORDED;
+    return JMM_OK;
 }
 
 extern "C" jmm_status jmm_start(jmm_handle *h) {
@@ -840,9 +877,17 @@ extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *r
                 h->stream_cap = n_words;
             }
             CK(cudaMemcpyAsync(h->d_stream, rng_stream, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(uint64_t), h->stream));
-            h->cursor = 0;
-        } else n_words = h->stream_cap;
+            h->stream_len = n_words;
+            if (h->keep_cursor) {
+                // first (re)load after jmm_checkpoint_load: the caller passes the SAME recording again and the run
+                // continues at the restored cursor
+                h->keep_cursor = false;
+                if (h->cursor > n_words) return fail(JMM_ERR_STREAM, "the restored cursor lies beyond the recorded stream passed to jmm_step");
+            } else {
+                CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(uint64_t), h->stream));
+                h->cursor = 0;
+            }
+        } else n_words = h->stream_len;
         if (!h->d_stream) return fail(JMM_ERR_INVALID, "JMM_RNG_RECORDED needs rng_stream");
     }
     if (accept_log && nsteps) {

@@ -227,13 +227,23 @@ def test_continue_at_a_step_number_matches_oracle(J, O, engine, monkeypatch):
         assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
 
 
-@pytest.mark.parametrize("variant", ["unroll4", "unroll8", "sliced"])
+@pytest.mark.parametrize("variant", ["unroll4", "unroll8", "sliced", "default", "lanes2", "lanes4", "lanes8", "lanes16", "lanes32",
+                                     "lanes8-sliced", "lanes4-sliced"])
 @pytest.mark.parametrize("name", ["small", "ljcut_nbn", "nlt"])
 def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, variant, monkeypatch):
-    """JMM_ARITH_FAST (prod.cuh, fastlj.cuh): one reciprocal per partner, r^-6/r^-12 differences only, 4 or 8
-    partners in flight, plain and time-sliced launches (40 chains = a ragged last tile).  Positions and the
-    accept/reject sequence must equal the oracle's exactly; the nine totals and twelve sums agree to 1e-12."""
-    monkeypatch.setenv("JMM_COOP_G", "0")
+    """JMM_ARITH_FAST (fastlj.cuh): one reciprocal per partner, r^-6/r^-12 differences only — in prod.cuh (one chain
+    per thread; 4 or 8 partners in flight, plain and time-sliced launches; 40 chains = a ragged last tile) and in
+    lanes.cuh (2 ... 32 lanes per chain, what a FAST handle with few chains gets by default; one chunk and
+    time-sliced).  Positions and the accept/reject sequence must equal the oracle's exactly; the nine totals and
+    twelve sums agree to 1e-12."""
+    if variant.startswith("lanes"):
+        monkeypatch.setenv("JMM_LANES_G", variant.split("-")[0][5:])
+        if variant.endswith("sliced"):
+            monkeypatch.setenv("JMM_FORCE_SLICE", "1")
+            monkeypatch.setenv("JMM_SLICE_CHUNK", "7")
+    elif variant != "default":
+        monkeypatch.setenv("JMM_LANES_G", "0")
+        monkeypatch.setenv("JMM_COOP_G", "0")
     if variant == "unroll4":
         monkeypatch.setenv("JMM_PROD_UNROLL", "4")
     if variant == "sliced":
@@ -263,6 +273,102 @@ def test_fast_arithmetic_same_trajectory_totals_within_1e12(J, O, name, variant,
         assert np.allclose(s["accum"][c], oc.accum, rtol=1e-11, atol=1e-9)
     with pytest.raises(J.JmmError):
         J.Handle(jmm_config_from_deck(J, DECKS["std"], arith=J.ARITH_FAST))          # HARMONIC has no fast arithmetic
+
+
+def _sweep_shape_pt(C):
+    """per-chain (P, T) of a RunJobs-style sweep (scripts/RunJobs.bash:16-27), a sqrt(C) x sqrt(C)-ish grid"""
+    side = int(math.ceil(math.sqrt(C)))
+    grid = np.linspace(0.1, 1.0, side)
+    P = np.array([grid[c // side] for c in range(C)])
+    T = np.array([grid[c % side] for c in range(C)])
+    return P, T
+
+
+SWEEP_DECK = dict(N=80, POT="LJ", NBN=-1, CUTOFF=math.inf, ENSEMBLE="NPT", P=0.5, T=0.5, MAXSTEP=0.1, MAXDV=2.0,
+                  ENGCHECK=10000, DADJ=1000000, VADJ=1000000, SEED=92847, RELAX=1)
+
+
+@pytest.mark.parametrize("engine", ["prod-reference", "sliced-reference", "coop8-reference", "prod-fast", "sliced-fast",
+                                    "lanes8-fast", "lanes4-fast", "lanes8sliced-fast", "lanes16-fast", "lanes2-fast"])
+@pytest.mark.parametrize("start", ["from0", "from1e6"])
+def test_sweep_shape_matches_oracle(J, O, engine, start, monkeypatch):
+    """The shape bench.py times as C4 (RunJobs deck: N = 80, LJ, NBN -1, NPT, RELAX, ENGCHECK 10000; per-chain P, T set
+    through jmm_set_state; device-side cadence) on every kernel that can serve it: 427 chains (13 full tiles of one
+    chain per thread + a ragged one; 107 warps of four chains), from step 0 across the in-kernel relaxVolume at step
+    10 000 (src/Main.cpp:173-176) and the ECheck there, and from step 10^6 (the production phase, no relaxation).
+    Sampled chains against the oracle: positions, box, counters, accept sequence bit-identical; totals and sums
+    bit-identical in reference arithmetic, <= 1e-12 in fast arithmetic."""
+    eng, arith = engine.split("-")
+    env = {"prod": {"JMM_COOP_G": "0", "JMM_LANES_G": "0"},
+           "sliced": {"JMM_COOP_G": "0", "JMM_LANES_G": "0", "JMM_FORCE_SLICE": "1", "JMM_SLICE_CHUNK": "97"},
+           "coop8": {"JMM_COOP_G": "8"},
+           "lanes8": {"JMM_LANES_G": "8"}, "lanes4": {"JMM_LANES_G": "4"}, "lanes16": {"JMM_LANES_G": "16"},
+           "lanes2": {"JMM_LANES_G": "2"},
+           "lanes8sliced": {"JMM_LANES_G": "8", "JMM_FORCE_SLICE": "1", "JMM_SLICE_CHUNK": "97"}}[eng]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    d = SWEEP_DECK
+    C, id0 = 427, 5000
+    sn0, nsteps = (0, 10_400) if start == "from0" else (1_000_000, 2_000)
+    P, T = _sweep_shape_pt(C)
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE, nchains=C, chain_id0=id0,
+                               arith=J.ARITH_FAST if arith == "fast" else J.ARITH_REFERENCE)
+    log_steps = 300
+    with J.Handle(cfg) as h:
+        h.set_state(P=P, T=T)
+        h.start()
+        if sn0:
+            h.set_step_number(sn0)
+        log = h.step(log_steps, accept_log=True)
+        h.step(nsteps - log_steps)
+        s = h.get_state()
+        checks, disc = h.echeck_stats()
+    assert disc == 0 and checks == C * ((sn0 + nsteps) // 10000 - sn0 // 10000)
+    assert np.all(s["counters"].sum(axis=1) == nsteps + 1)
+    sample = sorted(set([0, 1, 31, 32, 33, 3, 4, 7, 8, 127, 128, 351, 352, 415, 416, 417, 423, 424, 425, 426] +
+                        list(range(200, 204))))
+    for c in sample:
+        dc = dict(d, P=float(P[c]), T=float(T[c]))
+        oc = O.Chain(O.config_from_deck(dc, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=id0 + c))
+        oc.start()
+        if sn0:
+            oc.set_step_number(sn0)
+        relax0 = oc.relax_calls
+        want_log = oracle_accept_log(oc, log_steps)
+        oc.run(nsteps - log_steps)
+        assert oc.relax_calls == relax0 + (1 if start == "from0" else 0)
+        assert np.array_equal(log[:, c] & 3, want_log), f"chain {c}: accept sequence"
+        assert bits_equal(s["r"][c], oc.r), f"chain {c}: positions"
+        assert bits_equal(s["l"][c:c + 1], [oc.l]) and np.array_equal(s["counters"][c], oc.counters)
+        if arith == "reference":
+            assert bits_equal(s["totals"][c], oc.totals), f"chain {c}: totals"
+            assert bits_equal(s["accum"][c], oc.accum), f"chain {c}: running sums"
+        else:
+            assert totals_close(s["totals"][c], oc.totals, 1e-12), f"chain {c}: totals"
+            assert np.allclose(s["accum"][c], oc.accum, rtol=1e-11, atol=1e-9)
+
+
+def test_c2_bench_mode_matches_oracle_on_sampled_chains(J, O):
+    """The C2 workload as bench.py runs it (INPUTstd x 4096 chains on bond.cuh), with the step sizes adapted by the
+    host's libm (JMM_ADAPT_HOST: glibc log on both sides, so adaptation cannot hide a difference): 72 chains spread
+    over the launch, 2 500 steps = 25 adjustments of each kind, bit-identical to the oracle."""
+    d = dict(DECKS["std"])
+    C, nsteps = 4096, 2500
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C)
+    with J.Handle(cfg) as h:
+        h.start()
+        h.step(nsteps)
+        s = h.get_state()
+        ms, mv = h.get_step_sizes()
+    sample = sorted(set(list(range(0, C, 61)) + [1, 2, 15, 16, 17, 4094, 4095]))
+    assert len(sample) >= 64
+    for c in sample:
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=c))
+        oc.start(); oc.run(nsteps)
+        assert bits_equal(s["r"][c], oc.r), f"chain {c}: positions"
+        assert bits_equal(s["l"][c:c + 1], [oc.l]) and np.array_equal(s["counters"][c], oc.counters)
+        assert bits_equal(s["totals"][c][:2], oc.totals[:2]) and bits_equal(s["accum"][c][:10], oc.accum[:10])
+        assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
 
 
 def test_device_adaptation_matches_until_first_adjust_then_statistically(J, O):
