@@ -32,7 +32,8 @@ enum {
     JMM_ERR_IO = -3,           /* INPUT file missing or unreadable                               */
     JMM_ERR_STREAM = -4,       /* recorded random stream exhausted                               */
     JMM_ERR_UNKNOWN_POT = -5,  /* "FATAL ERROR: Unknown potential."  src/jmmMCState.cpp:396-399  */
-    JMM_ERR_UNKNOWN_ENS = -6   /* "FATAL ERROR: Unknown ensemble."   src/jmmMCState.cpp:422-425  */
+    JMM_ERR_UNKNOWN_ENS = -6,  /* "FATAL ERROR: Unknown ensemble."   src/jmmMCState.cpp:422-425  */
+    JMM_ERR_NCCL = -7          /* NCCL missing or a collective failed                            */
 };
 
 /* POT keyword -> phi / qav dispatch, src/jmmMCState.cpp:292-367 */
@@ -161,6 +162,10 @@ jmm_status jmm_adjust_step_sizes(jmm_handle *h, int32_t do_dis, int32_t do_vol);
 jmm_status jmm_get_state(jmm_handle *h, double *r, double *l, double *totals, double *accum, uint64_t *counters);
 /* what printThermo does to the sums after printing, :1922-1933 */
 jmm_status jmm_zero_accum(jmm_handle *h);
+/* overwrite the twelve running sums (accum [nchains][12]) and the number of updateThermo calls they hold: the inverse
+ * of jmm_get_state + jmm_zero_accum, for a driver that prints-and-zeroes like printThermo but wants the device-side
+ * summary records (jmm_summaries) to carry its whole-run sums */
+jmm_status jmm_set_accum(jmm_handle *h, const double *accum, uint64_t samples);
 /* getStepNum(), :2777 */
 uint64_t   jmm_step_number(const jmm_handle *h);
 /* Continue at a given step number: what a restart does with the step count of the last frame of config.dat.mcs
@@ -204,6 +209,31 @@ jmm_status jmm_checkpoint_load(jmm_handle *h, const char *path);
  * (|i-j| <= NBN rule, :1217,1312), so the trials commute.  Totals and counters are maintained;
  * the twelve sums are updated once per half-sweep.  trials_out = number of trial moves made. */
 jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *trials_out);
+
+/* ---- Multi-GPU.  The reference runs one process per state point (scripts/RunJobs.bash:99-101, one
+ * LSF job each) and joins the results through files (scripts/Analyze_Mean.py reads every thermo.dat.mcs).  Here chains
+ * are sharded over ranks (one process per GPU, cfg.chain_id0 = first global chain id of the rank, so the Philox streams
+ * do not depend on the sharding) with no data-path traffic, and the join is ONE ncclAllGather of per-chain records.
+ * Record = JMM_SUMMARY_DOUBLES doubles:
+ *   0 global chain id   1 P   2 T   3 N   4 samples = updateThermo calls in the sums (since jmm_zero_accum)
+ *   5..16 the twelve running sums (JMM_A_* order)   17..20 dAcc[0], dAcc[1], vAcc[0], vAcc[1]   21 l   22 E   23 Vir
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls return JMM_ERR_NCCL and everything else works. */
+enum { JMM_SUMMARY_DOUBLES = 24, JMM_COMM_ID_BYTES = 128 };
+typedef struct jmm_comm jmm_comm;
+/* ncclGetUniqueId: rank 0 calls it and hands the bytes to the other ranks (file, environment, launcher) */
+jmm_status jmm_comm_unique_id(uint8_t id[JMM_COMM_ID_BYTES]);
+/* ncclCommInitRank on `device`; collective over the `world` ranks */
+jmm_status jmm_comm_create(const uint8_t id[JMM_COMM_ID_BYTES], int32_t rank, int32_t world, int32_t device, jmm_comm **out);
+jmm_status jmm_comm_destroy(jmm_comm *c);
+/* this handle's records, packed on the device: records [nchains][JMM_SUMMARY_DOUBLES] (host) */
+jmm_status jmm_summaries(jmm_handle *h, double *records);
+/* Collective: every rank packs its records on the device, one ncclAllGather (NVLink) on the handle's stream, and the
+ * gathered table comes back to every rank's host buffer out [total_chains][JMM_SUMMARY_DOUBLES] in global chain order.
+ * Each rank may hold at most ceil(total_chains / world) chains; every chain id in [0, total_chains) must be held by
+ * exactly one rank. */
+jmm_status jmm_allgather_summaries(jmm_handle *h, jmm_comm *c, uint64_t total_chains, double *out);
+/* NCCL version code (e.g. 22809) of the library bound at run time, 0 if none */
+int32_t    jmm_nccl_version(void);
 
 /* instrumentation for bench.py: kernels launched so far, device time of the last jmm_step /
  * jmm_sweep / jmm_energy kernel(s) in ms (CUDA events on the handle's stream) */

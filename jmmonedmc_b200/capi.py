@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
         "jmm_adjust_step_sizes": (C.c_int32, [H, C.c_int32, C.c_int32]),
         "jmm_get_state": (C.c_int32, [H, dp, dp, dp, dp, u64p]),
         "jmm_zero_accum": (C.c_int32, [H]),
+        "jmm_set_accum": (C.c_int32, [H, dp, C.c_uint64]),
         "jmm_step_number": (C.c_uint64, [H]),
         "jmm_set_step_number": (C.c_int32, [H, C.c_uint64]),
         "jmm_echeck_stats": (C.c_int32, [H, u64p, u64p]),
@@ -116,6 +117,12 @@ def lib() -> C.CDLL:
         "jmm_version": (C.c_char_p, []),
         "jmm_rng_selftest": (C.c_int32, [u32p, u32p, u32p, C.c_uint64, u32p, C.c_uint32, C.c_int32]),
         "jmm_accept_selftest": (C.c_int32, [C.c_uint64, C.c_uint64, u64p, C.c_int32]),
+        "jmm_comm_unique_id": (C.c_int32, [u8p]),
+        "jmm_comm_create": (C.c_int32, [u8p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(H)]),
+        "jmm_comm_destroy": (C.c_int32, [H]),
+        "jmm_summaries": (C.c_int32, [H, dp]),
+        "jmm_allgather_summaries": (C.c_int32, [H, H, C.c_uint64, dp]),
+        "jmm_nccl_version": (C.c_int32, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -161,6 +168,42 @@ def rng_selftest(ctr, key, seed, n, device=0):
     t = np.zeros(max(n, 1), dtype=np.uint32)
     _check(lib().jmm_rng_selftest(c, k, o, int(seed), t.ctypes.data_as(C.POINTER(C.c_uint32)), int(n), int(device)))
     return list(o), t[:n]
+
+
+SUMMARY_DOUBLES, COMM_ID_BYTES = 24, 128
+SUMMARY_FIELDS = ("chain", "P", "T", "N", "samples", "rho", "rho2", "L", "L2", "E", "E2", "LE", "Vir", "Vir2", "EVir", "HV", "HV2",
+                  "dAcc", "dRej", "vAcc", "vRej", "L_final", "E_final", "Vir_final")
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0); hand the 128 bytes to the other ranks."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(lib().jmm_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Comm:
+    """RAII wrapper of jmm_comm (one NCCL communicator; collective constructor)."""
+
+    def __init__(self, uid: bytes, rank: int, world: int, device: int = 0):
+        self.L = lib()
+        self.c = C.c_void_p()
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(uid)
+        _check(self.L.jmm_comm_create(buf, int(rank), int(world), int(device), C.byref(self.c)))
+        self.rank, self.world = int(rank), int(world)
+
+    def close(self):
+        if getattr(self, "c", None) is not None and self.c:
+            self.L.jmm_comm_destroy(self.c)
+            self.c = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 class Handle:
@@ -242,6 +285,10 @@ class Handle:
     def zero_accum(self):
         _check(self.L.jmm_zero_accum(self.h))
 
+    def set_accum(self, accum, samples):
+        a = _f64(accum, (self.C, 12))
+        _check(self.L.jmm_set_accum(self.h, _dp(a), int(samples)))
+
     @property
     def step_number(self):
         return int(self.L.jmm_step_number(self.h))
@@ -291,6 +338,18 @@ class Handle:
 
     def set_stream(self, cuda_stream_ptr):
         _check(self.L.jmm_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def summaries(self):
+        """[nchains][SUMMARY_DOUBLES] per-chain records (SUMMARY_FIELDS), packed on the device."""
+        out = np.empty((self.C, SUMMARY_DOUBLES))
+        _check(self.L.jmm_summaries(self.h, _dp(out)))
+        return out
+
+    def allgather_summaries(self, comm: "Comm", total_chains: int):
+        """Collective: ONE ncclAllGather of every rank's records; [total_chains][SUMMARY_DOUBLES] in global chain order."""
+        out = np.empty((int(total_chains), SUMMARY_DOUBLES))
+        _check(self.L.jmm_allgather_summaries(self.h, comm.c, int(total_chains), _dp(out)))
+        return out
 
 
 def config(N, pot, nbn=-1, cutoff=math.inf, ensemble=ENS_NPT, relax=0, P=0.0, T=1.0, L=0.0, maxStep=0.1,

@@ -23,6 +23,7 @@ struct jmm_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t sn = 0, launches = 0;
+    uint64_t samples = 0;                // updateThermo calls accumulated in the running sums since jmm_zero_accum
     // many-chain launch shape
     int block = 32, pos_in_smem = 1;
     size_t smem = 0;
@@ -74,6 +75,9 @@ struct SweepShape {
 };
 
 #define JMM_INTERNAL __attribute__((visibility("hidden")))
+#include <string>
+// records the message for jmm_last_error() and returns `code` (jmm_gpu.cu)
+JMM_INTERNAL jmm_status jmm_fail(jmm_status code, const std::string &msg);
 // prod.cuh: many chains, one chain per thread or per G lanes (POT / arithmetic / G dispatch inside)
 JMM_INTERNAL cudaError_t jmm_launch_prod(jmm_handle *h, const jmm::StepArgs &a);
 // coop.cuh / bond.cuh: few chains, G lanes per chain

@@ -22,6 +22,7 @@ static jmm_status fail(jmm_status code, const std::string &msg) {
     g_err = msg;
     return code;
 }
+jmm_status jmm_fail(jmm_status code, const std::string &msg) { return fail(code, msg); }
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -484,6 +485,21 @@ extern "C" jmm_status jmm_zero_accum(jmm_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
     double *a = is_cb(h) ? h->cb_acc : h->S.acc;
     CK(cudaMemsetAsync(a, 0, h->S.nchains * 12 * sizeof(double), h->stream));
+    h->samples = 0;
+    return JMM_OK;
+}
+
+extern "C" jmm_status jmm_set_accum(jmm_handle *h, const double *accum, uint64_t samples) {
+    if (!h || !accum) return fail(JMM_ERR_INVALID, "jmm_set_accum: null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    if (is_cb(h)) {
+        CK(cudaMemcpyAsync(h->cb_acc, accum, h->S.nchains * 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        jmm_status st = upload_transposed(h, accum, h->S.acc, 12);
+        if (st != JMM_OK) return st;
+    }
+    h->samples = samples;
     return JMM_OK;
 }
 
@@ -601,6 +617,7 @@ struct CkptHeader {
     double cutoff;
     uint64_t eci, mdai, mvai;
     int32_t adapt, arith, relax, pad_;
+    uint64_t samples;
 };
 
 // the device arrays of a handle, in file order
@@ -633,7 +650,7 @@ CkptHeader ckpt_header(const jmm_handle *h) {
     k.cb_cur = 0; k.hist = h->H.ucount ? 1 : 0; k.gns = h->H.gns; k.rhonb = h->H.rhonb; k.gnb = h->H.gnb;
     k.rbw = h->H.rbw; k.gsw = h->H.gsw; k.gbw = h->H.gbw;
     k.cutoff = h->cfg.cutoff; k.eci = h->cfg.eci; k.mdai = h->cfg.mdai; k.mvai = h->cfg.mvai;
-    k.adapt = h->cfg.adapt; k.arith = h->cfg.arith; k.relax = h->cfg.relax; k.pad_ = 0;
+    k.adapt = h->cfg.adapt; k.arith = h->cfg.arith; k.relax = h->cfg.relax; k.pad_ = 0; k.samples = h->samples;
     return k;
 }
 }  // namespace
@@ -704,7 +721,7 @@ extern "C" jmm_status jmm_checkpoint_load(jmm_handle *h, const char *path) {
         return JMM_OK;
     });
     if (st != JMM_OK) return st;
-    h->sn = k.sn; h->halfsweeps = k.halfsweeps; h->cursor = k.cursor;
+    h->sn = k.sn; h->halfsweeps = k.halfsweeps; h->cursor = k.cursor; h->samples = k.samples;
     if (h->d_cursor) CK(cudaMemcpyAsync(h->d_cursor, &h->cursor, sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->keep_cursor = h->cfg.rng_kind == JMM_RNG_RECORDED;
@@ -722,9 +739,11 @@ extern "C" jmm_status jmm_start(jmm_handle *h) {
         k_sweep_finish<<<(unsigned) h->S.nchains, 32, 0, h->stream>>>(nullptr, 0, h->S.N, h->S.l, h->cb_tot, h->cb_acc, 1);
         h->launches++;
         CK(cudaGetLastError());
+        h->samples += 1;
         return JMM_OK;
     }
     CK(DISPATCH_POT_TABLE(h, launch_start, h, false));
+    h->samples += 1;
     return JMM_OK;
 }
 
@@ -734,6 +753,7 @@ extern "C" jmm_status jmm_start_parts(jmm_handle *h, int32_t do_fad, int32_t do_
     const int parts = (do_fad ? kStartFad : 0) | (do_relax ? kStartRelax : 0) | (do_thermo ? kStartThermo : 0);
     if (!parts) return JMM_OK;
     CK(DISPATCH_POT_TABLE(h, launch_start, h, false, parts));
+    if (do_thermo) h->samples += 1;
     return JMM_OK;
 }
 
@@ -923,7 +943,7 @@ extern "C" jmm_status jmm_step(jmm_handle *h, uint64_t nsteps, const uint32_t *r
         tick(h);
         CK(DISPATCH_POT_TABLE(h, launch_step_table, h, a));
         tock(h);
-        h->sn += n; remaining -= n; done += n;
+        h->sn += n; remaining -= n; done += n; h->samples += n;
         if (host_cadence) {
             const bool dis = a.mdai && h->sn % a.mdai == 0, vol = a.mvai && h->sn % a.mvai == 0;
             if (dis || vol) {
@@ -1092,7 +1112,7 @@ extern "C" jmm_status jmm_sweep(jmm_handle *h, uint64_t n_halfsweeps, uint64_t *
             CK(cudaGetLastError());
         }
         h->cb_cur ^= 1;
-        h->halfsweeps += nsub;
+        h->halfsweeps += nsub; h->samples += nsub;
         remaining -= nsub;
     }
     tock(h);

@@ -133,3 +133,51 @@ def test_bench_reference_arm_prints_the_contract_line(tmp_path):
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
     assert line["config"]["workload"].startswith("C2:")
+
+
+def test_read_input_defaults_and_nbn_zero(J, tmp_path):
+    """A deck without an NBN line means "no neighbour limit" (the reference leaves nbn uninitialised; 0 would silently
+    exclude every pair), and NBN 0 itself is refused by jmm_create."""
+    from jmmonedmc_b200.capi import config
+    p = tmp_path / "INPUT"
+    p.write_text("N 12\nPOT LJ\nT 0.9\nP 1.0\nNUMSTEPS 10\n")
+    cfg, _ = J.read_input(p)
+    assert cfg.nbn == -1
+    with pytest.raises(J.JmmError) as e:
+        J.Handle(config(N=10, pot=0, nbn=0))
+    assert e.value.status == -1 and "NBN 0" in str(e.value)
+
+
+def test_comm_api_without_a_gpu(J):
+    """The NCCL side of the ABI: the library loads without NCCL being linked (dlopen at first use); the unique id comes
+    from ncclGetUniqueId (no device needed); a communicator needs a CUDA device and says so."""
+    import torch
+    deps = subprocess.run(["ldd", str(J.lib_path())], capture_output=True, text=True).stdout
+    assert "nccl" not in deps
+    if J.lib().jmm_nccl_version() == 0:
+        with pytest.raises(J.JmmError) as e:
+            J.comm_unique_id()
+        assert e.value.status == -7
+        return
+    uid = J.comm_unique_id()
+    assert len(uid) == 128 and any(uid) and uid != J.comm_unique_id()
+    if not torch.cuda.is_available():
+        with pytest.raises(J.JmmError) as e:
+            J.Comm(uid, 0, 1, 0)
+        assert e.value.status == -2
+    with pytest.raises(J.JmmError) as e:
+        J.Comm(uid, 3, 2, 0)
+    assert e.value.status == -1
+
+
+def test_batch_driver_refuses_a_restart_deck_before_touching_outputs(J, tmp_path):
+    """jmm_run on a deck with a RESTART line: exit 1 with an explanation, existing outputs untouched (the reference
+    would reopen config.dat.mcs; silently starting from the lattice and truncating the old files would be worse)."""
+    run = ROOT / "jmmonedmc_b200" / "bin" / "jmm_run"
+    (tmp_path / "INPUT").write_text("RESTART\nN 10\nPOT LJ\nNBN -1\nT 0.9\nP 1.0\nNUMSTEPS 10\nTPI 1\nCPI 1\n")
+    (tmp_path / "thermo.dat.mcs").write_text("previous run\n")
+    (tmp_path / "config.dat.mcs").write_text("previous frames\n")
+    out = subprocess.run([str(run), "INPUT"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "RESTART" in out.stderr and "--resume" in out.stderr
+    assert (tmp_path / "thermo.dat.mcs").read_text() == "previous run\n"
+    assert (tmp_path / "config.dat.mcs").read_text() == "previous frames\n"
