@@ -270,13 +270,15 @@ class Handle:
     def adjust_step_sizes(self, dis=True, vol=True):
         _check(self.L.jmm_adjust_step_sizes(self.h, int(dis), int(vol)))
 
-    def get_state(self, r=True, l=True, totals=True, accum=True, counters=True):
+    def get_state(self, r=True, l=True, totals=True, accum=True, counters=True, out=None):
+        """out: optional dict of preallocated arrays (e.g. pinned, see pinned_empty) to fill instead of new ones."""
+        pre = out or {}
         out = {}
-        R = np.empty((self.C, self.N)) if r else None
-        Lb = np.empty(self.C) if l else None
-        T = np.empty((self.C, 9)) if totals else None
-        A = np.empty((self.C, 12)) if accum else None
-        Cn = np.empty((self.C, 4), dtype=np.uint64) if counters else None
+        R = pre.get("r", np.empty((self.C, self.N)) if r else None) if r else None
+        Lb = pre.get("l", np.empty(self.C) if l else None) if l else None
+        T = pre.get("totals", np.empty((self.C, 9)) if totals else None) if totals else None
+        A = pre.get("accum", np.empty((self.C, 12)) if accum else None) if accum else None
+        Cn = pre.get("counters", np.empty((self.C, 4), dtype=np.uint64) if counters else None) if counters else None
         _check(self.L.jmm_get_state(self.h, _dp(R), _dp(Lb), _dp(T), _dp(A),
                                     Cn.ctypes.data_as(C.POINTER(C.c_uint64)) if counters else None))
         out.update(r=R, l=Lb, totals=T, accum=A, counters=Cn)
@@ -350,6 +352,25 @@ class Handle:
         out = np.empty((int(total_chains), SUMMARY_DOUBLES))
         _check(self.L.jmm_allgather_summaries(self.h, comm.c, int(total_chains), _dp(out)))
         return out
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'd memory (jmm_host_alloc) viewed as a numpy array; freed with the object."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.L = lib()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = self.L.jmm_host_alloc(max(n, 1))
+        if not self.ptr:
+            raise JmmError(-2, "jmm_host_alloc failed")
+        buf = (C.c_uint8 * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.L.jmm_host_free(self.ptr)
+            self.ptr = None
 
 
 def config(N, pot, nbn=-1, cutoff=math.inf, ensemble=ENS_NPT, relax=0, P=0.0, T=1.0, L=0.0, maxStep=0.1,

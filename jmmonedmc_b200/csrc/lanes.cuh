@@ -28,22 +28,86 @@
 
 namespace jmm {
 
-constexpr int kLanesMaxWarps = 16;
+#ifndef JMM_LANES_MAXW
+#define JMM_LANES_MAXW 12
+#endif
+constexpr int kLanesMaxWarps = JMM_LANES_MAXW;   // 12 warps per CTA = 168 registers per thread (16 = 128: spills)
 
-// qad2 with the fast arithmetic, partners strided over the G lanes of the group.
-// NPL > 0: every lane visits exactly NPL slots p = lane + G i of a row padded to NPL*G positions (pads hold kFarAway
-// for ever); needs NBN < 0.  NPL == 0: run-time bounds (NBN >= 0 or an unusual N).
+// updateThermo :1941-1961 without twelve replicated accumulators.  Every lane of a group knows rho, l, E, Vir, HV of the
+// step, and replicated sums would cost 19 fp64 instructions per step and 24 registers in EVERY lane.  Instead the
+// five numbers of each step go into a small ring in shared memory (one lane writes), and every kThermoRing steps the
+// twelve sums — SPREAD over the lanes: lane k owns acc[k], acc[k+G], ... — are brought up to date: lane k reads its
+// operand pair (a, b) of every buffered step and does acc += a * b in step order (b = 1.0 for the linear terms: a * 1.0
+// is exact).  Same products, same order of addition per sum: the twelve sums stay bit-identical to the reference's.
+constexpr int kThermoRing = 8;                   // steps buffered
+constexpr int kThermoSlots = 6;                  // rho, l, E, Vir, HV, 1.0
+template <int G> struct ThermoLanes {
+    static constexpr int M = (kNAcc + G - 1) / G;
+    double acc[M];
+    uint32_t ia[M], ib[M];                        // operand slots of this lane's sums (byte offsets would save nothing)
+    double *ring;                                 // [kThermoRing][kThermoSlots] doubles of this group
+    uint32_t fill;
+    // sums in JMM_A_* order: rho, rho^2, l, l^2, E, E^2, l E, Vir, Vir^2, E Vir, HV, HV^2
+    static __device__ __forceinline__ void operands(uint32_t k, uint32_t &a, uint32_t &b) {
+        const uint32_t A[12] = {0, 0, 1, 1, 2, 2, 1, 3, 3, 2, 4, 4};
+        const uint32_t B[12] = {5, 0, 5, 1, 5, 2, 2, 5, 3, 3, 5, 4};
+        a = A[k < 12 ? k : 0]; b = B[k < 12 ? k : 0];
+    }
+    __device__ __forceinline__ void init(double *ring_, uint32_t lane, const double *acc_g, uint64_t C, uint64_t chain) {
+        ring = ring_; fill = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t k = lane + m * G;
+            operands(k, ia[m], ib[m]);
+            acc[m] = k < kNAcc ? __ldcg(acc_g + (uint64_t) k * C + chain) : 0.0;
+        }
+    }
+    template <int POT>
+    __device__ __forceinline__ void push(const Coop<POT, G> &c) {                 // one step's numbers (any one lane writes)
+        if (c.lane == 0) {
+            double *e = ring + fill * kThermoSlots;
+            e[0] = c.rho; e[1] = c.l; e[2] = c.tot[0]; e[3] = c.tot[1];
+            e[4] = PotTraits<POT>::NC > 6 ? c.tot[6] : 0.0;
+            e[5] = 1.0;
+        }
+        ++fill;
+    }
+    template <int POT>
+    __device__ __forceinline__ void flush(const Coop<POT, G> &c) {                // bring the sums up to date
+        c.sync();
+        if (fill == kThermoRing) {
+#pragma unroll
+            for (int e = 0; e < kThermoRing; ++e) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
+            }
+        } else {
+            for (uint32_t e = 0; e < fill; ++e) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
+            }
+        }
+        fill = 0;
+        c.sync();
+    }
+    __device__ __forceinline__ void store(uint32_t lane, double *acc_g, uint64_t C, uint64_t chain) const {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t k = lane + m * G;
+            if (k < kNAcc) acc_g[(uint64_t) k * C + chain] = acc[m];
+        }
+    }
+};
+
+// The partner sums of one displacement trial: s6 = sum(b^-6 - a^-6), s12 = sum(b^-12 - a^-12) over the partners of
+// `nm`, strided over the G lanes and closed by an xor butterfly (identical bits in every lane of the group).
+// The slot of the moved particle holds kFarAway while this runs (see lanes_run_chain), so there is no per-partner
+// index test.  NPL > 0: every lane visits exactly NPL slots p = lane + G i of a row padded to NPL*G positions (pads
+// hold kFarAway for ever); needs NBN < 0.  NPL == 0: run-time bounds (NBN >= 0 or an unusual N).
 template <int POT, int G, int NPL>
-__device__ __forceinline__ uint8_t lanes_displacement(Coop<POT, G> &c, uint32_t nm, double rn, double ran) {
+__device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32_t nm, double rnm, double rT, double &s6, double &s12) {
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
-    const double md = (rn - 0.5) * 2 * c.maxStep;
-    const double rnm = c.r[nm];
-    const double rT = rnm + md;
-    if (fabs(rT) > c.half_l) { c.cnt[1]++; return kLogWall; }
-    c.sync();                                     // every lane has read r[nm]
-    if (c.lane == 0) c.r[nm] = kFarAway;          // the moved particle leaves the loop without a per-partner test
-    c.sync();
-    double s6 = 0, s12 = 0;
+    s6 = 0; s12 = 0;
     if constexpr (NPL > 0) {
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
@@ -76,21 +140,21 @@ __device__ __forceinline__ uint8_t lanes_displacement(Coop<POT, G> &c, uint32_t 
         s6 += __shfl_xor_sync(c.gmask, s6, o, G);
         s12 += __shfl_xor_sync(c.gmask, s12, o, G);
     }
-    const double dE12 = 4 * s12, dE6 = 4 * s6;
-    const double dE = dE12 - dE6;
-    const bool acc = metropolis_accept(dE, c.T, c.invT, ran);
-    if (c.lane == 0) c.r[nm] = acc ? rT : rnm;    // (every lane is past its loads: the butterfly is a rendezvous)
-    c.sync();
-    if (!acc) { c.cnt[1]++; return 0; }
-    c.cnt[0]++;
-    const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
-    c.tot[0] += dE;  c.tot[2] += dE12; c.tot[4] += dE6;
-    c.tot[1] += dV12 - dV6; c.tot[3] += dV12; c.tot[5] += dV6;
-    c.tot[6] += dH12 - dH6; c.tot[7] += dH12; c.tot[8] += dH6;
-    return kLogAccepted;
 }
 
 // One chain (the G lanes of its group) advanced by `count` steps starting after step sn0.
+//
+// The step loop is software-pipelined, because with ~2000 warps on the machine this kernel is bound by the LATENCY
+// of one step, not by instruction throughput (first version: 3000 cycles per step, 62 % of the stall samples outside
+// the partner loop, profiles/r2a_c4lanes_*):
+//   * the random numbers of step t+1 are shuffled out of the Philox batch at the top of step t, so that their
+//     latency hides behind the partner loop of step t;
+//   * the end of a trial and the beginning of the next one are ONE shared-memory transaction by lane 0 — write
+//     r[nm] (new or old position), read r[nm'] of the next trial, put the far-away sentinel there — followed by one
+//     shuffle of that position and one group rendezvous, instead of three rendezvous per step;
+//   * the Metropolis rule is evaluated without branches (the exact expression only inside the approximation band);
+//   * the four interval countdowns (ECheck, the two adjustments, relaxVolume) are one counter; a step on which any
+//     of them is due takes the slow path, which first makes the positions consistent again.
 template <int POT, int G, int NPL, bool LOG>
 __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepArgs &a, uint64_t chain, double *row, uint32_t npad,
                                                 uint64_t sn0, uint32_t count, uint64_t log_row0) {
@@ -111,74 +175,139 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
 #pragma unroll
     for (int k = 0; k < NC; ++k) c.tot[k] = __ldcg(S.tot + k * C + chain);
 #pragma unroll
-    for (int k = 0; k < kNAcc; ++k) c.acc[k] = __ldcg(S.acc + k * C + chain);
-#pragma unroll
     for (int k = 0; k < kNCnt; ++k) c.cnt[k] = __ldcg(S.cnt + k * C + chain);
     c.vAErr = __ldcg(S.vAErr + chain); c.echecks = __ldcg(S.echeck + chain); c.discrepancies = __ldcg(S.echeck + C + chain);
     for (uint32_t i = c.lane; i < npad; i += G) row[i] = i < c.N ? __ldcg(S.r + (uint64_t) i * C + chain) : kFarAway;
+    ThermoLanes<G> th;                            // (c.acc is not used by this kernel)
+    th.init(c.sc + G * NC, c.lane, S.acc, C, chain);
     c.sync();
 
     const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32), cid = (uint32_t)(S.chain_id0 + chain);
     const uint32_t ntt = (uint32_t) S.numTrialTypes;
     const uint32_t scale = 0xffffffffu / ntt;
     const bool scaling_volume = (POT == kPotLJ) && S.nbn < 0;
+    const bool relax_on = a.adapt_device && S.relax > 0 && S.ensemble == kEnsNPT;
     uint64_t sn = sn0;
-    auto until = [&](uint64_t every) -> uint32_t {
-        if (!every) return 0xffffffffu;
-        const uint64_t left = every - sn % every;
-        return left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left;
+    // steps until the next one on which ECheck, an adjustment or a relaxation is due (a launch is far shorter than 2^32 steps)
+    auto until_event = [&]() -> uint32_t {
+        uint64_t left = 0xffffffffull;
+        auto upd = [&](uint64_t every) { if (every) left = min(left, every - sn % every); };
+        upd(a.eci);
+        if (a.adapt_device) { upd(a.mdai); upd(a.mvai); }
+        if (relax_on && sn < 1000000ull) upd(10000);
+        return (uint32_t) left;
     };
-    uint32_t eci_left = until(a.eci);
-    uint32_t mdai_left = a.adapt_device ? until(a.mdai) : 0xffffffffu;
-    uint32_t mvai_left = a.adapt_device ? until(a.mvai) : 0xffffffffu;
-    uint32_t relax_left = (a.adapt_device && S.relax > 0 && S.ensemble == kEnsNPT) ? until(10000) : 0xffffffffu;
-    const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
-    const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
-    const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
+    uint32_t ev_left = until_event();
 
     uint32_t my_nm = 0, my_w1 = 0, my_w2 = 0;                 // this lane's share of the Philox batch
     uint32_t batch_pos = G;                                   // G = empty
-
-    for (uint32_t s = 0; s < count; ++s) {
-        ++sn;
-        if (batch_pos == G) {                                 // lane j draws the block of step sn + j
-            const uint64_t mine = sn + c.lane;
+    // trial type and the two words of step `step` (called with consecutive step numbers): lane j of the group holds the
+    // block of the j-th step of the current batch, so one pass of Philox serves G steps
+    auto draw = [&](uint64_t step, uint32_t &nm_o, uint32_t &w1_o, uint32_t &w2_o) {
+        if (batch_pos == G) {
+            const uint64_t mine = step + c.lane;
             const Philox4 b = philox4x32_10((uint32_t) mine, (uint32_t)(mine >> 32), cid, kTagTrial, k0, k1);
             uint32_t k = b.w[0] / scale;                      // gsl_rng_uniform_int rule, see Rng<kRngPhilox>
             if (k >= ntt) { k = b.w[3] / scale; if (k >= ntt) k = mulhi32(b.w[3], ntt); }
             my_nm = k; my_w1 = b.w[1]; my_w2 = b.w[2];
             batch_pos = 0;
         }
-        const uint32_t nm = __shfl_sync(c.gmask, my_nm, batch_pos, G);
-        const double rn = u01(__shfl_sync(c.gmask, my_w1, batch_pos, G));
-        const double ran = u01(__shfl_sync(c.gmask, my_w2, batch_pos, G));
+        nm_o = __shfl_sync(c.gmask, my_nm, batch_pos, G);
+        w1_o = __shfl_sync(c.gmask, my_w1, batch_pos, G);
+        w2_o = __shfl_sync(c.gmask, my_w2, batch_pos, G);
         ++batch_pos;
+    };
+    // lane 0: [write `val` to r[nm_w]] [read r[nm_r], leave the sentinel there]; everyone gets that position
+    auto handover = [&](bool wr, uint32_t nm_w, double val, bool rd, uint32_t nm_r) -> double {
+        double got = 0.0;
+        if (c.lane == 0) {
+            if (wr) c.r[nm_w] = val;
+            if (rd) { got = c.r[nm_r]; c.r[nm_r] = kFarAway; }
+        }
+        got = __shfl_sync(c.gmask, got, 0, G);
+        c.sync();
+        return got;
+    };
+
+    uint32_t nm, w1, w2;
+    draw(sn + 1, nm, w1, w2);
+    bool disp = nm < c.N;
+    double rnm = handover(false, 0, 0.0, disp, nm);
+
+    for (uint32_t s = 0; s < count; ++s) {
+        ++sn;
+        const bool more = s + 1 < count;
+        uint32_t nm1 = 0, w11 = 0, w21 = 0;
+        if (more) draw(sn + 1, nm1, w11, w21);                // (uniform in the warp: every group runs `count` steps)
+        const bool disp1 = more && nm1 < c.N;
 
         uint8_t flags;
-        if (nm < c.N) flags = lanes_displacement<POT, G, NPL>(c, nm, rn, ran);
-        else {
+        bool acc = false;
+        double rT = 0.0;
+        if (disp) {                                           // qad2 :1160-1464
+            const double md = u01_shifted(w1, 1.5) * 2 * c.maxStep;     // (rn - 0.5) * 2 * maxStep, :1182
+            rT = rnm + md;
+            const bool wall = fabs(rT) > c.half_l;            // :1188
+            flags = wall ? kLogWall : 0;
+            if (!wall) {
+                double s6, s12;
+                lanes_partner_sums<POT, G, NPL>(c, nm, rnm, rT, s6, s12);
+                const double dE12 = 4 * s12, dE6 = 4 * s6;
+                const double dE = dE12 - dE6;
+                // Metropolis rule :1367-1377 through the band of metropolis_accept(), without early-out branches
+                const double ran = u01_shifted(w2, 1.0);
+                const double ea = (double) exp_neg_approx(dE * c.invT);
+                const bool down = dE <= 0;
+                const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+                acc = down | acc_b;
+                if (!(down | acc_b | rej_b)) acc = metropolis_exact(dE, c.T, ran);
+                if (acc) {
+                    const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
+                    c.tot[0] += dE;  c.tot[2] += dE12; c.tot[4] += dE6;
+                    c.tot[1] += dV12 - dV6; c.tot[3] += dV12; c.tot[5] += dV6;
+                    c.tot[6] += dH12 - dH6; c.tot[7] += dH12; c.tot[8] += dH6;
+                    flags = kLogAccepted;
+                }
+            }
+            c.cnt[0] += acc ? 1 : 0;
+            c.cnt[1] += acc ? 0 : 1;
+        } else {                                              // volume trial: no sentinel is out, the row is consistent
+            const double rn = u01(w1), ran = u01(w2);
+            th.flush(c);                                      // (fav's ordered sums use the scratch next to the ring; rare anyway)
             if constexpr (POT == kPotLJ) {
                 flags = scaling_volume ? coop_volume_scaling(c, rn, ran) : coop_volume_full(c, rn, ran);
             } else flags = coop_volume_full(c, rn, ran);
         }
-        if (--eci_left == 0) { coop_energy_check(c); eci_left = eci32; }
-        coop_update_thermo(c);
-        if (LOG && c.lane == 0) a.accept_log[(log_row0 + s) * C + chain] = flags;
-        if (a.adapt_device) {
-            if (--mdai_left == 0) { coop_adjust_max_step(c, a.log_ideal); mdai_left = mdai32; }
-            if (--mvai_left == 0) { coop_adjust_max_dl(c, a.log_ideal); mvai_left = mvai32; }
-            if (--relax_left == 0) { if (sn < 1000000ull) coop_relax_volume(c); relax_left = 10000; }
+
+        double rnm1;
+        if (--ev_left != 0) {
+            th.push(c);                                       // updateThermo :1805 (the state of this step; the sums follow in flush)
+            rnm1 = handover(disp, nm, acc ? rT : rnm, disp1, nm1);
+            if (th.fill == kThermoRing) th.flush(c);
+        } else {
+            handover(disp, nm, acc ? rT : rnm, false, 0);     // positions consistent for whatever is due now
+            th.flush(c);
+            if (a.eci && sn % a.eci == 0) coop_energy_check(c);                        // Step :1800
+            th.push(c); th.flush(c);                                                     // :1805
+            if (a.adapt_device) {                                                        // src/Main.cpp:145-176
+                if (a.mdai && sn % a.mdai == 0) coop_adjust_max_step(c, a.log_ideal);
+                if (a.mvai && sn % a.mvai == 0) coop_adjust_max_dl(c, a.log_ideal);
+                if (relax_on && sn % 10000 == 0 && sn < 1000000ull) coop_relax_volume(c);
+            }
+            ev_left = until_event();
+            rnm1 = handover(false, 0, 0.0, disp1, nm1);
         }
+        if (LOG && c.lane == 0) a.accept_log[(log_row0 + s) * C + chain] = flags;
+        nm = nm1; w1 = w11; w2 = w21; rnm = rnm1; disp = disp1;
     }
 
-    c.sync();
+    th.flush(c);
+    th.store(c.lane, S.acc, C, chain);
     for (uint32_t i = c.lane; i < c.N; i += G) S.r[(uint64_t) i * C + chain] = row[i];
     if (c.lane == 0) {
         S.l[chain] = c.l; S.maxStep[chain] = c.maxStep; S.maxdl[chain] = c.maxdl;
 #pragma unroll
         for (int k = 0; k < NC; ++k) S.tot[k * C + chain] = c.tot[k];
-#pragma unroll
-        for (int k = 0; k < kNAcc; ++k) S.acc[k * C + chain] = c.acc[k];
 #pragma unroll
         for (int k = 0; k < kNCnt; ++k) S.cnt[k * C + chain] = c.cnt[k];
         S.vAErr[chain] = c.vAErr; S.echeck[chain] = c.echecks; S.echeck[C + chain] = c.discrepancies;

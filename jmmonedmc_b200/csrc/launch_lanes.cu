@@ -76,7 +76,7 @@ void jmm_lanes_shape(jmm_handle *h, int g) {
     h->lanes_g = g;
     h->lanes_npl = unrolled ? npl_t : 0;
     h->lanes_npad = unrolled ? g * npl_t : N;
-    int stride = h->lanes_npad + g * 9;
+    int stride = h->lanes_npad + g * 9 + kThermoRing * kThermoSlots;   // positions, [G][NC] scratch, thermo ring
     while (stride % 16 != g % 16) ++stride;                  // the groups of a half-warp start G (mod 16) banks apart
     h->lanes_stride = stride;
 }
