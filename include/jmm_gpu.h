@@ -63,6 +63,16 @@ enum { JMM_ARITH_REFERENCE = 0, /* every pair term and sum as in src/pot.cpp / q
        JMM_ARITH_FAST = 1 };    /* LJ/LJcut: one division per partner, r^-6/r^-12 differences only;
                                    totals equal to <= 1e-12 relative, same decisions (see prod.cuh)   */
 
+/* jmm_config.flags.  The reference's running virial is path-dependent: its pair virial carries no 1/l
+ * (src/pot.cpp:60-63), fav / moveVolume / ECheck set Vir = sum of pair virials (src/jmmMCState.cpp:2261, 2908, 2077),
+ * but an accepted qavLJ move rescales Vir6, Vir12 by (l'/l)^-7, ^-13, adds the ideal term N T / l, and leaves HV, HV6,
+ * HV12 untouched (:1675-1686).  Lock-step and the default production mode reproduce that bit for bit.
+ * JMM_FLAG_CONSISTENT_VIRIAL makes an accepted qavLJ move keep the definition the other paths use — Vir6, HV6 scale
+ * by (l'/l)^-6, Vir12, HV12 by ^-12, Vir = Vir12 - Vir6, HV = HV12 - HV6, no ideal term — so that the running Vir and HV
+ * always equal the configuration sums (jmm_energy).  Positions, box length, E and every accept/reject decision are the
+ * same with and without the flag; only the Virial / HV columns of thermo.dat.mcs and Summary.dat change. */
+enum { JMM_FLAG_CONSISTENT_VIRIAL = 1 };
+
 /* index of each total in a 9-vector: the order phi() writes them, src/pot.cpp:90-100 */
 enum { JMM_E = 0, JMM_VIR, JMM_E12, JMM_VIR12, JMM_E6, JMM_VIR6, JMM_HV, JMM_HV12, JMM_HV6, JMM_NTOT };
 /* index of each running sum in a 12-vector: updateThermo, src/jmmMCState.cpp:1941-1961 */
@@ -95,7 +105,7 @@ typedef struct jmm_config {
     int32_t  adapt;        /* JMM_ADAPT_*                                                        */
     int32_t  device;       /* CUDA device ordinal                                                */
     int32_t  arith;        /* JMM_ARITH_*                                                        */
-    int32_t  reserved;     /* 0                                                                  */
+    int32_t  flags;        /* JMM_FLAG_* bits; 0 = everything as the reference does it           */
 } jmm_config;
 
 /* The print/cadence keywords of the INPUT deck that the hot path itself does not consume

@@ -8,7 +8,7 @@ CPU fallback — every compute call fails loudly if the CUDA library or a GPU is
 from .capi import (  # noqa: F401
     JmmError, Config, Deck, Handle, Comm, comm_unique_id, SUMMARY_DOUBLES, SUMMARY_FIELDS, lib, lib_path, read_input, rng_selftest, accept_selftest, declared_symbols,
     POT_LJ, POT_LJCUT, POT_HARMONIC, ENS_NPT, ENS_NLT, RNG_TAUS2, RNG_PHILOX, RNG_RECORDED,
-    MODE_TABLE, MODE_RECOMPUTE, MODE_CHECKERBOARD, ADAPT_HOST, ADAPT_DEVICE, ADAPT_CALLER, ARITH_REFERENCE, ARITH_FAST,
+    MODE_TABLE, MODE_RECOMPUTE, MODE_CHECKERBOARD, ADAPT_HOST, ADAPT_DEVICE, ADAPT_CALLER, ARITH_REFERENCE, ARITH_FAST, FLAG_CONSISTENT_VIRIAL,
     LOG_ACCEPTED, LOG_VOLUME, LOG_WALL,
 )
 from .build import build  # noqa: F401

@@ -17,6 +17,7 @@ RNG_TAUS2, RNG_PHILOX, RNG_RECORDED = 0, 1, 2
 MODE_TABLE, MODE_RECOMPUTE, MODE_CHECKERBOARD = 0, 1, 2
 ADAPT_HOST, ADAPT_DEVICE, ADAPT_CALLER = 0, 1, 2
 ARITH_REFERENCE, ARITH_FAST = 0, 1
+FLAG_CONSISTENT_VIRIAL = 1
 LOG_ACCEPTED, LOG_VOLUME, LOG_WALL = 1, 2, 4
 
 
@@ -35,7 +36,7 @@ class Config(C.Structure):
         ("eci", C.c_uint64), ("mdai", C.c_uint64), ("mvai", C.c_uint64),
         ("seed", C.c_uint64), ("nchains", C.c_uint64), ("chain_id0", C.c_uint64),
         ("rng_kind", C.c_int32), ("mode", C.c_int32), ("adapt", C.c_int32), ("device", C.c_int32),
-        ("arith", C.c_int32), ("reserved", C.c_int32),
+        ("arith", C.c_int32), ("flags", C.c_int32),
     ]
 
     def copy(self, **kw):
@@ -375,11 +376,12 @@ class PinnedBuffer:
 
 def config(N, pot, nbn=-1, cutoff=math.inf, ensemble=ENS_NPT, relax=0, P=0.0, T=1.0, L=0.0, maxStep=0.1,
            maxdl=0.1, eci=0, mdai=0, mvai=0, seed=1, nchains=1, chain_id0=0, rng_kind=RNG_PHILOX,
-           mode=MODE_RECOMPUTE, adapt=ADAPT_DEVICE, device=0, arith=ARITH_REFERENCE) -> Config:
+           mode=MODE_RECOMPUTE, adapt=ADAPT_DEVICE, device=0, arith=ARITH_REFERENCE, flags=0) -> Config:
     c = Config()
     c.N, c.nbn, c.pot, c.cutoff, c.ensemble, c.relax = N, nbn, pot, cutoff, ensemble, relax
     c.P, c.T, c.L, c.maxStep, c.maxdl = P, T, L, maxStep, maxdl
     c.eci, c.mdai, c.mvai, c.seed, c.nchains, c.chain_id0 = eci, mdai, mvai, seed, nchains, chain_id0
     c.rng_kind, c.mode, c.adapt, c.device = rng_kind, mode, adapt, device
     c.arith = arith
+    c.flags = flags
     return c

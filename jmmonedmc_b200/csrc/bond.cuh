@@ -106,7 +106,7 @@ __device__ __forceinline__ double b2_etest_partial(const B2Chain &c) {
 
 __device__ __forceinline__ void b2_load(B2Chain &c, const ChainsDev &S, uint64_t chain, double *row, uint32_t lane, uint32_t gmask) {
     const uint64_t C = S.nchains;
-    c.lane = lane; c.gmask = gmask; c.r = row; c.sc = nullptr; c.chain_of_bonds = true; c.lean = false;
+    c.lane = lane; c.gmask = gmask; c.r = row; c.sc = nullptr; c.chain_of_bonds = true; c.lean = false; c.consistent_virial = false;
     c.N = (uint32_t) S.N; c.nbn = S.nbn; c.cutoff = S.cutoff;
     c.P = S.P[chain]; c.T = S.T[chain]; c.maxStep = S.maxStep[chain]; c.maxdl = S.maxdl[chain];
     c.invT = 1.0 / c.T;

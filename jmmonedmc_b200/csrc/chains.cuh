@@ -35,6 +35,7 @@ struct ChainsDev {
     uint64_t *echeck; // [2][nchains] checks, discrepancies
     uint32_t *taus;   // [3][nchains]
     uint64_t seed, chain_id0;
+    int flags;        // JMM_FLAG_* of the handle's jmm_config
 };
 
 struct StepArgs {
@@ -177,6 +178,7 @@ struct Chain {
     double acc[kNAcc];
     uint64_t cnt[kNCnt];
     uint64_t vAErr, echecks, discrepancies;
+    bool consistent_virial;       // JMM_FLAG_CONSISTENT_VIRIAL
 };
 
 // r *= f for the whole chain (qavLJ :1692, fav :2264-2266, moveVolume :2847-2849)
@@ -456,10 +458,15 @@ __device__ __forceinline__ uint8_t volume_trial_scaling(Chain<POT> &ch, double r
     ch.tot[2] = E12Trial;
     ch.tot[4] = E6Trial;
     ch.l = ch.l + dl;
-    const double lRat7 = lRat6 / lRat1, lRat13 = lRat12 / lRat1;
-    ch.tot[5] = lRat7 * ch.tot[5];
-    ch.tot[3] = lRat13 * ch.tot[3];
-    ch.tot[1] = (double) ch.N * ch.T / ch.l + ch.tot[3] - ch.tot[5];                 // :1686
+    if (ch.consistent_virial) {            // JMM_FLAG_CONSISTENT_VIRIAL: the definition fav / moveVolume / ECheck use
+        ch.tot[5] = lRat6 * ch.tot[5];  ch.tot[3] = lRat12 * ch.tot[3];  ch.tot[1] = ch.tot[3] - ch.tot[5];
+        ch.tot[8] = lRat6 * ch.tot[8];  ch.tot[7] = lRat12 * ch.tot[7];  ch.tot[6] = ch.tot[7] - ch.tot[8];
+    } else {
+        const double lRat7 = lRat6 / lRat1, lRat13 = lRat12 / lRat1;
+        ch.tot[5] = lRat7 * ch.tot[5];
+        ch.tot[3] = lRat13 * ch.tot[3];
+        ch.tot[1] = (double) ch.N * ch.T / ch.l + ch.tot[3] - ch.tot[5];             // :1686 (HV, HV6, HV12 stay as they were)
+    }
     if (defer_scale) *defer_scale = lRat1;                                           // the caller scales (prod.cuh: warp-cooperative)
     else scale_positions(ch, lRat1);                                                 // :1692
     if (TABLE) {
@@ -581,7 +588,7 @@ template <int POT, bool CG = false>
 __device__ __forceinline__ void load_chain(Chain<POT> &ch, const ChainsDev &S, uint64_t c, double *smem_col,
                                            uint32_t smem_stride) {
     constexpr int NC = PotTraits<POT>::NC;
-    ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff;
+    ch.N = (uint32_t) S.N; ch.nbn = S.nbn; ch.cutoff = S.cutoff; ch.consistent_virial = (S.flags & 1) != 0;
     ch.l = ld_state<CG>(S.l + c); ch.P = ld_state<CG>(S.P + c); ch.T = ld_state<CG>(S.T + c);
     ch.maxStep = ld_state<CG>(S.maxStep + c); ch.maxdl = ld_state<CG>(S.maxdl + c);
     ch.invT = 1.0 / ch.T;

@@ -44,6 +44,7 @@ struct Coop {
     uint32_t lane;                                // 0..G-1 inside the group
     uint32_t gmask;                               // lanes of this group inside the warp
     bool chain_of_bonds;                          // NBN == 1 and N-1 <= G: one nearest-neighbour pair per lane
+    bool consistent_virial;                       // JMM_FLAG_CONSISTENT_VIRIAL (include/jmm_gpu.h)
     bool lean;                                    // scratch is [G][NC] only: ordered sums spread over the lanes (lanes.cuh)
 
     __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
@@ -388,10 +389,15 @@ __device__ __forceinline__ uint8_t coop_volume_scaling(Coop<POT, G> &c, double r
     c.tot[2] = E12Trial;
     c.tot[4] = E6Trial;
     c.set_l(c.l + dl);
-    const double lRat7 = lRat6 / lRat1, lRat13 = lRat12 / lRat1;
-    c.tot[5] = lRat7 * c.tot[5];
-    c.tot[3] = lRat13 * c.tot[3];
-    c.tot[1] = (double) c.N * c.T / c.l + c.tot[3] - c.tot[5];
+    if (c.consistent_virial) {
+        c.tot[5] = lRat6 * c.tot[5];  c.tot[3] = lRat12 * c.tot[3];  c.tot[1] = c.tot[3] - c.tot[5];
+        c.tot[8] = lRat6 * c.tot[8];  c.tot[7] = lRat12 * c.tot[7];  c.tot[6] = c.tot[7] - c.tot[8];
+    } else {
+        const double lRat7 = lRat6 / lRat1, lRat13 = lRat12 / lRat1;
+        c.tot[5] = lRat7 * c.tot[5];
+        c.tot[3] = lRat13 * c.tot[3];
+        c.tot[1] = (double) c.N * c.T / c.l + c.tot[3] - c.tot[5];
+    }
     coop_scale_positions(c, lRat1, true);
     return kLogVolume | kLogAccepted;
 }
@@ -459,6 +465,7 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
     c.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     c.chain_of_bonds = (S.nbn == 1) && (S.N - 1 <= (uint64_t) G);
     c.lean = false;
+    c.consistent_virial = (S.flags & 1) != 0;
     const size_t per_group = (size_t) npad + (size_t) kCoopChunk * 2 * NC;
     c.r = smem + gib * per_group;
     c.sc = c.r + npad;

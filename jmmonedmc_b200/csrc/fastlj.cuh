@@ -62,6 +62,41 @@ __device__ __forceinline__ void lj_partner(double a, double b, double cutoff, do
     s12 = __fma_rn(d6, t6, s12);
 }
 
+// NP partners at once, written stage by stage (all first differences, all squares, all sixth powers, all reciprocals,
+// ...) so that the NP independent dependency chains are issued interleaved: consecutive instructions of one chain
+// are then NP issue slots (2 NP cycles) apart, which covers the fp64 latency without a second warp.  Written one
+// partner after the other (lj_partner in an unrolled loop) ptxas keeps only ~2 chains in flight when registers are
+// tight and the loop stalls on its own dependencies (profiles/r2b_c4lanes_*: "wait" 2.1 warps per issue).
+// a[i], b[i] = old and new signed distance of partner i; the sums are accumulated in index order (as lj_partner).
+template <bool CUT, int NP>
+__device__ __forceinline__ void lj_partners(const double (&a)[NP], const double (&b)[NP], double cutoff, double &s6, double &s12) {
+    double A[NP], B[NP], x[NP], y[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { A[i] = a[i] * a[i]; B[i] = b[i] * b[i]; }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { x[i] = A[i] * A[i]; y[i] = B[i] * B[i]; }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { A[i] = x[i] * A[i]; B[i] = y[i] * B[i]; }          // a^6, b^6
+#pragma unroll
+    for (int i = 0; i < NP; ++i) x[i] = A[i] * B[i];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) x[i] = __fma_rn(-x[i], y[i], 1.0);                    // e = 1 - x y
+#pragma unroll
+    for (int i = 0; i < NP; ++i) x[i] = __fma_rn(x[i], x[i], x[i]);                    // e + e^2
+#pragma unroll
+    for (int i = 0; i < NP; ++i) y[i] = __fma_rn(y[i], x[i], y[i]);                    // 1/(A B), see rcp_cubic
+    if constexpr (CUT) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) { mask_beyond(A[i], b[i], cutoff); mask_beyond(B[i], a[i], cutoff); }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { x[i] = (A[i] - B[i]) * y[i]; y[i] = (A[i] + B[i]) * y[i]; }   // d6, t6
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { s6 += x[i]; s12 = __fma_rn(x[i], y[i], s12); }
+}
+
 // The nine deltas of qad2 from (s6, s12), component order of src/pot.cpp:90-100.
 __device__ __forceinline__ void lj_nine(double s6, double s12, double (&d)[9]) {
     const double e12 = 4 * s12, e6 = 4 * s6;

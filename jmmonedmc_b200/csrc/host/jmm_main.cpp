@@ -9,6 +9,7 @@
 //                                       (default DIR/.jmm_nccl_id, written by rank 0).
 //           [--layout runjobs]          also write data/<POT>/m<NBN>/N<N>/P<P>_T<T>/{INPUT,thermo.dat.mcs} per state
 //                                       point under DIR: the tree scripts/RunJobs.bash:27 creates with one LSF job each
+//           [--consistent-virial]       JMM_FLAG_CONSISTENT_VIRIAL: the running Virial/HV columns equal the configuration sums
 //           [--device D]                CUDA device (default: the deck's GPU keyword; the rank when --world > 1)
 //           [--checkpoint F] [--resume F]   exact restart (jmm_checkpoint_save / jmm_checkpoint_load): write F at the
 //                                       end of the run / continue from F (outputs are appended, never truncated)
@@ -63,7 +64,7 @@ static std::string short_num(double x) {
 int main(int argc, char **argv) {
     std::string input = "INPUT", outdir = ".", ckpt_out, ckpt_in, id_file, layout;
     uint64_t chains = 0, rank = 0, world = 1;
-    bool lockstep = false, fast = false;
+    bool lockstep = false, fast = false, consistent = false;
     int device = -1;                     // --device D; default: the deck's GPU keyword, or the rank when --world > 1
     double sp[3] = {0, 0, 0}, st[3] = {0, 0, 0};
     for (int i = 1; i < argc; ++i) {
@@ -73,6 +74,7 @@ int main(int argc, char **argv) {
         else if (a == "--outdir") { need(1); outdir = argv[++i]; }
         else if (a == "--lockstep") lockstep = true;
         else if (a == "--fast") fast = true;
+        else if (a == "--consistent-virial") consistent = true;
         else if (a == "--checkpoint") { need(1); ckpt_out = argv[++i]; }
         else if (a == "--resume") { need(1); ckpt_in = argv[++i]; }
         else if (a == "--id-file") { need(1); id_file = argv[++i]; }
@@ -98,6 +100,7 @@ int main(int argc, char **argv) {
     if (layout.size() && layout != "runjobs") { fprintf(stderr, "jmm_run: unknown --layout %s\n", layout.c_str()); return 1; }
     if (rank >= world) { fprintf(stderr, "jmm_run: --rank must be < --world\n"); return 1; }
     if (fast) cfg.arith = JMM_ARITH_FAST;
+    if (consistent) cfg.flags |= JMM_FLAG_CONSISTENT_VIRIAL;
     if (device >= 0) cfg.device = device;
     else if (world > 1 && cfg.device == 0) cfg.device = (int32_t) rank;
     if (id_file.empty()) id_file = outdir + "/.jmm_nccl_id";

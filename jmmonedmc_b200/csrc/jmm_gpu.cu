@@ -164,6 +164,10 @@ static jmm_status validate(const jmm_config *c) {
     if (c->mode < JMM_MODE_TABLE || c->mode > JMM_MODE_CHECKERBOARD) return fail(JMM_ERR_INVALID, "bad mode");
     if (c->adapt < JMM_ADAPT_HOST || c->adapt > JMM_ADAPT_CALLER) return fail(JMM_ERR_INVALID, "bad adapt");
     if (c->arith != JMM_ARITH_REFERENCE && c->arith != JMM_ARITH_FAST) return fail(JMM_ERR_INVALID, "bad arith");
+    if (c->flags & ~JMM_FLAG_CONSISTENT_VIRIAL) return fail(JMM_ERR_INVALID, "unknown bits in jmm_config.flags");
+    if ((c->flags & JMM_FLAG_CONSISTENT_VIRIAL) && (c->mode == JMM_MODE_TABLE || c->rng_kind != JMM_RNG_PHILOX))
+        return fail(JMM_ERR_INVALID, "JMM_FLAG_CONSISTENT_VIRIAL is a production option (Philox stream, RECOMPUTE or CHECKERBOARD mode); "
+                                     "lock-step reproduces the reference's running virial as it is");
     if (c->arith == JMM_ARITH_FAST && (c->pot == JMM_POT_HARMONIC || c->mode == JMM_MODE_TABLE || c->rng_kind != JMM_RNG_PHILOX))
         return fail(JMM_ERR_INVALID, "JMM_ARITH_FAST is for LJ/LJcut with the Philox stream (RECOMPUTE or CHECKERBOARD mode)");
     if (c->rng_kind == JMM_RNG_RECORDED && c->nchains != 1)
@@ -230,7 +234,7 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
     S.nchains = C; S.N = N; S.npairs = N * (N - 1) / 2;
     S.numTrialTypes = (cfg->ensemble == JMM_ENS_NPT) ? N + 1 : N;   // :405,415
     S.nbn = cfg->nbn; S.ensemble = cfg->ensemble; S.relax = h->cfg.relax; S.pot = cfg->pot;
-    S.cutoff = h->cfg.cutoff; S.seed = cfg->seed; S.chain_id0 = cfg->chain_id0;
+    S.cutoff = h->cfg.cutoff; S.seed = cfg->seed; S.chain_id0 = cfg->chain_id0; S.flags = cfg->flags;
     CKH(dalloc(h, &S.l, C)); CKH(dalloc(h, &S.P, C)); CKH(dalloc(h, &S.T, C));
     CKH(dalloc(h, &S.maxStep, C)); CKH(dalloc(h, &S.maxdl, C));
 
@@ -616,7 +620,7 @@ struct CkptHeader {
     // (format 2) what decides the cadence and the arithmetic of the continuation
     double cutoff;
     uint64_t eci, mdai, mvai;
-    int32_t adapt, arith, relax, pad_;
+    int32_t adapt, arith, relax, flags;
     uint64_t samples;
 };
 
@@ -650,7 +654,7 @@ CkptHeader ckpt_header(const jmm_handle *h) {
     k.cb_cur = 0; k.hist = h->H.ucount ? 1 : 0; k.gns = h->H.gns; k.rhonb = h->H.rhonb; k.gnb = h->H.gnb;
     k.rbw = h->H.rbw; k.gsw = h->H.gsw; k.gbw = h->H.gbw;
     k.cutoff = h->cfg.cutoff; k.eci = h->cfg.eci; k.mdai = h->cfg.mdai; k.mvai = h->cfg.mvai;
-    k.adapt = h->cfg.adapt; k.arith = h->cfg.arith; k.relax = h->cfg.relax; k.pad_ = 0; k.samples = h->samples;
+    k.adapt = h->cfg.adapt; k.arith = h->cfg.arith; k.relax = h->cfg.relax; k.flags = h->cfg.flags; k.samples = h->samples;
     return k;
 }
 }  // namespace
@@ -694,10 +698,10 @@ extern "C" jmm_status jmm_checkpoint_load(jmm_handle *h, const char *path) {
                                      "(N, nchains, mode, pot, NBN, ensemble, generator, seed or chain_id0)");
     }
     if (memcmp(&k.cutoff, &me.cutoff, sizeof(double)) != 0 || k.eci != me.eci || k.mdai != me.mdai || k.mvai != me.mvai ||
-        k.adapt != me.adapt || k.arith != me.arith || k.relax != me.relax) {
+        k.adapt != me.adapt || k.arith != me.arith || k.relax != me.relax || k.flags != me.flags) {
         fclose(f);
         return fail(JMM_ERR_INVALID, "checkpoint was written by a handle with a different cadence or arithmetic "
-                                     "(cutoff, ENGCHECK, DADJ, VADJ, adapt, arith or RELAX): the continuation would not be exact");
+                                     "(cutoff, ENGCHECK, DADJ, VADJ, adapt, arith, flags or RELAX): the continuation would not be exact");
     }
     if (k.hist != me.hist || (k.hist && (k.rhonb != me.rhonb || k.gnb != me.gnb || k.gns != me.gns || k.rbw != me.rbw ||
                                          k.gsw != me.gsw || k.gbw != me.gbw))) {

@@ -109,16 +109,26 @@ __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
     s6 = 0; s12 = 0;
     if constexpr (NPL > 0) {
+        double a[NPL], b[NPL];
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
             const uint32_t p = c.lane + G * i;
             const double r = c.r[p];
             if constexpr (POT == kPotLJcut) {
                 const bool left = p < nm;
-                lj_partner<true>(left ? rnm - r : r - rnm, left ? rT - r : r - rT, c.cutoff, s6, s12);
-            } else {
-                lj_partner<false>(r - rnm, r - rT, c.cutoff, s6, s12);
-            }
+                a[i] = left ? rnm - r : r - rnm; b[i] = left ? rT - r : r - rT;
+            } else { a[i] = r - rnm; b[i] = r - rT; }
+        }
+        constexpr int H = NPL > 10 ? NPL / 2 : NPL;           // at most ten chains in flight (registers)
+        if constexpr (H == NPL) lj_partners<POT == kPotLJcut, NPL>(a, b, c.cutoff, s6, s12);
+        else {
+            double a1[H], b1[H], a2[NPL - H], b2[NPL - H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) { a1[i] = a[i]; b1[i] = b[i]; }
+#pragma unroll
+            for (int i = H; i < NPL; ++i) { a2[i - H] = a[i]; b2[i - H] = b[i]; }
+            lj_partners<POT == kPotLJcut, H>(a1, b1, c.cutoff, s6, s12);
+            lj_partners<POT == kPotLJcut, NPL - H>(a2, b2, c.cutoff, s6, s12);
         }
     } else {
         const uint32_t N = c.N;
@@ -165,6 +175,7 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
     c.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     c.chain_of_bonds = false;
     c.lean = true;
+    c.consistent_virial = (S.flags & 1) != 0;
     c.r = row;
     c.sc = row + npad;
     c.N = (uint32_t) S.N; c.nbn = S.nbn; c.cutoff = S.cutoff;
