@@ -121,7 +121,7 @@ __device__ __forceinline__ void b2_load(B2Chain &c, const ChainsDev &S, uint64_t
     for (uint32_t i = lane; i < c.N; i += kB2G) row[i] = S.r[(uint64_t) i * C + chain];
 }
 
-__device__ __forceinline__ void b2_store(const B2Chain &c, const ChainsDev &S, uint64_t chain) {
+__device__ __forceinline__ void b2_store(const B2Chain &c, const ChainsDev &S, uint64_t chain, bool with_acc = true) {
     const uint64_t C = S.nchains;
     for (uint32_t i = c.lane; i < c.N; i += kB2G) S.r[(uint64_t) i * C + chain] = c.r[i];
     if (c.lane == 0) {
@@ -130,8 +130,10 @@ __device__ __forceinline__ void b2_store(const B2Chain &c, const ChainsDev &S, u
         for (int k = 0; k < 2; ++k) S.tot[k * C + chain] = c.tot[k];
 #pragma unroll
         for (int k = 2; k < kNTot; ++k) S.tot[k * C + chain] = 0.0;
+        if (with_acc) {
 #pragma unroll
-        for (int k = 0; k < kNAcc; ++k) S.acc[k * C + chain] = c.acc[k];
+            for (int k = 0; k < kNAcc; ++k) S.acc[k * C + chain] = c.acc[k];
+        }
 #pragma unroll
         for (int k = 0; k < kNCnt; ++k) S.cnt[k * C + chain] = c.cnt[k];
         S.vAErr[chain] = c.vAErr; S.echeck[chain] = c.echecks; S.echeck[C + chain] = c.discrepancies;
@@ -235,6 +237,193 @@ __global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs 
     }
     __syncwarp(gmask);
     b2_store(A, S, chainA);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_chains_step_bond2 — the same chains, but the step loop is built around the LATENCY of one step, which is what
+// bounds a launch of 4096 serial Markov chains (k_chains_step_bond: 1825 cycles per step, 346 warp instructions, the
+// fp64 pipe 37 % busy, profiles/r02p_c2_*):
+//   * Positions live in REGISTERS: lane q of the chain's 16 lanes holds r[q] and copies of r[q-1], r[q+1].  Every lane
+//     evaluates the trial "my particle moves by md" with the common md; the lane that owns particle nm has the real
+//     one, and its decision reaches the others through one ballot.  No shared memory, no rendezvous, no position
+//     shuffles on the critical path; the neighbours of nm update their copies with the same r + md (same operands,
+//     same double).
+//   * The energy check of step t (:1965-2095: fresh bond energies, a butterfly sum, a comparison that never fires) and
+//     the updateThermo of step t (:1941-1961) are RESOLVED DURING STEP t+1, after the trial of t+1 has been issued and
+//     before it is committed — so E, Vir, l and the positions are still those of step t, an "Energy discrepancy" reset
+//     would be taken on exactly the state the reference takes it on, and the butterfly's latency hides behind the
+//     trial's.  The twelve sums are spread over the lanes (ThermoLanes, coop.cuh): 4 instead of 19 fp64 instructions
+//     per step, same products, same order of addition.
+//   * The random numbers of step t+1 are shuffled out of the Philox batch during step t.
+//   * Volume trials (fav, one step in eleven), adjustments and an ECheck that fires go through coop.cuh's functions:
+//     the positions are parked in the chain's shared-memory row for the duration and read back afterwards.
+// Arithmetic and order of operations are those of k_chains_step_bond / coop.cuh: bit-identical to the oracle.
+template <bool INF>
+__device__ __forceinline__ double b2_bond_energy(double d, double cutoff) {     // phi_energy<HARMONIC>, selects only
+    const double rijm = d - 1.0;
+    return (d > 0) ? ((INF || d < cutoff) ? rijm * rijm : 0.0) : 10E10;
+}
+
+template <bool LOG, bool INF>
+__global__ void __launch_bounds__(128) k_chains_step_bond2(ChainsDev S, StepArgs a, int npad) {
+    extern __shared__ double smem[];
+    const uint32_t gib = threadIdx.x / kB2G, lane = threadIdx.x % kB2G;
+    const uint64_t chain = (uint64_t) blockIdx.x * (blockDim.x / kB2G) + gib;
+    const uint64_t C = S.nchains;
+    if (chain >= C) return;
+    const uint32_t gbase = (threadIdx.x & 31) / kB2G * kB2G;
+    const uint32_t gmask = 0xffffu << gbase;
+    B2Chain c;
+    double *row = smem + (size_t) gib * npad;
+    b2_load(c, S, chain, row, lane, gmask);
+    ThermoLanes<kB2G> th;
+    th.init(row + ((S.N + 1) & ~1ull), lane, S.acc, C, chain);
+    __syncwarp(gmask);
+    const uint32_t N = (uint32_t) S.N;
+    const bool hasL = lane > 0 && lane < N, hasR = lane + 1 < N, bond = lane + 1 < N;
+    double r = 0, rprev = 0, rnext = 0;                       // my particle and copies of its neighbours
+    auto fetch = [&]() {
+        r = row[lane < N ? lane : 0];
+        rprev = row[hasL ? lane - 1 : 0];
+        rnext = row[hasR ? lane + 1 : 0];
+    };
+    auto park = [&]() {                                        // positions -> shared row (for coop.cuh's functions)
+        if (lane < N) row[lane] = r;
+        __syncwarp(gmask);
+    };
+    fetch();
+
+    const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32);
+    const uint32_t cid = (uint32_t)(S.chain_id0 + chain);
+    const uint32_t ntt = (uint32_t) S.numTrialTypes, scale = 0xffffffffu / ntt;
+    uint64_t sn = a.sn0;
+    auto until_event = [&]() -> uint32_t {                    // steps until an adjustment is due (the ECheck has its own cadence)
+        uint64_t left = 0xffffffffull;
+        if (a.adapt_device) {
+            if (a.mdai) left = min(left, a.mdai - sn % a.mdai);
+            if (a.mvai) left = min(left, a.mvai - sn % a.mvai);
+        }
+        return (uint32_t) left;
+    };
+    uint32_t ev_left = until_event();
+    const bool check_every_step = a.eci == 1;
+    const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
+    uint32_t eci_left = a.eci ? (uint32_t) min((uint64_t) 0xffffffffull, a.eci - sn % a.eci) : 0xffffffffu;
+
+    uint32_t my_nm = 0, my_w1 = 0, my_w2 = 0;                 // this lane's share of the Philox batch
+    uint32_t batch_pos = kB2G;
+    auto draw = [&](uint64_t step, uint32_t &nm_o, uint32_t &w1_o, uint32_t &w2_o) {
+        if (batch_pos == kB2G) {                              // lane j draws the block of step `step` + j
+            const uint64_t mine = step + lane;
+            const Philox4 b = philox4x32_10((uint32_t) mine, (uint32_t)(mine >> 32), cid, kTagTrial, k0, k1);
+            uint32_t k = b.w[0] / scale;
+            if (k >= ntt) k = b2_redraw(b.w[3], scale, ntt);  // probability ~ ntt / 2^32
+            my_nm = k; my_w1 = b.w[1]; my_w2 = b.w[2];
+            batch_pos = 0;
+        }
+        nm_o = __shfl_sync(gmask, my_nm, batch_pos, kB2G);
+        w1_o = __shfl_sync(gmask, my_w1, batch_pos, kB2G);
+        w2_o = __shfl_sync(gmask, my_w2, batch_pos, kB2G);
+        ++batch_pos;
+    };
+
+    // what the previous step left to be resolved: its energy check (etest = the butterfly sum issued then) and its
+    // updateThermo
+    bool pend_check = false, pend_thermo = false;
+    double etest = 0.0;
+    auto resolve = [&]() {                                     // state = the previous step's: exactly where the reference checks
+        if (pend_check) {
+            c.echecks++;
+            if (fabs(etest - c.tot[0]) > 0.0001) {             // never in practice: decide again on the reference-order sum
+                c.echecks--;
+                park();
+                coop_energy_check(c);
+            }
+            pend_check = false;
+        }
+        if (pend_thermo) {
+            th.push(c);
+            if (th.fill == kThermoRing) th.flush(c);
+            pend_thermo = false;
+        }
+    };
+
+    uint32_t nm, w1, w2;
+    draw(sn + 1, nm, w1, w2);
+    for (uint32_t s = 0; s < (uint32_t) a.nsteps; ++s) {
+        ++sn;
+        const bool more = s + 1 < (uint32_t) a.nsteps;
+        uint32_t nm1 = 0, w11 = 0, w21 = 0;
+        if (more) draw(sn + 1, nm1, w11, w21);
+
+        uint8_t flags;
+        if (nm < N) {                                          // qad2 :1160-1464, NBN == 1
+            const double md = u01_shifted(w1, 1.5) * 2 * c.maxStep;           // (rn - 0.5) * 2 * maxStep, :1182
+            const double ran = u01_shifted(w2, 1.0);
+            const double rT = r + md;                                          // "my particle moves"
+            const bool wall = fabs(rT) > c.half_l;                             // :1188
+            double po0, po1, pn0, pn1, qo0, qo1, qn0, qn1;
+            b2_phi<INF>(r - rprev, c.cutoff, c.two_over_l, po0, po1);
+            b2_phi<INF>(rT - rprev, c.cutoff, c.two_over_l, pn0, pn1);
+            b2_phi<INF>(rnext - r, c.cutoff, c.two_over_l, qo0, qo1);
+            b2_phi<INF>(rnext - rT, c.cutoff, c.two_over_l, qn0, qn1);
+            const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0, l1 = hasL ? (0.0 - po1 + pn1) : 0.0;   // :1244
+            const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;   // :1339
+            const double dE_own = l0 + r0, dV_own = l1 + r1;                                         // :1354
+            const double ea = (double) exp_neg_approx(dE_own * c.invT);
+            const bool down = dE_own <= 0;
+            const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+            bool accept = down | acc_b;
+            const uint32_t bit = 1u << (gbase + nm);
+            const bool undecided = !(down | acc_b | rej_b) && !wall;
+            if (__ballot_sync(gmask, undecided) & bit) accept = metropolis_exact(dE_own, c.T, ran);    // 2e-5 of the trials
+            const bool ok = (__ballot_sync(gmask, accept && !wall) & bit) != 0;
+            // the owner's deltas for the replicated totals (off the critical path of the next trial)
+            const double dE = __shfl_sync(gmask, dE_own, nm, kB2G), dV = __shfl_sync(gmask, dV_own, nm, kB2G);
+            resolve();                                         // step t-1's check and thermo, on step t-1's state
+            c.cnt[0] += ok ? 1 : 0;
+            c.cnt[1] += ok ? 0 : 1;
+            c.tot[0] = ok ? c.tot[0] + dE : c.tot[0];
+            c.tot[1] = ok ? c.tot[1] + dV : c.tot[1];
+            if (ok) {
+                if (lane == nm) r = rT;
+                if (lane + 1 == nm) rnext = rnext + md;        // the same r[nm] + md
+                if (lane == nm + 1) rprev = rprev + md;
+            }
+            if constexpr (LOG) {
+                const bool wall_nm = (__ballot_sync(gmask, wall) & bit) != 0;
+                flags = wall_nm ? kLogWall : (ok ? kLogAccepted : 0);
+            } else flags = 0;
+        } else {                                               // fav :2161-2293 through coop.cuh on the parked positions
+            resolve();
+            th.flush(c);                                       // (fav's ordered sums do not touch the ring, but keep it simple)
+            park();
+            flags = coop_volume_full(c, u01(w1), u01(w2));
+            __syncwarp(gmask);
+            fetch();
+        }
+        // this step's energy check: fresh bond energies + butterfly now, comparison during the next step
+        pend_check = check_every_step;
+        if (!check_every_step && --eci_left == 0) { pend_check = true; eci_left = eci32; }
+        if (pend_check) {
+            etest = bond ? b2_bond_energy<INF>(rnext - r, c.cutoff) : 0.0;
+#pragma unroll
+            for (int o = kB2G / 2; o > 0; o >>= 1) etest += __shfl_xor_sync(gmask, etest, o, kB2G);
+        }
+        pend_thermo = true;
+        if (LOG && lane == 0) a.accept_log[(uint64_t) s * C + chain] = flags;
+        if (--ev_left == 0) {                                  // maxDisAdjust / maxDVAdjust (src/Main.cpp:145-165): after the thermo
+            resolve();
+            b2_adapt(c, a, a.mdai && sn % a.mdai == 0, a.mvai && sn % a.mvai == 0);
+            ev_left = until_event();
+        }
+        nm = nm1; w1 = w11; w2 = w21;
+    }
+    resolve();
+    th.flush(c);
+    th.store(lane, S.acc, C, chain);
+    park();
+    b2_store(c, S, chain, false);
 }
 
 

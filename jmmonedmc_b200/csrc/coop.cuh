@@ -554,4 +554,71 @@ __global__ void __launch_bounds__(128) k_chains_step_coop(ChainsDev S, StepArgs 
     }
 }
 
+// updateThermo :1941-1961 without twelve replicated accumulators.  Every lane of a group knows rho, l, E, Vir, HV of the
+// step, and replicated sums would cost 19 fp64 instructions per step and 24 registers in EVERY lane.  Instead the
+// five numbers of each step go into a small ring in shared memory (one lane writes), and every kThermoRing steps the
+// twelve sums — SPREAD over the lanes: lane k owns acc[k], acc[k+G], ... — are brought up to date: lane k reads its
+// operand pair (a, b) of every buffered step and does acc += a * b in step order (b = 1.0 for the linear terms: a * 1.0
+// is exact).  Same products, same order of addition per sum: the twelve sums stay bit-identical to the reference's.
+constexpr int kThermoRing = 8;                   // steps buffered
+constexpr int kThermoSlots = 6;                  // rho, l, E, Vir, HV, 1.0
+template <int G> struct ThermoLanes {
+    static constexpr int M = (kNAcc + G - 1) / G;
+    double acc[M];
+    uint32_t ia[M], ib[M];                        // operand slots of this lane's sums (byte offsets would save nothing)
+    double *ring;                                 // [kThermoRing][kThermoSlots] doubles of this group
+    uint32_t fill;
+    // sums in JMM_A_* order: rho, rho^2, l, l^2, E, E^2, l E, Vir, Vir^2, E Vir, HV, HV^2
+    static __device__ __forceinline__ void operands(uint32_t k, uint32_t &a, uint32_t &b) {
+        const uint32_t A[12] = {0, 0, 1, 1, 2, 2, 1, 3, 3, 2, 4, 4};
+        const uint32_t B[12] = {5, 0, 5, 1, 5, 2, 2, 5, 3, 3, 5, 4};
+        a = A[k < 12 ? k : 0]; b = B[k < 12 ? k : 0];
+    }
+    __device__ __forceinline__ void init(double *ring_, uint32_t lane, const double *acc_g, uint64_t C, uint64_t chain) {
+        ring = ring_; fill = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t k = lane + m * G;
+            operands(k, ia[m], ib[m]);
+            acc[m] = k < kNAcc ? __ldcg(acc_g + (uint64_t) k * C + chain) : 0.0;
+        }
+    }
+    template <int POT>
+    __device__ __forceinline__ void push(const Coop<POT, G> &c) {                 // one step's numbers (any one lane writes)
+        if (c.lane == 0) {
+            double *e = ring + fill * kThermoSlots;
+            e[0] = c.rho; e[1] = c.l; e[2] = c.tot[0]; e[3] = c.tot[1];
+            e[4] = PotTraits<POT>::NC > 6 ? c.tot[6] : 0.0;
+            e[5] = 1.0;
+        }
+        ++fill;
+    }
+    template <int POT>
+    __device__ __forceinline__ void flush(const Coop<POT, G> &c) {                // bring the sums up to date
+        c.sync();
+        if (fill == kThermoRing) {
+#pragma unroll
+            for (int e = 0; e < kThermoRing; ++e) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
+            }
+        } else {
+            for (uint32_t e = 0; e < fill; ++e) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
+            }
+        }
+        fill = 0;
+        c.sync();
+    }
+    __device__ __forceinline__ void store(uint32_t lane, double *acc_g, uint64_t C, uint64_t chain) const {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t k = lane + m * G;
+            if (k < kNAcc) acc_g[(uint64_t) k * C + chain] = acc[m];
+        }
+    }
+};
+
+
 }  // namespace jmm

@@ -27,7 +27,7 @@ struct jmm_handle {
     // many-chain launch shape
     int block = 32, pos_in_smem = 1;
     size_t smem = 0;
-    int bond = 0;                   // bond.cuh serves this handle (HARMONIC, NBN 1, N <= 17, no RELAX)
+    int bond = 0;                   // bond.cuh serves this handle (HARMONIC, NBN 1, N <= 17, no RELAX): 1 = k_chains_step_bond, 2 = ..._bond2
     int coop_g = 0;                 // lanes per chain of the cooperative kernel (0 = one chain per thread)
     int coop_npad = 0;
     size_t coop_smem = 0;

@@ -322,7 +322,7 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
             const char *eb = getenv("JMM_BOND");
             if (h->coop_g && cfg->pot == JMM_POT_HARMONIC && cfg->nbn == 1 && N - 1 <= 16 && !(h->cfg.relax > 0) &&
                 C <= 16384 && !(eb && atoi(eb) == 0))
-                h->bond = 1;
+                h->bond = (eb && atoi(eb) == 1) ? 1 : 2;         // 2 = k_chains_step_bond2 (registers-only, deferred ECheck); JMM_BOND=1: the first kernel
         }
     }
     CKH(cudaStreamSynchronize(h->stream));

@@ -33,72 +33,6 @@ namespace jmm {
 #endif
 constexpr int kLanesMaxWarps = JMM_LANES_MAXW;   // 12 warps per CTA = 168 registers per thread (16 = 128: spills)
 
-// updateThermo :1941-1961 without twelve replicated accumulators.  Every lane of a group knows rho, l, E, Vir, HV of the
-// step, and replicated sums would cost 19 fp64 instructions per step and 24 registers in EVERY lane.  Instead the
-// five numbers of each step go into a small ring in shared memory (one lane writes), and every kThermoRing steps the
-// twelve sums — SPREAD over the lanes: lane k owns acc[k], acc[k+G], ... — are brought up to date: lane k reads its
-// operand pair (a, b) of every buffered step and does acc += a * b in step order (b = 1.0 for the linear terms: a * 1.0
-// is exact).  Same products, same order of addition per sum: the twelve sums stay bit-identical to the reference's.
-constexpr int kThermoRing = 8;                   // steps buffered
-constexpr int kThermoSlots = 6;                  // rho, l, E, Vir, HV, 1.0
-template <int G> struct ThermoLanes {
-    static constexpr int M = (kNAcc + G - 1) / G;
-    double acc[M];
-    uint32_t ia[M], ib[M];                        // operand slots of this lane's sums (byte offsets would save nothing)
-    double *ring;                                 // [kThermoRing][kThermoSlots] doubles of this group
-    uint32_t fill;
-    // sums in JMM_A_* order: rho, rho^2, l, l^2, E, E^2, l E, Vir, Vir^2, E Vir, HV, HV^2
-    static __device__ __forceinline__ void operands(uint32_t k, uint32_t &a, uint32_t &b) {
-        const uint32_t A[12] = {0, 0, 1, 1, 2, 2, 1, 3, 3, 2, 4, 4};
-        const uint32_t B[12] = {5, 0, 5, 1, 5, 2, 2, 5, 3, 3, 5, 4};
-        a = A[k < 12 ? k : 0]; b = B[k < 12 ? k : 0];
-    }
-    __device__ __forceinline__ void init(double *ring_, uint32_t lane, const double *acc_g, uint64_t C, uint64_t chain) {
-        ring = ring_; fill = 0;
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const uint32_t k = lane + m * G;
-            operands(k, ia[m], ib[m]);
-            acc[m] = k < kNAcc ? __ldcg(acc_g + (uint64_t) k * C + chain) : 0.0;
-        }
-    }
-    template <int POT>
-    __device__ __forceinline__ void push(const Coop<POT, G> &c) {                 // one step's numbers (any one lane writes)
-        if (c.lane == 0) {
-            double *e = ring + fill * kThermoSlots;
-            e[0] = c.rho; e[1] = c.l; e[2] = c.tot[0]; e[3] = c.tot[1];
-            e[4] = PotTraits<POT>::NC > 6 ? c.tot[6] : 0.0;
-            e[5] = 1.0;
-        }
-        ++fill;
-    }
-    template <int POT>
-    __device__ __forceinline__ void flush(const Coop<POT, G> &c) {                // bring the sums up to date
-        c.sync();
-        if (fill == kThermoRing) {
-#pragma unroll
-            for (int e = 0; e < kThermoRing; ++e) {
-#pragma unroll
-                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
-            }
-        } else {
-            for (uint32_t e = 0; e < fill; ++e) {
-#pragma unroll
-                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
-            }
-        }
-        fill = 0;
-        c.sync();
-    }
-    __device__ __forceinline__ void store(uint32_t lane, double *acc_g, uint64_t C, uint64_t chain) const {
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const uint32_t k = lane + m * G;
-            if (k < kNAcc) acc_g[(uint64_t) k * C + chain] = acc[m];
-        }
-    }
-};
-
 // The partner sums of one displacement trial: s6 = sum(b^-6 - a^-6), s12 = sum(b^-12 - a^-12) over the partners of
 // `nm`, strided over the G lanes and closed by an xor butterfly (identical bits in every lane of the group).
 // The slot of the moved particle holds kFarAway while this runs (see lanes_run_chain), so there is no per-partner
@@ -145,11 +79,19 @@ __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32
             }
         }
     }
+    // Two sums over the G lanes with one value per lane after the first exchange: even lanes carry s12, odd lanes s6
+    // (G + 2 log2 G... shuffles of one double instead of two per round).  Commutative additions: every lane of the group
+    // ends up with the same bits.  Full-warp mask: the step loop keeps the warp converged here (lanes_run_chain).
+    if constexpr (G == 1) return;
+    __syncwarp();                                 // (run-time partner bounds: the groups may have left the loop apart)
+    const bool odd = c.lane & 1;
+    const double give = odd ? s12 : s6, keep = odd ? s6 : s12;
+    double v = keep + __shfl_xor_sync(0xffffffffu, give, 1, G);
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {         // commutative additions: the same bits in every lane of the group
-        s6 += __shfl_xor_sync(c.gmask, s6, o, G);
-        s12 += __shfl_xor_sync(c.gmask, s12, o, G);
-    }
+    for (int o = 2; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    const double other = __shfl_xor_sync(0xffffffffu, v, 1, G);
+    s12 = odd ? other : v;
+    s6 = odd ? v : other;
 }
 
 // One chain (the G lanes of its group) advanced by `count` steps starting after step sn0.
@@ -166,7 +108,7 @@ __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32
 //   * the four interval countdowns (ECheck, the two adjustments, relaxVolume) are one counter; a step on which any
 //     of them is due takes the slow path, which first makes the positions consistent again.
 template <int POT, int G, int NPL, bool LOG>
-__device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepArgs &a, uint64_t chain, double *row, uint32_t npad,
+__device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepArgs &a, uint64_t chain, bool own, double *row, uint32_t npad,
                                                 uint64_t sn0, uint32_t count, uint64_t log_row0) {
     constexpr int NC = PotTraits<POT>::NC;
     const uint64_t C = S.nchains;
@@ -223,9 +165,9 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
             my_nm = k; my_w1 = b.w[1]; my_w2 = b.w[2];
             batch_pos = 0;
         }
-        nm_o = __shfl_sync(c.gmask, my_nm, batch_pos, G);
-        w1_o = __shfl_sync(c.gmask, my_w1, batch_pos, G);
-        w2_o = __shfl_sync(c.gmask, my_w2, batch_pos, G);
+        nm_o = __shfl_sync(0xffffffffu, my_nm, batch_pos, G);
+        w1_o = __shfl_sync(0xffffffffu, my_w1, batch_pos, G);
+        w2_o = __shfl_sync(0xffffffffu, my_w2, batch_pos, G);
         ++batch_pos;
     };
     // lane 0: [write `val` to r[nm_w]] [read r[nm_r], leave the sentinel there]; everyone gets that position
@@ -235,60 +177,65 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
             if (wr) c.r[nm_w] = val;
             if (rd) { got = c.r[nm_r]; c.r[nm_r] = kFarAway; }
         }
-        got = __shfl_sync(c.gmask, got, 0, G);
-        c.sync();
+        got = __shfl_sync(0xffffffffu, got, 0, G);
+        __syncwarp();
         return got;
     };
 
     uint32_t nm, w1, w2;
+    __syncwarp();
     draw(sn + 1, nm, w1, w2);
     bool disp = nm < c.N;
     double rnm = handover(false, 0, 0.0, disp, nm);
 
     for (uint32_t s = 0; s < count; ++s) {
         ++sn;
+        __syncwarp();
         const bool more = s + 1 < count;
         uint32_t nm1 = 0, w11 = 0, w21 = 0;
         if (more) draw(sn + 1, nm1, w11, w21);                // (uniform in the warp: every group runs `count` steps)
         const bool disp1 = more && nm1 < c.N;
 
-        uint8_t flags;
+        // The whole warp runs the displacement code CONVERGED (full-mask shuffles: a per-group mask costs a MATCH + REDUX +
+        // VOTE per shuffle): a group whose trial is a volume trial computes a discarded dummy, a move through the wall is
+        // a predicate on the decision (:1188), not a branch around the pair terms.
+        uint8_t flags = 0;
         bool acc = false;
-        double rT = 0.0;
-        if (disp) {                                           // qad2 :1160-1464
+        double rT;
+        {                                                     // qad2 :1160-1464
             const double md = u01_shifted(w1, 1.5) * 2 * c.maxStep;     // (rn - 0.5) * 2 * maxStep, :1182
             rT = rnm + md;
             const bool wall = fabs(rT) > c.half_l;            // :1188
-            flags = wall ? kLogWall : 0;
-            if (!wall) {
-                double s6, s12;
-                lanes_partner_sums<POT, G, NPL>(c, nm, rnm, rT, s6, s12);
-                const double dE12 = 4 * s12, dE6 = 4 * s6;
-                const double dE = dE12 - dE6;
-                // Metropolis rule :1367-1377 through the band of metropolis_accept(), without early-out branches
-                const double ran = u01_shifted(w2, 1.0);
-                const double ea = (double) exp_neg_approx(dE * c.invT);
-                const bool down = dE <= 0;
-                const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
-                acc = down | acc_b;
-                if (!(down | acc_b | rej_b)) acc = metropolis_exact(dE, c.T, ran);
-                if (acc) {
-                    const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
-                    c.tot[0] += dE;  c.tot[2] += dE12; c.tot[4] += dE6;
-                    c.tot[1] += dV12 - dV6; c.tot[3] += dV12; c.tot[5] += dV6;
-                    c.tot[6] += dH12 - dH6; c.tot[7] += dH12; c.tot[8] += dH6;
-                    flags = kLogAccepted;
-                }
+            double s6, s12;
+            lanes_partner_sums<POT, G, NPL>(c, disp ? nm : 0u, rnm, rT, s6, s12);
+            const double dE12 = 4 * s12, dE6 = 4 * s6;
+            const double dE = dE12 - dE6;
+            // Metropolis rule :1367-1377 through the band of metropolis_accept(), without early-out branches
+            const double ran = u01_shifted(w2, 1.0);
+            const double ea = (double) exp_neg_approx(dE * c.invT);
+            const bool down = dE <= 0;
+            const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+            acc = down | acc_b;
+            if (disp && !wall && !(down | acc_b | rej_b)) acc = metropolis_exact(dE, c.T, ran);
+            acc = acc && disp && !wall;
+            if (acc) {
+                const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
+                c.tot[0] += dE;  c.tot[2] += dE12; c.tot[4] += dE6;
+                c.tot[1] += dV12 - dV6; c.tot[3] += dV12; c.tot[5] += dV6;
+                c.tot[6] += dH12 - dH6; c.tot[7] += dH12; c.tot[8] += dH6;
             }
+            if (LOG) flags = (disp && wall) ? kLogWall : (acc ? kLogAccepted : 0);
             c.cnt[0] += acc ? 1 : 0;
-            c.cnt[1] += acc ? 0 : 1;
-        } else {                                              // volume trial: no sentinel is out, the row is consistent
+            c.cnt[1] += (disp && !acc) ? 1 : 0;
+        }
+        if (!disp) {                                          // volume trial: no sentinel is out, the row is consistent
             const double rn = u01(w1), ran = u01(w2);
             th.flush(c);                                      // (fav's ordered sums use the scratch next to the ring; rare anyway)
             if constexpr (POT == kPotLJ) {
                 flags = scaling_volume ? coop_volume_scaling(c, rn, ran) : coop_volume_full(c, rn, ran);
             } else flags = coop_volume_full(c, rn, ran);
         }
+        __syncwarp();                                         // converged again
 
         double rnm1;
         if (--ev_left != 0) {
@@ -308,11 +255,12 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
             ev_left = until_event();
             rnm1 = handover(false, 0, 0.0, disp1, nm1);
         }
-        if (LOG && c.lane == 0) a.accept_log[(log_row0 + s) * C + chain] = flags;
+        if (LOG && own && c.lane == 0) a.accept_log[(log_row0 + s) * C + chain] = flags;
         nm = nm1; w1 = w11; w2 = w21; rnm = rnm1; disp = disp1;
     }
 
     th.flush(c);
+    if (!own) return;                                         // a surplus group of a ragged last tile shadows the last chain
     th.store(c.lane, S.acc, C, chain);
     for (uint32_t i = c.lane; i < c.N; i += G) S.r[(uint64_t) i * C + chain] = row[i];
     if (c.lane == 0) {
@@ -354,7 +302,8 @@ __global__ void __launch_bounds__(kLanesMaxWarps * 32, 1) k_chains_step_lanes(Ch
         const uint64_t chain = (uint64_t) tile * CPW + lane / G;
         const uint32_t s0 = k * chunk;
         const uint32_t count = min(chunk, (uint32_t) a.nsteps - s0);
-        if (chain < S.nchains) lanes_run_chain<POT, G, NPL, LOG>(S, a, chain, row, npad, a.sn0 + s0, count, s0);
+        const bool own = chain < S.nchains;
+        lanes_run_chain<POT, G, NPL, LOG>(S, a, own ? chain : S.nchains - 1, own, row, npad, a.sn0 + s0, count, s0);
         __threadfence();
         __syncwarp();
         if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(progress + tile), "r"(k + 1) : "memory");

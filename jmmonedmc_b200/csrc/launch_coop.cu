@@ -24,15 +24,25 @@ static cudaError_t launch_step_coop_g(jmm_handle *h, const StepArgs &a) {
 }
 
 static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
-    int npad = (int) h->S.N;
-    npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
     const bool inf = std::isinf(h->S.cutoff);
-    auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
-                             : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
     // threads per CTA: 128 (a warp per sub-partition); JMM_BOND_BLOCK = 32, 64 or 96 for wave-quantisation experiments
     unsigned threads = 128;
     if (const char *e = getenv("JMM_BOND_BLOCK")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) threads = (unsigned) v; }
     const unsigned per_block = threads / kB2G;
+    if (h->bond == 2) {
+        // k_chains_step_bond2: the shared row only parks the positions for the rare paths; the thermo ring follows it
+        int npad = (int) ((h->S.N + 1) & ~1ull) + kThermoRing * kThermoSlots;
+        npad += (npad & 1) ? 0 : 1;
+        auto kern = a.accept_log ? (inf ? k_chains_step_bond2<true, true> : k_chains_step_bond2<true, false>)
+                                 : (inf ? k_chains_step_bond2<false, true> : k_chains_step_bond2<false, false>);
+        kern<<<nblk(h->S.nchains, per_block), threads, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
+        h->launches++;
+        return cudaGetLastError();
+    }
+    int npad = (int) h->S.N;
+    npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
+    auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
+                             : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
     kern<<<nblk(h->S.nchains, per_block), threads, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
     h->launches++;
     return cudaGetLastError();

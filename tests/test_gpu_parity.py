@@ -140,6 +140,8 @@ def test_recorded_stream_exhaustion_is_an_error(J, O, gold):
 DECKS = {
     "std": dict(N=10, POT="HARMONIC", NBN=1, CUTOFF=math.inf, ENSEMBLE="NPT", P=0.7, T=0.4, MAXSTEP=0.1, MAXDV=1.0,
                 ENGCHECK=1, DADJ=100, VADJ=100, SEED=125, RELAX=0),
+    "std_cut": dict(N=13, POT="HARMONIC", NBN=1, CUTOFF=1.35, ENSEMBLE="NPT", P=0.4, T=0.6, MAXSTEP=0.2, MAXDV=1.5,
+                    ENGCHECK=7, DADJ=130, VADJ=90, SEED=31, RELAX=0),
     "small": dict(N=10, POT="LJ", NBN=-1, CUTOFF=math.inf, ENSEMBLE="NPT", P=1.0, T=0.9, MAXSTEP=0.1, MAXDV=0.1,
                   ENGCHECK=1000, DADJ=1000, VADJ=1000, SEED=92847, RELAX=1),
     "ljcut_nbn": dict(N=24, POT="LJcut", NBN=3, CUTOFF=2.5, ENSEMBLE="NPT", P=0.5, T=0.7, MAXSTEP=0.15, MAXDV=0.4,
@@ -151,7 +153,8 @@ DECKS = {
 
 ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gpu.cu: launch_step_table)
     "coop": {"JMM_COOP_G": "16", "JMM_BOND": "0"},     # coop.cuh, 16 lanes per chain
-    "bond": {"JMM_COOP_G": "16", "JMM_BOND": "1"},      # bond.cuh (HARMONIC NBN 1 decks; others fall to coop.cuh)
+    "bond": {"JMM_COOP_G": "16", "JMM_BOND": "1"},      # bond.cuh, k_chains_step_bond (HARMONIC NBN 1 decks; others fall to coop.cuh)
+    "bond2": {"JMM_COOP_G": "16", "JMM_BOND": "2"},     # bond.cuh, k_chains_step_bond2 (registers-only, deferred ECheck): the default
     "coop32": {"JMM_COOP_G": "32"},
     "coop8": {"JMM_COOP_G": "8"},
     "prod": {"JMM_COOP_G": "0"},                        # prod.cuh, one chain per thread, shared tile
@@ -161,7 +164,7 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
 
 
 @pytest.mark.parametrize("name", list(DECKS))
-@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
+@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-bond2", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
 def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
     """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
     every chain must equal the oracle bit for bit, including after adjustments and relaxations —
@@ -658,3 +661,37 @@ def test_checkpoint_restart_is_an_exact_continuation(J, O, case, tmp_path, monke
     with mk() as h:
         with pytest.raises(J.JmmError):
             h.checkpoint_load(tmp_path / "missing.jmmckpt")
+
+
+@pytest.mark.parametrize("engine", ["prod", "coop", "generic", "lanes8-fast"])
+def test_consistent_virial_flag_changes_only_the_virial_bookkeeping(J, O, engine, monkeypatch):
+    """JMM_FLAG_CONSISTENT_VIRIAL (include/jmm_gpu.h): the reference's accepted qavLJ move rescales Vir6/Vir12 by
+    (l'/l)^-7/-13, adds N T / l and never touches HV (src/jmmMCState.cpp:1675-1686), so its running virial is
+    path-dependent.  With the flag the running Vir and HV must equal the configuration sums (a fresh jmm_energy) at any
+    time, while positions, box, E, counters and the accept sequence are those of the default (reference-exact) run."""
+    env = {"prod": {"JMM_COOP_G": "0"}, "coop": {"JMM_COOP_G": "16"}, "generic": {"JMM_COOP_G": "0", "JMM_NO_PROD": "1"},
+           "lanes8": {"JMM_LANES_G": "8"}}[engine.split("-")[0]]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fast = engine.endswith("fast")
+    d = dict(DECKS["small"], N=24, MAXDV=0.4)
+    C, nsteps = 45, 3000
+    runs = {}
+    for flags in (0, J.FLAG_CONSISTENT_VIRIAL):
+        cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C, chain_id0=9,
+                                   flags=flags, arith=J.ARITH_FAST if fast else J.ARITH_REFERENCE)
+        with J.Handle(cfg) as h:
+            h.start()
+            log = h.step(nsteps, accept_log=True)
+            runs[flags] = (h.get_state(), log, h.energy(exact_order=True))
+    (s0, log0, fresh0), (s1, log1, fresh1) = runs[0], runs[J.FLAG_CONSISTENT_VIRIAL]
+    assert np.array_equal(log0, log1) and bits_equal(s0["r"], s1["r"]) and bits_equal(s0["l"], s1["l"])
+    assert np.array_equal(s0["counters"], s1["counters"]) and np.all(s0["counters"][:, 2] > 10)      # volume moves were accepted
+    for k in (0, 2, 4):                                                    # E, E12, E6: the same bookkeeping
+        assert bits_equal(s0["totals"][:, k], s1["totals"][:, k])
+    assert bits_equal(s0["accum"][:, :7], s1["accum"][:, :7])              # rho, rho^2, L, L^2, E, E^2, LE
+    assert totals_close(s1["totals"], fresh1, 1e-11), "with the flag every running total is the configuration sum"
+    # without it the reference's bookkeeping is reproduced: Vir carries N T / l and HV lags behind
+    assert not totals_close(s0["totals"], fresh0, 1e-6)
+    with pytest.raises(J.JmmError):
+        J.Handle(jmm_config_from_deck(J, d, rng_kind=J.RNG_TAUS2, mode=J.MODE_TABLE, flags=J.FLAG_CONSISTENT_VIRIAL))
