@@ -264,23 +264,27 @@ __device__ __forceinline__ double b2_bond_energy(double d, double cutoff) {     
     return (d > 0) ? ((INF || d < cutoff) ? rijm * rijm : 0.0) : 10E10;
 }
 
-template <bool LOG, bool INF>
-__global__ void __launch_bounds__(128) k_chains_step_bond2(ChainsDev S, StepArgs a, int npad) {
+template <bool LOG, bool INF, bool EVERY>          // EVERY: ENGCHECK 1 (the INPUTstd cadence): no check countdown at all
+__global__ void __launch_bounds__(128, 4) k_chains_step_bond2(ChainsDev S, StepArgs a, int npad) {
     extern __shared__ double smem[];
     const uint32_t gib = threadIdx.x / kB2G, lane = threadIdx.x % kB2G;
-    const uint64_t chain = (uint64_t) blockIdx.x * (blockDim.x / kB2G) + gib;
     const uint64_t C = S.nchains;
-    if (chain >= C) return;
+    uint64_t chain = (uint64_t) blockIdx.x * (blockDim.x / kB2G) + gib;
+    // The two chains of a warp run ONE converged instruction stream (full-mask votes and shuffles: a per-group mask
+    // costs a MATCH + REDUX + VOTE each); a surplus half-warp shadows the last chain and stores nothing.
+    const bool own = chain < C;
+    if (!own) chain = C - 1;
     const uint32_t gbase = (threadIdx.x & 31) / kB2G * kB2G;
     const uint32_t gmask = 0xffffu << gbase;
+    constexpr uint32_t FULL = 0xffffffffu;
     B2Chain c;
     double *row = smem + (size_t) gib * npad;
     b2_load(c, S, chain, row, lane, gmask);
     ThermoLanes<kB2G> th;
     th.init(row + ((S.N + 1) & ~1ull), lane, S.acc, C, chain);
-    __syncwarp(gmask);
+    __syncwarp();
     const uint32_t N = (uint32_t) S.N;
-    const bool hasL = lane > 0 && lane < N, hasR = lane + 1 < N, bond = lane + 1 < N;
+    const bool hasL = lane > 0 && lane < N, hasR = lane + 1 < N;
     double r = 0, rprev = 0, rnext = 0;                       // my particle and copies of its neighbours
     auto fetch = [&]() {
         r = row[lane < N ? lane : 0];
@@ -306,7 +310,6 @@ __global__ void __launch_bounds__(128) k_chains_step_bond2(ChainsDev S, StepArgs
         return (uint32_t) left;
     };
     uint32_t ev_left = until_event();
-    const bool check_every_step = a.eci == 1;
     const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
     uint32_t eci_left = a.eci ? (uint32_t) min((uint64_t) 0xffffffffull, a.eci - sn % a.eci) : 0xffffffffu;
 
@@ -321,30 +324,26 @@ __global__ void __launch_bounds__(128) k_chains_step_bond2(ChainsDev S, StepArgs
             my_nm = k; my_w1 = b.w[1]; my_w2 = b.w[2];
             batch_pos = 0;
         }
-        nm_o = __shfl_sync(gmask, my_nm, batch_pos, kB2G);
-        w1_o = __shfl_sync(gmask, my_w1, batch_pos, kB2G);
-        w2_o = __shfl_sync(gmask, my_w2, batch_pos, kB2G);
+        nm_o = __shfl_sync(FULL, my_nm, batch_pos, kB2G);
+        w1_o = __shfl_sync(FULL, my_w1, batch_pos, kB2G);
+        w2_o = __shfl_sync(FULL, my_w2, batch_pos, kB2G);
         ++batch_pos;
     };
 
     // what the previous step left to be resolved: its energy check (etest = the butterfly sum issued then) and its
-    // updateThermo
+    // updateThermo.  Called with the warp converged; the state is still the previous step's.
     bool pend_check = false, pend_thermo = false;
     double etest = 0.0;
-    auto resolve = [&]() {                                     // state = the previous step's: exactly where the reference checks
-        if (pend_check) {
-            c.echecks++;
-            if (fabs(etest - c.tot[0]) > 0.0001) {             // never in practice: decide again on the reference-order sum
-                c.echecks--;
-                park();
-                coop_energy_check(c);
-            }
-            pend_check = false;
+    auto resolve = [&]() {
+        const bool fire = pend_check && fabs(etest - c.tot[0]) > 0.0001;
+        c.echecks += pend_check ? 1 : 0;
+        if (__any_sync(FULL, fire)) {                          // never in practice: decide again on the reference-order sum
+            if (fire) { c.echecks--; park(); coop_energy_check(c); }
+            __syncwarp();
         }
-        if (pend_thermo) {
+        if (pend_thermo) {                                     // (uniform: false only before the first step of a launch)
             th.push(c);
             if (th.fill == kThermoRing) th.flush(c);
-            pend_thermo = false;
         }
     };
 
@@ -352,79 +351,88 @@ __global__ void __launch_bounds__(128) k_chains_step_bond2(ChainsDev S, StepArgs
     draw(sn + 1, nm, w1, w2);
     for (uint32_t s = 0; s < (uint32_t) a.nsteps; ++s) {
         ++sn;
+        __syncwarp();
         const bool more = s + 1 < (uint32_t) a.nsteps;
         uint32_t nm1 = 0, w11 = 0, w21 = 0;
         if (more) draw(sn + 1, nm1, w11, w21);
+        const bool disp = nm < N;
 
-        uint8_t flags;
-        if (nm < N) {                                          // qad2 :1160-1464, NBN == 1
-            const double md = u01_shifted(w1, 1.5) * 2 * c.maxStep;           // (rn - 0.5) * 2 * maxStep, :1182
-            const double ran = u01_shifted(w2, 1.0);
-            const double rT = r + md;                                          // "my particle moves"
-            const bool wall = fabs(rT) > c.half_l;                             // :1188
-            double po0, po1, pn0, pn1, qo0, qo1, qn0, qn1;
-            b2_phi<INF>(r - rprev, c.cutoff, c.two_over_l, po0, po1);
-            b2_phi<INF>(rT - rprev, c.cutoff, c.two_over_l, pn0, pn1);
-            b2_phi<INF>(rnext - r, c.cutoff, c.two_over_l, qo0, qo1);
-            b2_phi<INF>(rnext - rT, c.cutoff, c.two_over_l, qn0, qn1);
-            const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0, l1 = hasL ? (0.0 - po1 + pn1) : 0.0;   // :1244
-            const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;   // :1339
-            const double dE_own = l0 + r0, dV_own = l1 + r1;                                         // :1354
-            const double ea = (double) exp_neg_approx(dE_own * c.invT);
-            const bool down = dE_own <= 0;
-            const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
-            bool accept = down | acc_b;
-            const uint32_t bit = 1u << (gbase + nm);
-            const bool undecided = !(down | acc_b | rej_b) && !wall;
-            if (__ballot_sync(gmask, undecided) & bit) accept = metropolis_exact(dE_own, c.T, ran);    // 2e-5 of the trials
-            const bool ok = (__ballot_sync(gmask, accept && !wall) & bit) != 0;
-            // the owner's deltas for the replicated totals (off the critical path of the next trial)
-            const double dE = __shfl_sync(gmask, dE_own, nm, kB2G), dV = __shfl_sync(gmask, dV_own, nm, kB2G);
-            resolve();                                         // step t-1's check and thermo, on step t-1's state
-            c.cnt[0] += ok ? 1 : 0;
-            c.cnt[1] += ok ? 0 : 1;
-            c.tot[0] = ok ? c.tot[0] + dE : c.tot[0];
-            c.tot[1] = ok ? c.tot[1] + dV : c.tot[1];
-            if (ok) {
-                if (lane == nm) r = rT;
-                if (lane + 1 == nm) rnext = rnext + md;        // the same r[nm] + md
-                if (lane == nm + 1) rprev = rprev + md;
+        // qad2 :1160-1464, NBN == 1, for "my particle" — evaluated by every lane of both chains, a volume step included
+        // (its result is discarded): the warp stays converged
+        const double md = u01_shifted(w1, 1.5) * 2 * c.maxStep;               // (rn - 0.5) * 2 * maxStep, :1182
+        const double ran = u01_shifted(w2, 1.0);
+        const double rT = r + md;
+        const bool wall = fabs(rT) > c.half_l;                                 // :1188
+        double po0, po1, pn0, pn1, qo0, qo1, qn0, qn1;
+        b2_phi<INF>(r - rprev, c.cutoff, c.two_over_l, po0, po1);
+        b2_phi<INF>(rT - rprev, c.cutoff, c.two_over_l, pn0, pn1);
+        b2_phi<INF>(rnext - r, c.cutoff, c.two_over_l, qo0, qo1);
+        b2_phi<INF>(rnext - rT, c.cutoff, c.two_over_l, qn0, qn1);
+        const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0, l1 = hasL ? (0.0 - po1 + pn1) : 0.0;   // :1244
+        const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;   // :1339
+        const double dE_own = l0 + r0, dV_own = l1 + r1;                                         // :1354
+        const double ea = (double) exp_neg_approx(dE_own * c.invT);
+        const bool down = dE_own <= 0;
+        const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+        bool accept = down | acc_b;
+        const bool mine = disp && lane == nm;                  // this lane owns the moved particle
+        const bool undecided = mine && !(down | acc_b | rej_b) && !wall;
+        if (__any_sync(FULL, undecided)) {                     // 2e-5 of the trials
+            if (undecided) accept = metropolis_exact(dE_own, c.T, ran);
+            __syncwarp();
+        }
+        const uint32_t votes = __ballot_sync(FULL, mine && accept && !wall);
+        const bool ok = (votes & gmask) != 0;
+        // the owner's deltas for the replicated totals (off the critical path of the next trial)
+        const double dE = __shfl_sync(FULL, dE_own, disp ? nm : 0u, kB2G), dV = __shfl_sync(FULL, dV_own, disp ? nm : 0u, kB2G);
+        resolve();                                             // step t-1's check and thermo, on step t-1's state
+        c.cnt[0] += ok ? 1 : 0;
+        c.cnt[1] += (disp && !ok) ? 1 : 0;
+        c.tot[0] = ok ? c.tot[0] + dE : c.tot[0];
+        c.tot[1] = ok ? c.tot[1] + dV : c.tot[1];
+        r = (ok && lane == nm) ? rT : r;
+        rnext = (ok && lane + 1 == nm) ? rnext + md : rnext;   // the same r[nm] + md
+        rprev = (ok && lane == nm + 1) ? rprev + md : rprev;
+        uint8_t flags = 0;
+        if constexpr (LOG) {
+            const bool wall_nm = (__ballot_sync(FULL, mine && wall) & gmask) != 0;
+            flags = wall_nm ? kLogWall : (ok ? kLogAccepted : 0);
+        }
+        if (__any_sync(FULL, !disp)) {                         // a volume trial in at least one of the two chains
+            if (!disp) {                                       // fav :2161-2293 through coop.cuh on the parked positions
+                th.flush(c);
+                park();
+                flags = coop_volume_full(c, u01(w1), u01(w2));
+                __syncwarp(gmask);
+                fetch();
             }
-            if constexpr (LOG) {
-                const bool wall_nm = (__ballot_sync(gmask, wall) & bit) != 0;
-                flags = wall_nm ? kLogWall : (ok ? kLogAccepted : 0);
-            } else flags = 0;
-        } else {                                               // fav :2161-2293 through coop.cuh on the parked positions
-            resolve();
-            th.flush(c);                                       // (fav's ordered sums do not touch the ring, but keep it simple)
-            park();
-            flags = coop_volume_full(c, u01(w1), u01(w2));
-            __syncwarp(gmask);
-            fetch();
+            __syncwarp();
         }
         // this step's energy check: fresh bond energies + butterfly now, comparison during the next step
-        pend_check = check_every_step;
-        if (!check_every_step && --eci_left == 0) { pend_check = true; eci_left = eci32; }
-        if (pend_check) {
-            etest = bond ? b2_bond_energy<INF>(rnext - r, c.cutoff) : 0.0;
+        if constexpr (EVERY) pend_check = true;
+        else { pend_check = false; if (--eci_left == 0) { pend_check = true; eci_left = eci32; } }
+        if (EVERY || __any_sync(FULL, pend_check)) {
+            etest = hasR ? b2_bond_energy<INF>(rnext - r, c.cutoff) : 0.0;
 #pragma unroll
-            for (int o = kB2G / 2; o > 0; o >>= 1) etest += __shfl_xor_sync(gmask, etest, o, kB2G);
+            for (int o = kB2G / 2; o > 0; o >>= 1) etest += __shfl_xor_sync(FULL, etest, o, kB2G);
         }
         pend_thermo = true;
-        if (LOG && lane == 0) a.accept_log[(uint64_t) s * C + chain] = flags;
+        if (LOG && own && lane == 0) a.accept_log[(uint64_t) s * C + chain] = flags;
         if (--ev_left == 0) {                                  // maxDisAdjust / maxDVAdjust (src/Main.cpp:145-165): after the thermo
             resolve();
+            pend_check = false; pend_thermo = false;
             b2_adapt(c, a, a.mdai && sn % a.mdai == 0, a.mvai && sn % a.mvai == 0);
             ev_left = until_event();
         }
         nm = nm1; w1 = w11; w2 = w21;
     }
+    __syncwarp();
     resolve();
     th.flush(c);
+    if (!own) return;
     th.store(lane, S.acc, C, chain);
     park();
     b2_store(c, S, chain, false);
 }
-
 
 }  // namespace jmm

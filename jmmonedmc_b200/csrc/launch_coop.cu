@@ -33,8 +33,12 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
         // k_chains_step_bond2: the shared row only parks the positions for the rare paths; the thermo ring follows it
         int npad = (int) ((h->S.N + 1) & ~1ull) + kThermoRing * kThermoSlots;
         npad += (npad & 1) ? 0 : 1;
-        auto kern = a.accept_log ? (inf ? k_chains_step_bond2<true, true> : k_chains_step_bond2<true, false>)
-                                 : (inf ? k_chains_step_bond2<false, true> : k_chains_step_bond2<false, false>);
+        const bool every = a.eci == 1;
+        void (*kern)(ChainsDev, StepArgs, int);
+        if (a.accept_log) kern = inf ? (every ? k_chains_step_bond2<true, true, true> : k_chains_step_bond2<true, true, false>)
+                                     : (every ? k_chains_step_bond2<true, false, true> : k_chains_step_bond2<true, false, false>);
+        else kern = inf ? (every ? k_chains_step_bond2<false, true, true> : k_chains_step_bond2<false, true, false>)
+                        : (every ? k_chains_step_bond2<false, false, true> : k_chains_step_bond2<false, false, false>);
         kern<<<nblk(h->S.nchains, per_block), threads, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
         h->launches++;
         return cudaGetLastError();

@@ -4,9 +4,12 @@
 The checkerboard half-sweep of jmm_sweep (csrc/sweep.cuh) is a different Markov chain from the reference's
 one-random-particle-per-Step (src/jmmMCState.cpp:1758-1811); both must sample the same Boltzmann distribution.
 This script runs the COMPILED REFERENCE (oracle/_ref/jmmOneDMC_ref, OMP_NUM_THREADS=1) on a test/INPUT-style deck
-— NLT, N = 2000, LJcut 5.0, NBN 4, lattice spacing 1.12, T = 0.9: config C3's physics at a size the reference can
-allocate — 16 independent seeds x 400 sweeps (800 000 steps), one thermo row per sweep (TPI = N), and stores the
-per-sweep mean energies and the acceptance counters.  ~7 minutes per run; needs /root/reference.
+— NLT, LJcut 5.0, NBN 4, lattice spacing 1.12, T = 0.9: config C3's physics — at N = 64, 16 independent seeds x
+40 000 sweeps (2 560 000 steps), one thermo row per 100 sweeps (TPI = 100 N), and stores the block means of E and
+E^2 and the acceptance counters.  N is small on purpose: a 1-D chain at fixed L relaxes its long-wavelength density
+modes in ~N^2 sweeps — at N = 2000 the energy of both samplers still drifts after 3000 sweeps (measured with the
+oracle), and a 2 sigma test on a drifting quantity tests the transient, not the distribution; at N = 64 the block
+means are flat from the first 4000 sweeps on.  ~25 s per run; needs /root/reference.
 
     python tests/golden/make_golden_colour.py
 """
@@ -22,16 +25,16 @@ from oracle import oracle as O  # noqa: E402
 from make_golden import deck_with, summarise  # noqa: E402
 
 DECK = """ENSEMBLE   NLT
-N          2000
-L          2240
+N          64
+L          71.68
 T          0.9
-NUMSTEPS   800000
+NUMSTEPS   2560000
 POT        LJcut 5.0
 NBN        4
 MAXSTEP    0.12
 MAXDV      2.0
 CPI        100000000
-TPI        2000
+TPI        6400
 RBW        0.05
 RHONB      1
 RHOPI      50000000
@@ -57,12 +60,12 @@ def main(nseeds=16, seed0=774281, workers=8):
             R = O.run_reference(deck_with(DECK, SEED=seed0 + k), tmp)
             rows = [l.split("\t") for l in Path(R["thermo"]).read_text().splitlines()[1:]]
             return {"seed": seed0 + k, "counters": summarise(R["stdout"])["counters"],
-                    "E_per_sweep": [float(r[1]) for r in rows], "E2_per_sweep": [float(r[2]) for r in rows]}
+                    "E_blocks": [float(r[1]) for r in rows], "E2_blocks": [float(r[2]) for r in rows]}
 
     with ThreadPoolExecutor(workers) as ex:
         runs = list(ex.map(one, range(nseeds)))
     (out / "INPUT").write_text(DECK)
-    (out / "summary.json").write_text(json.dumps({"note": "thermo rows of the compiled reference: row k = mean over sweep k (TPI = N = 2000 steps); row 0 = step 0",
+    (out / "summary.json").write_text(json.dumps({"note": "thermo rows of the compiled reference: row k = mean over the k-th block of 100 sweeps (TPI = 100 N = 6400 steps); row 0 = step 0",
                                                   "runs": runs}) + "\n")
     print("colour_ensemble:", len(runs), "runs")
 

@@ -58,3 +58,54 @@ def test_production_ensemble_matches_reference_within_2_sigma(J, O, gold):
         assert abs(a.mean() - b.mean()) < 2 * sigma + 0.005, f"{name} acceptance: reference {a.mean():.4f}, GPU {b.mean():.4f}"
         report["acc_" + name] = (a.mean(), b.mean())
     print("ensemble check (ref mean, ref se, gpu mean, gpu se, z):", {k: tuple(round(float(x), 5) for x in v) for k, v in report.items()})
+
+
+def test_colour_sampler_matches_the_sequential_reference_ensemble(J, O, gold):
+    """The checkerboard half-sweep (jmm_sweep: draw a colour, try every particle of that colour) is a different Markov
+    chain from the reference's one-random-particle-per-Step (src/jmmMCState.cpp:1758-1811); north_star asks that it move
+    many particles at once "without breaking detailed balance", i.e. that it sample the same Boltzmann distribution.
+    Reference side: tests/golden/colour_ensemble = 16 independent runs of the COMPILED REFERENCE on a test/INPUT-style
+    NLT deck (N = 64, LJcut 5.0, NBN 4, spacing 1.12, T = 0.9: C3's physics at a size whose slowest density mode relaxes
+    within the run), 40 000 sweeps each in blocks of 100 sweeps, the first 5 000 discarded.  GPU side: 256 independent
+    chains of the same deck in JMM_MODE_CHECKERBOARD (reference arithmetic and fast), 5 000 + 20 000 sweeps.
+    <E>, Var(E) and the displacement acceptance must agree within 2 sigma (standard errors over independent runs)."""
+    from jmmonedmc_b200.capi import config
+    g = gold("colour_ensemble")
+    runs = g["summary"]["runs"]
+    d = O.parse_deck(g["deck_text"])
+    N, nbn = int(d["N"]), int(d["NBN"])
+    assert len(runs) == 16 and N == 64 and nbn == 4 and all(len(r["E_blocks"]) == 401 for r in runs)
+    Eb = np.array([r["E_blocks"][51:] for r in runs]); E2b = np.array([r["E2_blocks"][51:] for r in runs])
+    ref_E = Eb.mean(axis=1)
+    ref_var = E2b.mean(axis=1) - ref_E ** 2                  # rows are block means of E and E^2: the variance of the instantaneous E
+    cr = np.array([r["counters"] for r in runs], dtype=np.float64)
+    ref_acc = cr[:, 0] / (cr[:, 0] + cr[:, 1])
+    C, ncol = 256, nbn + 1
+    n_eq, n_run = 5_000 * ncol, 20_000 * ncol                 # half-sweeps: one sweep = ncol half-sweeps = N trials on average
+    report = {}
+    for arith in ("reference", "fast"):
+        cfg = config(N=N, pot=J.POT_LJCUT, nbn=nbn, cutoff=d["CUTOFF"], ensemble=J.ENS_NLT, L=d["L"], T=d["T"], maxStep=d["MAXSTEP"],
+                     seed=20261018, nchains=C, chain_id0=0, mode=J.MODE_CHECKERBOARD,
+                     arith=J.ARITH_FAST if arith == "fast" else J.ARITH_REFERENCE)
+        with J.Handle(cfg) as h:
+            h.start()
+            h.sweep(n_eq)
+            h.zero_accum()
+            c0 = h.get_state(r=False, l=False, totals=False, accum=False)["counters"].astype(np.float64)
+            h.sweep(n_run)
+            s = h.get_state()
+            fresh = h.energy()
+        assert np.all(np.diff(s["r"], axis=1) > 0) and np.all(np.abs(s["r"]) <= d["L"] / 2)       # order kept, walls respected
+        assert np.max(np.abs(s["totals"][:, 0] - fresh[:, 0])) < 1e-7                                 # bookkeeping still exact
+        acc = s["accum"] / n_run                             # one updateThermo per half-sweep
+        gpu_E, gpu_var = acc[:, 4], acc[:, 5] - acc[:, 4] ** 2
+        dc = s["counters"].astype(np.float64) - c0
+        gpu_acc = dc[:, 0] / (dc[:, 0] + dc[:, 1])
+        for name, a, b in (("E", ref_E, gpu_E), ("varE", ref_var, gpu_var), ("acceptance", ref_acc, gpu_acc)):
+            sigma = np.hypot(a.std(ddof=1) / np.sqrt(a.size), b.std(ddof=1) / np.sqrt(b.size))
+            z = (b.mean() - a.mean()) / sigma
+            report[f"{arith}:{name}"] = (round(float(a.mean()), 5), round(float(b.mean()), 5), round(float(z), 2))
+            # the reference's acceptance counters include its equilibration (12 % of the run): 0.2 % absolute for that
+            slack = 0.002 if name == "acceptance" else 0.0
+            assert abs(b.mean() - a.mean()) < 2 * sigma + slack, f"{arith} {name}: reference {a.mean():.5f}, checkerboard {b.mean():.5f}, z = {z:.2f}"
+    print("colour sampler vs sequential reference (ref mean, gpu mean, z):", report)

@@ -448,7 +448,8 @@ def test_banded_acceptance_rules_decide_like_the_reference_expressions(J):
 
 @pytest.mark.parametrize("arith", ["reference", "fast", "fast-g1", "fast-g8", "fast-g32"])
 @pytest.mark.parametrize("pot,nbn,cutoff,N,C", [("LJcut", 4, 5.0, 20000, 2), ("LJ", 2, math.inf, 5001, 1),
-                                                 ("HARMONIC", 1, math.inf, 8192, 3), ("LJ", 24, math.inf, 6000, 2)])
+                                                 ("HARMONIC", 1, math.inf, 8192, 3), ("LJ", 24, math.inf, 6000, 2),
+                                                 ("LJcut", 4, 5.0, 64, 7)])
 def test_checkerboard_sweeps_match_oracle(J, O, pot, nbn, cutoff, N, C, arith, monkeypatch):
     from jmmonedmc_b200.capi import config
     if arith != "reference" and pot == "HARMONIC":
