@@ -565,7 +565,7 @@ constexpr int kThermoSlots = 6;                  // rho, l, E, Vir, HV, 1.0
 template <int G> struct ThermoLanes {
     static constexpr int M = (kNAcc + G - 1) / G;
     double acc[M];
-    uint32_t ia[M], ib[M];                        // operand slots of this lane's sums (byte offsets would save nothing)
+    const double *pa[M], *pb[M];                  // this lane's operand slots in ring entry 0 (entry e: + e * kThermoSlots)
     double *ring;                                 // [kThermoRing][kThermoSlots] doubles of this group
     uint32_t fill;
     // sums in JMM_A_* order: rho, rho^2, l, l^2, E, E^2, l E, Vir, Vir^2, E Vir, HV, HV^2
@@ -579,9 +579,14 @@ template <int G> struct ThermoLanes {
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             const uint32_t k = lane + m * G;
-            operands(k, ia[m], ib[m]);
+            uint32_t ia, ib;
+            operands(k, ia, ib);
+            pa[m] = ring + ia; pb[m] = ring + ib;
             acc[m] = k < kNAcc ? __ldcg(acc_g + (uint64_t) k * C + chain) : 0.0;
         }
+        if (lane < kThermoRing) ring[lane * kThermoSlots + 5] = 1.0;      // the constant operand of the linear sums, once
+        if (G < kThermoRing && lane == 0)
+            for (int e = G; e < kThermoRing; ++e) ring[e * kThermoSlots + 5] = 1.0;
     }
     template <int POT>
     __device__ __forceinline__ void push(const Coop<POT, G> &c) {                 // one step's numbers (any one lane writes)
@@ -589,7 +594,6 @@ template <int G> struct ThermoLanes {
             double *e = ring + fill * kThermoSlots;
             e[0] = c.rho; e[1] = c.l; e[2] = c.tot[0]; e[3] = c.tot[1];
             e[4] = PotTraits<POT>::NC > 6 ? c.tot[6] : 0.0;
-            e[5] = 1.0;
         }
         ++fill;
     }
@@ -600,12 +604,12 @@ template <int G> struct ThermoLanes {
 #pragma unroll
             for (int e = 0; e < kThermoRing; ++e) {
 #pragma unroll
-                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
+                for (int m = 0; m < M; ++m) acc[m] = acc[m] + pa[m][e * kThermoSlots] * pb[m][e * kThermoSlots];
             }
         } else {
             for (uint32_t e = 0; e < fill; ++e) {
 #pragma unroll
-                for (int m = 0; m < M; ++m) acc[m] = acc[m] + ring[e * kThermoSlots + ia[m]] * ring[e * kThermoSlots + ib[m]];
+                for (int m = 0; m < M; ++m) acc[m] = acc[m] + pa[m][e * kThermoSlots] * pb[m][e * kThermoSlots];
             }
         }
         fill = 0;

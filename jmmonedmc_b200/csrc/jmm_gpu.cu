@@ -322,7 +322,9 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
             const char *eb = getenv("JMM_BOND");
             if (h->coop_g && cfg->pot == JMM_POT_HARMONIC && cfg->nbn == 1 && N - 1 <= 16 && !(h->cfg.relax > 0) &&
                 C <= 16384 && !(eb && atoi(eb) == 0))
-                h->bond = (eb && atoi(eb) == 1) ? 1 : 2;         // 2 = k_chains_step_bond2 (registers-only, deferred ECheck); JMM_BOND=1: the first kernel
+                // 1 = k_chains_step_bond (default: 4.43e9 trials/s on C2), 2 = k_chains_step_bond2 (registers-only, deferred
+                // ECheck: 3.99e9 — fewer rendezvous but no fewer instructions, profiles/r2e_c2_*; kept selectable, parity-tested)
+                h->bond = (eb && atoi(eb) == 2) ? 2 : 1;
         }
     }
     CKH(cudaStreamSynchronize(h->stream));

@@ -83,7 +83,7 @@ __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32
     // (G + 2 log2 G... shuffles of one double instead of two per round).  Commutative additions: every lane of the group
     // ends up with the same bits.  Full-warp mask: the step loop keeps the warp converged here (lanes_run_chain).
     if constexpr (G == 1) return;
-    __syncwarp();                                 // (run-time partner bounds: the groups may have left the loop apart)
+    if constexpr (NPL == 0) __syncwarp();         // (run-time partner bounds: the groups may have left the loop apart)
     const bool odd = c.lane & 1;
     const double give = odd ? s12 : s6, keep = odd ? s6 : s12;
     double v = keep + __shfl_xor_sync(0xffffffffu, give, 1, G);
@@ -189,8 +189,7 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
     double rnm = handover(false, 0, 0.0, disp, nm);
 
     for (uint32_t s = 0; s < count; ++s) {
-        ++sn;
-        __syncwarp();
+        ++sn;                                                 // (the warp is converged here: every iteration ends in handover's rendezvous)
         const bool more = s + 1 < count;
         uint32_t nm1 = 0, w11 = 0, w21 = 0;
         if (more) draw(sn + 1, nm1, w11, w21);                // (uniform in the warp: every group runs `count` steps)

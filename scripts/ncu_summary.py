@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Condense an .ncu-rep into the numbers DESIGN.md / profiles/ quote: duration, occupancy, issue rate,
-fp64 pipe, DRAM traffic, stall reasons and the SASS opcode mix.  Usage: ncu_summary.py rep [units-per-launch]"""
+fp64 pipe, DRAM traffic, stall reasons and the SASS opcode mix.  Usage: ncu_summary.py rep [units-per-launch] [--traffic KEY]
+--traffic KEY also records dram__bytes_read.sum + dram__bytes_write.sum of the captured launch under KEY in
+profiles/traffic.json, which bench.py quotes as roofline.traffic."""
 import collections
 import csv
 import io
@@ -14,14 +16,32 @@ def raw(rep):
     return rows[0], rows[1], rows[-1]
 
 
+def to_bytes(val, unit):
+    x = float(val.replace(",", ""))
+    return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
 def main():
-    rep = sys.argv[1]
-    units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+    argv = list(sys.argv)
+    key = None
+    if "--traffic" in argv:
+        i = argv.index("--traffic"); key = argv[i + 1]; del argv[i:i + 2]
+    rep = argv[1]
+    units = float(argv[2]) if len(argv) > 2 else None
     hdr, unit, val = raw(rep)
     d = {h: (v, u) for h, u, v in zip(hdr, unit, val)}
     def g(k):
         return d.get(k, ("", ""))
     print(f"# {rep}\nkernel: {g('Kernel Name')[0]}")
+    if key:
+        import json
+        from pathlib import Path
+        tj = Path(__file__).resolve().parent.parent / "profiles" / "traffic.json"
+        t = json.loads(tj.read_text()) if tj.exists() else {}
+        t[key] = {"dram_bytes": int(to_bytes(*g("dram__bytes_read.sum")) + to_bytes(*g("dram__bytes_write.sum"))),
+                  "kernel": g("Kernel Name")[0], "duration_us_under_ncu": g("gpu__time_duration.sum")[0] + " " + g("gpu__time_duration.sum")[1],
+                  "source": "ncu --set full --clock-control none, " + Path(rep).name}
+        tj.write_text(json.dumps(t, indent=1, sort_keys=True) + "\n")
     keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
             "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
