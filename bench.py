@@ -65,7 +65,7 @@ EXTRA = {
                per_step=64, e2e_mult=16, flop=33 * 8 + 37, bytes_per_trial=16.0),
     "c4": dict(desc="C4: RunJobs-style sweep, 65,536 chains (256x256 P,T grid in [0.1,1]) x N=80, LJ, NBN -1, NPT, RELAX",
                kind="chains", N=80, nchains=C4_TOTAL, pot="LJ", nbn=-1, cutoff=math.inf, maxStep=0.1, maxdl=2.0, eci=10000,
-               mdai=10 ** 6, mvai=10 ** 6, seed=92847, relax=1, per_step=2000, e2e_mult=1, flop=33 * 79 + 37,
+               mdai=10 ** 6, mvai=10 ** 6, seed=92847, relax=1, per_step=20000, e2e_mult=1, flop=33 * 79 + 37,
                bytes_per_trial=None),
     "c5": dict(desc="C5: 8 chains x N=262,144, LJ, NBN 64 (128 partners), NLT (L=1.12N), T=0.9, checkerboard half-sweeps",
                kind="sweep", N=1 << 18, nchains=8, pot="LJ", nbn=64, cutoff=math.inf, T=0.9, maxStep=0.12, seed=92847,
@@ -667,7 +667,9 @@ def gpu_arm(args) -> None:
 
 def gpu_arm_strong(E: Env, args) -> None:
     """N > 1: BASELINE.json configs[3] as written — 65 536 chains sharded over the GPUs, strong scaling."""
-    m = measure_c4(E, "fast", args.steps, args.warmup, strong=True, min_seconds=0.0)
+    # 50 000 MC steps per chain and bench step: 0.07 s (8 GPUs) ... 0.35 s (1 GPU) per step, so that the K timed steps the driver asks
+    # for give the clock sampler a region of ~1 s and the host copies of the e2e leg are those of a realistic call
+    m = measure_c4(E, "fast", args.steps, args.warmup, strong=True, min_seconds=0.0, per_step=int(os.environ.get("JMM_BENCH_PER_STEP", 50000)))
     z = measure_c4(E, "fast", 2, 1, strong=True, from_zero=True, min_seconds=0.0, with_e2e=False, per_step=10000)
     weak = measure_c2(E, 5, 3, with_e2e=False)
     w = EXTRA["c4"]
