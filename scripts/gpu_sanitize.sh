@@ -20,6 +20,12 @@ ljc = dict(N=24, pot=J.POT_LJCUT, nbn=3, cutoff=2.5, P=0.5, T=0.7, maxStep=0.15,
 which = os.environ.get("SAN_CASE", "all")
 cases = {
  "bond": lambda: run(config(nchains=37, **std)),
+ "bond2": lambda: (os.environ.__setitem__("JMM_BOND", "2"), run(config(nchains=37, **std)), os.environ.__setitem__("JMM_BOND", "1")),
+ "lanes": lambda: [(os.environ.__setitem__("JMM_LANES_G", g), run(config(nchains=21, arith=J.ARITH_FAST, adapt=J.ADAPT_DEVICE, **lj), 90),
+                    run(config(nchains=21, arith=J.ARITH_FAST, **ljc), 90)) for g in ("8", "4", "32")] + [os.environ.pop("JMM_LANES_G")],
+ "lanes80": lambda: (os.environ.__setitem__("JMM_FORCE_SLICE", "1"), os.environ.__setitem__("JMM_SLICE_CHUNK", "13"),
+                     run(config(nchains=70, arith=J.ARITH_FAST, N=80, pot=J.POT_LJ, nbn=-1, P=0.5, T=0.5, maxStep=0.1, maxdl=2.0, eci=30, mdai=10**6, mvai=10**6, seed=92847, relax=1), 70),
+                     os.environ.pop("JMM_FORCE_SLICE"), os.environ.pop("JMM_SLICE_CHUNK")),
  "coop": lambda: (os.environ.__setitem__("JMM_BOND", "0"), run(config(nchains=37, **std)), run(config(nchains=9, **lj)), run(config(nchains=9, **ljc))),
  "prod": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), run(config(nchains=70, **lj)), run(config(nchains=70, arith=J.ARITH_FAST, **ljc))),
  "sliced": lambda: (os.environ.__setitem__("JMM_COOP_G", "0"), os.environ.__setitem__("JMM_FORCE_SLICE", "1"), os.environ.__setitem__("JMM_SLICE_CHUNK", "7"), run(config(nchains=70, **lj))),
@@ -35,7 +41,7 @@ for k, f in cases.items():
     if which in ("all", k): f(); print("case", k, "ok")
 PY
 for tool in memcheck racecheck; do
-  for c in ${SAN_CASES:-bond coop prod sliced generic sweep sweep_shapes}; do
+  for c in ${SAN_CASES:-bond bond2 lanes lanes80 coop prod sliced generic sweep sweep_shapes}; do
     echo "== $tool $c"
     SAN_CASE=$c timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|case|Error|error|hazard|Invalid" | head -8
   done

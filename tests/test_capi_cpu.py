@@ -181,3 +181,17 @@ def test_batch_driver_refuses_a_restart_deck_before_touching_outputs(J, tmp_path
     assert out.returncode == 1 and "RESTART" in out.stderr and "--resume" in out.stderr
     assert (tmp_path / "thermo.dat.mcs").read_text() == "previous run\n"
     assert (tmp_path / "config.dat.mcs").read_text() == "previous frames\n"
+
+
+def test_bench_reference_arm_at_several_gpus_times_the_sweep_deck():
+    """bench.py --impl reference --gpus N (N > 1): the GPU arm's headline there is BASELINE config 4 (the 65 536-chain sweep,
+    strong scaling), so the reference arm times one chain of that sweep per host core and says so."""
+    import json, os, sys
+    env = dict(os.environ, JMM_BENCH_REF_STEPS="4000")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "4", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 4 and line["scaling"] == "strong"
+    assert line["config"]["workload"].startswith("C4:") and "C4 (one chain)" in line["cpu_baseline"]["sample"]
+    assert line["value"] > 0 and line["gpu_launches"] == 0
