@@ -782,6 +782,12 @@ static __global__ void k_transpose_out(const double *__restrict__ src /*[n][ncha
     const uint64_t c = t / n, i = t % n;
     dst[t] = src[i * nchains + c];
 }
+static __global__ void k_lattice_chain_major(double *r /*[nchains][N]*/, const double *l, uint64_t nchains, uint64_t N) {   // :561
+    const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nchains * N) return;
+    const uint64_t c = t / N, i = t % N;
+    r[t] = (((double) i + 0.5) / (double) N - 0.5) * l[c];
+}
 static __global__ void k_lattice(double *r /*[N][nchains]*/, const double *l, uint64_t nchains, uint64_t N) {   // :561
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchains * N) return;

@@ -238,28 +238,26 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
     CKH(dalloc(h, &S.l, C)); CKH(dalloc(h, &S.P, C)); CKH(dalloc(h, &S.T, C));
     CKH(dalloc(h, &S.maxStep, C)); CKH(dalloc(h, &S.maxdl, C));
 
-    std::vector<double> v(C);
-    auto fill = [&](double *d, double x) {
-        std::fill(v.begin(), v.end(), x);
-        return cudaMemcpyAsync(d, v.data(), C * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    };
     const double l0 = (cfg->ensemble == JMM_ENS_NPT) ? (double) N : cfg->L;   // :553, :414
-    CKH(fill(S.l, l0)); CKH(cudaStreamSynchronize(h->stream));
-    CKH(fill(S.P, cfg->P)); CKH(cudaStreamSynchronize(h->stream));
-    CKH(fill(S.T, cfg->T)); CKH(cudaStreamSynchronize(h->stream));
-    CKH(fill(S.maxStep, cfg->maxStep)); CKH(cudaStreamSynchronize(h->stream));
-    CKH(fill(S.maxdl, cfg->maxdl)); CKH(cudaStreamSynchronize(h->stream));
+    {   // five per-chain constants: one staging buffer each, one synchronisation
+        std::vector<double> v5(5 * C);
+        const double vals[5] = {l0, cfg->P, cfg->T, cfg->maxStep, cfg->maxdl};
+        double *dst[5] = {S.l, S.P, S.T, S.maxStep, S.maxdl};
+        for (int k = 0; k < 5; ++k) {
+            std::fill(v5.begin() + k * C, v5.begin() + (k + 1) * C, vals[k]);
+            CKH(cudaMemcpyAsync(dst[k], v5.data() + k * C, C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        }
+        CKH(cudaStreamSynchronize(h->stream));
+    }
 
     if (is_cb(h)) {
         CKH(dalloc(h, &h->cb_r[0], C * N)); CKH(dalloc(h, &h->cb_r[1], C * N));
         CKH(dalloc(h, &h->cb_tot, C * 9)); CKH(dalloc(h, &h->cb_acc, C * 12));
         CKH(dalloc(h, &h->cb_counts, C * 2));
         CKH(dalloc(h, &h->cb_tile_done, C));
-        // lattice, chain-major: same formula as :561 (k_lattice with nchains = 1 per chain)
-        for (uint64_t c = 0; c < C; ++c) {
-            k_lattice<<<nblk(N, 256), 256, 0, h->stream>>>(h->cb_r[0] + c * N, S.l + c, 1, N);
-            h->launches++;
-        }
+        // lattice, chain-major: same formula as :561, every chain in one launch
+        k_lattice_chain_major<<<nblk(C * N, 256), 256, 0, h->stream>>>(h->cb_r[0], S.l, C, N);
+        h->launches++;
         CKH(cudaGetLastError());
     } else {
         CKH(dalloc(h, &S.r, C * N));

@@ -182,6 +182,7 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
         return got;
     };
 
+    uint32_t n_acc = 0, n_rej = 0;
     uint32_t nm, w1, w2;
     __syncwarp();
     draw(sn + 1, nm, w1, w2);
@@ -224,8 +225,8 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
                 c.tot[6] += dH12 - dH6; c.tot[7] += dH12; c.tot[8] += dH6;
             }
             if (LOG) flags = (disp && wall) ? kLogWall : (acc ? kLogAccepted : 0);
-            c.cnt[0] += acc ? 1 : 0;
-            c.cnt[1] += (disp && !acc) ? 1 : 0;
+            n_acc += acc ? 1u : 0u;                           // (32-bit tallies, folded into the 64-bit counters at events)
+            n_rej += (disp && !acc) ? 1u : 0u;
         }
         if (!disp) {                                          // volume trial: no sentinel is out, the row is consistent
             const double rn = u01(w1), ran = u01(w2);
@@ -243,6 +244,7 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
             if (th.fill == kThermoRing) th.flush(c);
         } else {
             handover(disp, nm, acc ? rT : rnm, false, 0);     // positions consistent for whatever is due now
+            c.cnt[0] += n_acc; c.cnt[1] += n_rej; n_acc = n_rej = 0;
             th.flush(c);
             if (a.eci && sn % a.eci == 0) coop_energy_check(c);                        // Step :1800
             th.push(c); th.flush(c);                                                     // :1805
@@ -259,6 +261,7 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
     }
 
     th.flush(c);
+    c.cnt[0] += n_acc; c.cnt[1] += n_rej;
     if (!own) return;                                         // a surplus group of a ragged last tile shadows the last chain
     th.store(c.lane, S.acc, C, chain);
     for (uint32_t i = c.lane; i < c.N; i += G) S.r[(uint64_t) i * C + chain] = row[i];

@@ -47,6 +47,19 @@ struct SweepDev {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
+// The neighbour hand-shake of k_sweep_fast as release/acquire operations of the PTX memory model (CTA scope, shared
+// memory): a warp publishes "half-sweep t done" with a release store after its position writes, a neighbour polls with
+// acquire loads; what the publisher wrote before the release is visible after the acquire that reads it.  (Round 1 used a
+// volatile int + __threadfence_block(), correct on the hardware but defined only by observed behaviour.)
+__device__ __forceinline__ void st_release_cta(int *p, int v) {
+    asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int colour_of(uint64_t seed, uint32_t chain, uint64_t step, int ncol) {
     const Philox4 b = philox4x32_10((uint32_t) step, (uint32_t)(step >> 32), 0xFFFFFFFFu, kTagColour | chain,
                                     (uint32_t) seed, (uint32_t)(seed >> 32));
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
     int *firsts = reinterpret_cast<int *>(w + wcap);                  // [nsub] window index of the first particle to try
     int *bases = firsts + nsub;                                       // [nsub] the same, moved down to an EVEN trial index
     uint32_t *jbs = reinterpret_cast<uint32_t *>(bases + nsub);       // [nsub] that (even) trial index within the half-sweep
-    volatile int *done = bases + 2 * nsub;                            // [nwarps] half-sweeps completed by each warp
+    int *done = bases + 2 * nsub;                                     // [nwarps] half-sweeps completed by each warp (release/acquire)
     double2 *wsum = reinterpret_cast<double2 *>(w + wcap + ((3 * nsub + nwarps + 3) >> 2) * 2);   // [nsub][nwarps] (s12, s6)
     double *ts = reinterpret_cast<double *>(wsum + nsub * nwarps);    // [nsub][9], last CTA of a chain only
     __shared__ __align__(8) unsigned long long mbar;
@@ -406,8 +419,7 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
                 // w_lo + j, one vote per poll, the pause doubling up to 160 ns
                 const int v = min(w_lo + lane32, w_hi);
                 unsigned ns = 20;
-                while (!__all_sync(0xffffffffu, done[v] >= t)) { __nanosleep(ns); ns = min(ns * 2, 160u); }
-                __threadfence_block();
+                while (!__all_sync(0xffffffffu, ld_acquire_cta(done + v) >= t)) { __nanosleep(ns); ns = min(ns * 2, 160u); }
             }
 #endif
             // One Philox block serves the trials 2m and 2m+1 of a half-sweep (words 0,1 and 2,3).
@@ -514,8 +526,7 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
         }
         __syncwarp();
         // this warp's half-sweep is complete: publish it (the position writes above first), then its two sums
-        __threadfence_block();
-        if (lane32 == 0) done[warp] = t + 1;
+        if (lane32 == 0) st_release_cta(done + warp, t + 1);      // (the __syncwarp above orders the other lanes' writes before it)
         // two sums over the warp with one value per lane after the first exchange: even lanes carry s12, odd lanes s6
         {
             const bool odd = lane32 & 1;
