@@ -2,6 +2,14 @@
 # Round-2 final visit: full parity suite, smoke, the default bench line, the reference arm, launch list, one ncu --set full
 # capture per kernel family (with traffic.json), the fp64-peak microbenchmark under ncu, compute-sanitizer on the new kernels.
 OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r2z}
+export JMM_TRAFFIC_JSON=$PWD/$OUT/traffic_$TAG.json
+# gpurun brings back at most 64 MiB: every .ncu-rep is condensed to text on the box (scripts/ncu_summary.py, ncu_lines.py) and removed
+condense() {  # rep-basename units traffic-key
+  python scripts/ncu_summary.py $OUT/$1.ncu-rep $2 --traffic $3 > $OUT/$1.txt 2>&1
+  echo "---- per source line (warp instructions per unit, share of stall samples)" >> $OUT/$1.txt
+  python scripts/ncu_lines.py $OUT/$1.ncu-rep $2 40 >> $OUT/$1.txt 2>&1
+  rm -f $OUT/$1.ncu-rep
+}
 PT="--timeout 1500 --timeout-method thread"
 timeout 2400 python -m pytest tests -m gpu -q $PT --durations=6 > $OUT/pytest_gpu_$TAG.log 2>&1
 tail -12 $OUT/pytest_gpu_$TAG.log
@@ -36,18 +44,23 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_launches_$TAG.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_bond -s 3 -c 1 -f -o $OUT/prof_c2_$TAG \
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_c2_$TAG.log 2>&1; tail -1 $OUT/ncu_c2_$TAG.log | cut -c1-200
+condense prof_c2_$TAG 409600000 k_chains_step_bond          # unit = one warp step (2048 warps x 200 000 steps)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_prod -s 1 -c 1 -f -o $OUT/prof_c4fast_$TAG \
     python bench.py --workload c4 --arith fast --steps 1 --warmup 3 --no-cpu --no-e2e --min-seconds 0 > $OUT/ncu_c4fast_$TAG.log 2>&1; tail -1 $OUT/ncu_c4fast_$TAG.log | cut -c1-200
+condense prof_c4fast_$TAG 40960000 k_chains_step_prod_sliced  # unit = one warp step (2048 tiles x 20 000 steps)
 JMM_BENCH_CHAINS=8192 JMM_BENCH_PER_STEP=2000 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_lanes -s 1 -c 1 -f -o $OUT/prof_c4lanes_$TAG \
     python bench.py --workload c4 --arith fast --steps 1 --warmup 3 --no-cpu --no-e2e --min-seconds 0 > $OUT/ncu_c4lanes_$TAG.log 2>&1; tail -1 $OUT/ncu_c4lanes_$TAG.log | cut -c1-200
+condense prof_c4lanes_$TAG 4096000 k_chains_step_lanes      # unit = one warp step (2048 tiles x 2000 steps)
 for w in c3 c5; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_sweep_fast -s 4 -c 1 -f -o $OUT/prof_${w}fast_$TAG \
       python bench.py --workload $w --arith fast --steps 1 --warmup 3 --no-cpu --no-e2e --min-seconds 0 > $OUT/ncu_${w}fast_$TAG.log 2>&1; tail -1 $OUT/ncu_${w}fast_$TAG.log | cut -c1-200
+  condense prof_${w}fast_$TAG 13421772 k_sweep_fast_$w          # unit = one trial of a 64-half-sweep launch (approx.)
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_${w}fast_$TAG.csv \
       python bench.py --workload $w --arith fast --steps 1 --warmup 3 --no-cpu --no-e2e --min-seconds 0 > /dev/null 2>&1
 done
 # the roofline denominator itself: the DFMA microbenchmark under ncu (pipe_fp64 counter)
 timeout 200 ncu --set full --clock-control none -k regex:k_fp64_peak -s 2 -c 1 -f -o $OUT/prof_fp64peak_$TAG \
     python -c "import jmmonedmc_b200 as J; print(J.lib().jmm_fp64_peak_tflops(0))" > $OUT/ncu_fp64peak_$TAG.log 2>&1; tail -2 $OUT/ncu_fp64peak_$TAG.log | cut -c1-200
+condense prof_fp64peak_$TAG 1 k_fp64_peak
 SAN_CASES="bond2 lanes lanes80" bash scripts/gpu_sanitize.sh > $OUT/sanitizer_$TAG.txt 2>&1; tail -14 $OUT/sanitizer_$TAG.txt
 ls -la $OUT | tail -30

@@ -36,7 +36,8 @@ def main():
     if key:
         import json
         from pathlib import Path
-        tj = Path(__file__).resolve().parent.parent / "profiles" / "traffic.json"
+        import os
+        tj = Path(os.environ.get("JMM_TRAFFIC_JSON", str(Path(__file__).resolve().parent.parent / "profiles" / "traffic.json")))
         t = json.loads(tj.read_text()) if tj.exists() else {}
         t[key] = {"dram_bytes": int(to_bytes(*g("dram__bytes_read.sum")) + to_bytes(*g("dram__bytes_write.sum"))),
                   "kernel": g("Kernel Name")[0], "duration_us_under_ncu": g("gpu__time_duration.sum")[0] + " " + g("gpu__time_duration.sum")[1],
