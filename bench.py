@@ -558,10 +558,10 @@ def measure_sweep(E: Env, workload: str, arith: str, steps: int, warmup: int, mi
     return out
 
 
-def roofline_fp64(E: Env, per_gpu_value: float, flop: float, kernel: str, k_ms, bytes_per_trial=None, extra=None) -> dict:
+def roofline_fp64(E: Env, per_gpu_value: float, flop: float, kernel: str, k_ms, bytes_per_trial=None, extra=None, traffic_key=None) -> dict:
     peak = E.fp64_peak()
     tf = per_gpu_value * flop / 1e12
-    traffic, tsrc = _traffic(kernel)
+    traffic, tsrc = _traffic(traffic_key or kernel)
     peaks = _peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     r = {"bound": "fp64", "kernel": kernel, "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak and peak > 0 else None,
@@ -723,7 +723,8 @@ def extra_arm(args) -> None:
                            "first_step": m.get("first_step", 0), "l2": "flushed between timed iterations (256 MiB fill)"},
                 "gpu_launches": m["launches"], "clocks": m["clocks"], "timed_s": m["dev_ms"] * 1e-3,
                 "ms_steps": [round(x, 4) for x in m["per_step_ms"][:64]],
-                "roofline": roofline_fp64(E, per_gpu, w["flop"], kernel, m["kernel_ms"], w["bytes_per_trial"]),
+                "roofline": roofline_fp64(E, per_gpu, w["flop"], kernel, m["kernel_ms"], w["bytes_per_trial"],
+                                          traffic_key=(kernel + "_" + wl) if kernel == "k_sweep_fast" else None),
                 "acceptance": m["acceptance"], "e2e": m.get("e2e"),
                 "cpu_baseline": cpu_baseline_extra(wl, w) if not args.no_cpu else None}
         print(json.dumps(line), flush=True)

@@ -696,3 +696,35 @@ def test_consistent_virial_flag_changes_only_the_virial_bookkeeping(J, O, engine
     assert not totals_close(s0["totals"], fresh0, 1e-6)
     with pytest.raises(J.JmmError):
         J.Handle(jmm_config_from_deck(J, d, rng_kind=J.RNG_TAUS2, mode=J.MODE_TABLE, flags=J.FLAG_CONSISTENT_VIRIAL))
+
+
+@pytest.mark.parametrize("g", ["2", "4", "8", "16"])
+@pytest.mark.parametrize("pot,N", [("LJcut", 78), ("LJ", 73)])
+def test_lanes_paired_steps_with_padded_rows_match_oracle(J, O, pot, N, g, monkeypatch):
+    """lanes.cuh with the unrolled partner loop (NBN -1, N in (G (NPL-1), G NPL]): rows padded with far-away slots
+    (N = 78 and 73 against 80 slots), two commuting trials per loop iteration (the pair terms between the two moved
+    particles evaluated apart, in the reference's orientation: LJcut's `d <= cutOff` is a test on the SIGNED distance,
+    src/pot.cpp:53), volume trials through fav with the lean ordered sums (LJcut) or qavLJ (LJ), ECheck every 50 steps,
+    device-side adjustments off (DADJ/VADJ beyond the run).  Every chain against the oracle: accept sequence, positions,
+    box and counters bit-identical; totals and sums to 1e-12."""
+    monkeypatch.setenv("JMM_LANES_G", g)
+    d = dict(N=N, POT=pot, NBN=-1, CUTOFF=2.5 if pot == "LJcut" else math.inf, ENSEMBLE="NPT", P=0.6, T=0.8, MAXSTEP=0.12, MAXDV=1.5,
+             ENGCHECK=50, DADJ=10 ** 6, VADJ=10 ** 6, SEED=4242, RELAX=0)
+    C, nsteps, id0 = 11, 1200, 77
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_DEVICE, nchains=C, chain_id0=id0,
+                               arith=J.ARITH_FAST)
+    with J.Handle(cfg) as h:
+        h.start()
+        log = h.step(nsteps, accept_log=True)
+        s = h.get_state()
+        checks, disc = h.echeck_stats()
+    assert disc == 0 and checks == C * (nsteps // 50)
+    for c in range(C):
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=id0 + c))
+        oc.start()
+        want_log = oracle_accept_log(oc, nsteps)
+        assert np.array_equal(log[:, c] & 3, want_log), f"chain {c}: accept sequence"
+        assert bits_equal(s["r"][c], oc.r), f"chain {c}: positions"
+        assert bits_equal(s["l"][c:c + 1], [oc.l]) and np.array_equal(s["counters"][c], oc.counters)
+        assert totals_close(s["totals"][c], oc.totals, 1e-12), f"chain {c}: totals"
+        assert np.allclose(s["accum"][c], oc.accum, rtol=1e-11, atol=1e-9)
