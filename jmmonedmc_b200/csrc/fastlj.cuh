@@ -97,26 +97,6 @@ __device__ __forceinline__ void lj_partners(const double (&a)[NP], const double 
     for (int i = 0; i < NP; ++i) { s6 += x[i]; s12 = __fma_rn(x[i], y[i], s12); }
 }
 
-// The same stages with the terms kept apart: d6[i] = b^-6 - a^-6 and t6[i] = b^-6 + a^-6 (so that b^-12 - a^-12 = d6 t6).
-template <bool CUT, int NP>
-__device__ __forceinline__ void lj_terms(const double (&a)[NP], const double (&b)[NP], double cutoff, double (&d6)[NP], double (&t6)[NP]) {
-    double A[NP], B[NP], x[NP], y[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) { A[i] = a[i] * a[i]; B[i] = b[i] * b[i]; }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) { x[i] = A[i] * A[i]; y[i] = B[i] * B[i]; }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) { A[i] = x[i] * A[i]; B[i] = y[i] * B[i]; }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) y[i] = rcp_cubic(A[i] * B[i]);
-    if constexpr (CUT) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) { mask_beyond(A[i], b[i], cutoff); mask_beyond(B[i], a[i], cutoff); }
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) { d6[i] = (A[i] - B[i]) * y[i]; t6[i] = (A[i] + B[i]) * y[i]; }
-}
-
 // The nine deltas of qad2 from (s6, s12), component order of src/pot.cpp:90-100.
 __device__ __forceinline__ void lj_nine(double s6, double s12, double (&d)[9]) {
     const double e12 = 4 * s12, e6 = 4 * s6;

@@ -33,64 +33,38 @@ namespace jmm {
 #endif
 constexpr int kLanesMaxWarps = JMM_LANES_MAXW;   // 12 warps per CTA = 168 registers per thread (16 = 128: spills)
 
-// Two sums over the G lanes with one value per lane after the first exchange: even lanes carry s12, odd lanes s6
-// (4 shuffles of one double per... log2 G + 1 rounds instead of two doubles per round).  Commutative additions: every lane
-// of the group ends up with the same bits.  Full-warp mask: the step loop keeps the warp converged here.
-template <int G>
-__device__ __forceinline__ void lanes_butterfly(uint32_t lane, double &s6, double &s12) {
-    if constexpr (G == 1) return;
-    const bool odd = lane & 1;
-    const double give = odd ? s12 : s6, keep = odd ? s6 : s12;
-    double v = keep + __shfl_xor_sync(0xffffffffu, give, 1, G);
-#pragma unroll
-    for (int o = 2; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
-    const double other = __shfl_xor_sync(0xffffffffu, v, 1, G);
-    s12 = odd ? other : v;
-    s6 = odd ? v : other;
-}
-
-// This lane's share of the partner sums of one displacement trial: s6 = sum(b^-6 - a^-6), s12 = sum(b^-12 - a^-12) over
-// the NPL slots p = lane + G i of the (padded) row held in rr[].  The slot of a moved particle holds kFarAway while this
-// runs (see lanes_run_chain), so there is no per-partner index test.
-template <int POT, int G, int NPL>
-__device__ __forceinline__ void lanes_row_sums(const Coop<POT, G> &c, const double (&rr)[NPL], uint32_t nm, double rnm, double rT,
-                                               double &s6, double &s12) {
-    double a[NPL], b[NPL];
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-        const double r = rr[i];
-        if constexpr (POT == kPotLJcut) {
-            const bool left = c.lane + G * i < nm;
-            a[i] = left ? rnm - r : r - rnm; b[i] = left ? rT - r : r - rT;
-        } else { a[i] = r - rnm; b[i] = r - rT; }
-    }
-    s6 = 0; s12 = 0;
-    constexpr int H = NPL > 10 ? NPL / 2 : NPL;               // at most ten chains in flight (registers)
-    if constexpr (H == NPL) lj_partners<POT == kPotLJcut, NPL>(a, b, c.cutoff, s6, s12);
-    else {
-        double a1[H], b1[H], a2[NPL - H], b2[NPL - H];
-#pragma unroll
-        for (int i = 0; i < H; ++i) { a1[i] = a[i]; b1[i] = b[i]; }
-#pragma unroll
-        for (int i = H; i < NPL; ++i) { a2[i - H] = a[i]; b2[i - H] = b[i]; }
-        lj_partners<POT == kPotLJcut, H>(a1, b1, c.cutoff, s6, s12);
-        lj_partners<POT == kPotLJcut, NPL - H>(a2, b2, c.cutoff, s6, s12);
-    }
-}
-
-// The partner sums of one displacement trial, strided over the G lanes and closed by the butterfly (identical bits in
-// every lane of the group).  NPL > 0: every lane visits exactly NPL slots of a row padded to NPL*G positions (pads hold
-// kFarAway for ever); needs NBN < 0.  NPL == 0: run-time bounds (NBN >= 0 or an unusual N).
+// The partner sums of one displacement trial: s6 = sum(b^-6 - a^-6), s12 = sum(b^-12 - a^-12) over the partners of
+// `nm`, strided over the G lanes and closed by an xor butterfly (identical bits in every lane of the group).
+// The slot of the moved particle holds kFarAway while this runs (see lanes_run_chain), so there is no per-partner
+// index test.  NPL > 0: every lane visits exactly NPL slots p = lane + G i of a row padded to NPL*G positions (pads
+// hold kFarAway for ever); needs NBN < 0.  NPL == 0: run-time bounds (NBN >= 0 or an unusual N).
 template <int POT, int G, int NPL>
 __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32_t nm, double rnm, double rT, double &s6, double &s12) {
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
+    s6 = 0; s12 = 0;
     if constexpr (NPL > 0) {
-        double rr[NPL];
+        double a[NPL], b[NPL];
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) rr[i] = c.r[c.lane + G * i];
-        lanes_row_sums<POT, G, NPL>(c, rr, nm, rnm, rT, s6, s12);
+        for (int i = 0; i < NPL; ++i) {
+            const uint32_t p = c.lane + G * i;
+            const double r = c.r[p];
+            if constexpr (POT == kPotLJcut) {
+                const bool left = p < nm;
+                a[i] = left ? rnm - r : r - rnm; b[i] = left ? rT - r : r - rT;
+            } else { a[i] = r - rnm; b[i] = r - rT; }
+        }
+        constexpr int H = NPL > 10 ? NPL / 2 : NPL;           // at most ten chains in flight (registers)
+        if constexpr (H == NPL) lj_partners<POT == kPotLJcut, NPL>(a, b, c.cutoff, s6, s12);
+        else {
+            double a1[H], b1[H], a2[NPL - H], b2[NPL - H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) { a1[i] = a[i]; b1[i] = b[i]; }
+#pragma unroll
+            for (int i = H; i < NPL; ++i) { a2[i - H] = a[i]; b2[i - H] = b[i]; }
+            lj_partners<POT == kPotLJcut, H>(a1, b1, c.cutoff, s6, s12);
+            lj_partners<POT == kPotLJcut, NPL - H>(a2, b2, c.cutoff, s6, s12);
+        }
     } else {
-        s6 = 0; s12 = 0;
         const uint32_t N = c.N;
         const uint32_t lo = (c.nbn < 0 || (uint32_t) c.nbn > nm) ? 0u : nm - (uint32_t) c.nbn;
         const uint32_t hi = (c.nbn < 0 || nm + (uint32_t) c.nbn > N - 1) ? N - 1 : nm + (uint32_t) c.nbn;
@@ -104,9 +78,20 @@ __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32
                 lj_partner<false>(r - rnm, r - rT, c.cutoff, s6, s12);
             }
         }
-        __syncwarp();                             // (run-time partner bounds: the groups may have left the loop apart)
     }
-    lanes_butterfly<G>(c.lane, s6, s12);
+    // Two sums over the G lanes with one value per lane after the first exchange: even lanes carry s12, odd lanes s6
+    // (G + 2 log2 G... shuffles of one double instead of two per round).  Commutative additions: every lane of the group
+    // ends up with the same bits.  Full-warp mask: the step loop keeps the warp converged here (lanes_run_chain).
+    if constexpr (G == 1) return;
+    if constexpr (NPL == 0) __syncwarp();         // (run-time partner bounds: the groups may have left the loop apart)
+    const bool odd = c.lane & 1;
+    const double give = odd ? s12 : s6, keep = odd ? s6 : s12;
+    double v = keep + __shfl_xor_sync(0xffffffffu, give, 1, G);
+#pragma unroll
+    for (int o = 2; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    const double other = __shfl_xor_sync(0xffffffffu, v, 1, G);
+    s12 = odd ? other : v;
+    s6 = odd ? v : other;
 }
 
 // One chain (the G lanes of its group) advanced by `count` steps starting after step sn0.
@@ -185,151 +170,80 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
         w2_o = __shfl_sync(0xffffffffu, my_w2, batch_pos, G);
         ++batch_pos;
     };
-    // lane 0: [write up to two positions] [read up to two positions of the next trials and leave the far-away sentinel
-    // there]; everyone gets those positions; one rendezvous
-    auto handover = [&](bool wr0, uint32_t nw0, double v0, bool wr1, uint32_t nw1, double v1,
-                        bool rd0, uint32_t nr0, bool rd1, uint32_t nr1, double &g0, double &g1) {
-        double a0 = 0.0, a1 = 0.0;
+    // lane 0: [write `val` to r[nm_w]] [read r[nm_r], leave the sentinel there]; everyone gets that position
+    auto handover = [&](bool wr, uint32_t nm_w, double val, bool rd, uint32_t nm_r) -> double {
+        double got = 0.0;
         if (c.lane == 0) {
-            if (wr0) c.r[nw0] = v0;
-            if (wr1) c.r[nw1] = v1;
-            if (rd0) a0 = c.r[nr0];
-            if (rd1) a1 = c.r[nr1];
-            if (rd0) c.r[nr0] = kFarAway;
-            if (rd1) c.r[nr1] = kFarAway;
+            if (wr) c.r[nm_w] = val;
+            if (rd) { got = c.r[nm_r]; c.r[nm_r] = kFarAway; }
         }
-        g0 = __shfl_sync(0xffffffffu, a0, 0, G);
-        g1 = __shfl_sync(0xffffffffu, a1, 0, G);
+        got = __shfl_sync(0xffffffffu, got, 0, G);
         __syncwarp();
-    };
-    // Metropolis rule :1367-1377 through the band of metropolis_accept(), without early-out branches
-    auto decide = [&](double dE, double ran, bool live) -> bool {
-        const double ea = (double) exp_neg_approx(dE * c.invT);
-        const bool down = dE <= 0;
-        const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
-        bool acc = down | acc_b;
-        if (live && !(down | acc_b | rej_b)) acc = metropolis_exact(dE, c.T, ran);
-        return acc && live;
-    };
-    auto commit = [&](double s6, double s12) {                // the nine totals of an accepted displacement
-        const double dE12 = 4 * s12, dE6 = 4 * s6;
-        const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
-        c.tot[0] += dE12 - dE6;  c.tot[2] += dE12; c.tot[4] += dE6;
-        c.tot[1] += dV12 - dV6; c.tot[3] += dV12; c.tot[5] += dV6;
-        c.tot[6] += dH12 - dH6; c.tot[7] += dH12; c.tot[8] += dH6;
+        return got;
     };
 
-    // Drawn but not yet executed trials (steps sn+1 ... sn+qn), at most four; the queue is the same in every group of the warp
-    uint32_t qnm[4], qw1[4], qw2[4], qn = 0;
-    const uint64_t sn_end = sn0 + count;
-    uint64_t drawn = sn;
-    auto refill = [&]() {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (qn == (uint32_t) k && drawn < sn_end) { draw(++drawn, qnm[k], qw1[k], qw2[k]); qn = k + 1; }
-    };
-    // Two consecutive trials of a chain that move DIFFERENT particles differ by one pair term only (the second trial
-    // sees the first particle at its old or at its new position), so both partner loops can run in one pass: half the
-    // hand-overs, rendezvous and loop overhead per step, and two independent dependency chains for the scheduler.
-    // Warp-uniform decision (the groups of a warp stay in lock-step): every group's next two trials are displacements of
-    // two different particles, and the first of the two steps is not one on which an ECheck / adjustment / relaxation is due.
-    auto pairable = [&](uint32_t nm_first, uint32_t nm_second, uint32_t have, uint32_t ev) -> bool {
-        if (NPL == 0 || have < 2 || ev < 2) return false;     // (run-time partner bounds: single steps only)
-        const bool ok = nm_first < c.N && nm_second < c.N && nm_first != nm_second;
-        return __all_sync(0xffffffffu, ok);
-    };
-
-    uint32_t n_acc = 0, n_rej = 0, done = 0;
+    uint32_t n_acc = 0, n_rej = 0;
+    uint32_t nm, w1, w2;
     __syncwarp();
-    refill();
-    bool pair = pairable(qnm[0], qnm[1], qn, ev_left);
-    double rnmA, rnmB;
-    handover(false, 0, 0.0, false, 0, 0.0, qnm[0] < c.N, qnm[0], pair, pair ? qnm[1] : 0u, rnmA, rnmB);
+    draw(sn + 1, nm, w1, w2);
+    bool disp = nm < c.N;
+    double rnm = handover(false, 0, 0.0, disp, nm);
 
-    while (done < count) {                                    // (the warp is converged here: every iteration ends in handover's rendezvous)
-        refill();                                             // the shuffles of the next trials' random numbers overlap the partner loops
-        const uint32_t nmA = qnm[0], nmB = qnm[1];
-        const bool dispA = nmA < c.N;
-        uint32_t n = 1;                                       // steps taken by this iteration
-        bool accA = false, accB = false;
-        double rTA = 0.0, rTB = 0.0;
-        uint8_t flagsA = 0, flagsB = 0;
-        if (pair) {
-            if constexpr (NPL > 0) {
-                n = 2;
-                rTA = rnmA + u01_shifted(qw1[0], 1.5) * 2 * c.maxStep;        // (rn - 0.5) * 2 * maxStep, :1182
-                rTB = rnmB + u01_shifted(qw1[1], 1.5) * 2 * c.maxStep;
-                const bool wallA = fabs(rTA) > c.half_l, wallB = fabs(rTB) > c.half_l;   // :1188
-                double rr[NPL];
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) rr[i] = c.r[c.lane + G * i];     // both moved particles read as far away
-                double s6A, s12A, s6B, s12B;
-                lanes_row_sums<POT, G, NPL>(c, rr, nmA, rnmA, rTA, s6A, s12A);
-                lanes_row_sums<POT, G, NPL>(c, rr, nmB, rnmB, rTB, s6B, s12B);
-                lanes_butterfly<G>(c.lane, s6A, s12A);
-                lanes_butterfly<G>(c.lane, s6B, s12B);
-                // the three pair terms the sentinels took out: B seen from trial A; A (old position) and A (new position)
-                // seen from trial B.  Signed distances in the reference's orientation (r[j] - r[i], j > i by index).
-                const bool BleftOfA = nmB < nmA;
-                double xa[3], xb[3], d6[3], t6[3];
-                xa[0] = BleftOfA ? rnmA - rnmB : rnmB - rnmA;   xb[0] = BleftOfA ? rTA - rnmB : rnmB - rTA;
-                xa[1] = BleftOfA ? rnmA - rnmB : rnmB - rnmA;   xb[1] = BleftOfA ? rnmA - rTB : rTB - rnmA;
-                xa[2] = BleftOfA ? rTA - rnmB : rnmB - rTA;     xb[2] = BleftOfA ? rTA - rTB : rTB - rTA;
-                lj_terms<POT == kPotLJcut, 3>(xa, xb, c.cutoff, d6, t6);
-                s6A += d6[0]; s12A = __fma_rn(d6[0], t6[0], s12A);
-                accA = decide(4 * s12A - 4 * s6A, u01_shifted(qw2[0], 1.0), !wallA);
-                const double d6x = accA ? d6[2] : d6[1], t6x = accA ? t6[2] : t6[1];
-                s6B += d6x; s12B = __fma_rn(d6x, t6x, s12B);
-                accB = decide(4 * s12B - 4 * s6B, u01_shifted(qw2[1], 1.0), !wallB);
-                if (accA) commit(s6A, s12A);
-                th.push(c);                                   // updateThermo of the first step :1805
-                if (th.fill == kThermoRing) th.flush(c);
-                if (accB) commit(s6B, s12B);
-                n_acc += (accA ? 1u : 0u) + (accB ? 1u : 0u);
-                n_rej += (accA ? 0u : 1u) + (accB ? 0u : 1u);
-                if (LOG) { flagsA = wallA ? kLogWall : (accA ? kLogAccepted : 0); flagsB = wallB ? kLogWall : (accB ? kLogAccepted : 0); }
-            }
-        } else {
-            // One step.  The whole warp runs the displacement code CONVERGED (full-mask shuffles: a per-group mask costs a
-            // MATCH + REDUX + VOTE per shuffle): a group whose trial is a volume trial computes a discarded dummy, a move
-            // through the wall is a predicate on the decision (:1188), not a branch around the pair terms.
-            n = 1;
-            rTA = rnmA + u01_shifted(qw1[0], 1.5) * 2 * c.maxStep;            // qad2 :1160-1464
-            const bool wall = fabs(rTA) > c.half_l;
+    for (uint32_t s = 0; s < count; ++s) {
+        ++sn;                                                 // (the warp is converged here: every iteration ends in handover's rendezvous)
+        const bool more = s + 1 < count;
+        uint32_t nm1 = 0, w11 = 0, w21 = 0;
+        if (more) draw(sn + 1, nm1, w11, w21);                // (uniform in the warp: every group runs `count` steps)
+        const bool disp1 = more && nm1 < c.N;
+
+        // The whole warp runs the displacement code CONVERGED (full-mask shuffles: a per-group mask costs a MATCH + REDUX +
+        // VOTE per shuffle): a group whose trial is a volume trial computes a discarded dummy, a move through the wall is
+        // a predicate on the decision (:1188), not a branch around the pair terms.
+        uint8_t flags = 0;
+        bool acc = false;
+        double rT;
+        {                                                     // qad2 :1160-1464
+            const double md = u01_shifted(w1, 1.5) * 2 * c.maxStep;     // (rn - 0.5) * 2 * maxStep, :1182
+            rT = rnm + md;
+            const bool wall = fabs(rT) > c.half_l;            // :1188
             double s6, s12;
-            lanes_partner_sums<POT, G, NPL>(c, dispA ? nmA : 0u, rnmA, rTA, s6, s12);
-            accA = decide(4 * s12 - 4 * s6, u01_shifted(qw2[0], 1.0), dispA && !wall);
-            if (accA) commit(s6, s12);
-            if (LOG) flagsA = (dispA && wall) ? kLogWall : (accA ? kLogAccepted : 0);
-            n_acc += accA ? 1u : 0u;
-            n_rej += (dispA && !accA) ? 1u : 0u;
-            if (!dispA) {                                     // volume trial: no sentinel is out, the row is consistent
-                const double rn = u01(qw1[0]), ran = u01(qw2[0]);
-                th.flush(c);                                  // (fav's ordered sums use the scratch next to the ring; rare anyway)
-                if constexpr (POT == kPotLJ) {
-                    flagsA = scaling_volume ? coop_volume_scaling(c, rn, ran) : coop_volume_full(c, rn, ran);
-                } else flagsA = coop_volume_full(c, rn, ran);
+            lanes_partner_sums<POT, G, NPL>(c, disp ? nm : 0u, rnm, rT, s6, s12);
+            const double dE12 = 4 * s12, dE6 = 4 * s6;
+            const double dE = dE12 - dE6;
+            // Metropolis rule :1367-1377 through the band of metropolis_accept(), without early-out branches
+            const double ran = u01_shifted(w2, 1.0);
+            const double ea = (double) exp_neg_approx(dE * c.invT);
+            const bool down = dE <= 0;
+            const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+            acc = down | acc_b;
+            if (disp && !wall && !(down | acc_b | rej_b)) acc = metropolis_exact(dE, c.T, ran);
+            acc = acc && disp && !wall;
+            if (acc) {
+                const double dV12 = 12 * dE12, dV6 = 6 * dE6, dH12 = 144 * dE12, dH6 = 36 * dE6;
+                c.tot[0] += dE;  c.tot[2] += dE12; c.tot[4] += dE6;
+                c.tot[1] += dV12 - dV6; c.tot[3] += dV12; c.tot[5] += dV6;
+                c.tot[6] += dH12 - dH6; c.tot[7] += dH12; c.tot[8] += dH6;
             }
-            __syncwarp();                                     // converged again
+            if (LOG) flags = (disp && wall) ? kLogWall : (acc ? kLogAccepted : 0);
+            n_acc += acc ? 1u : 0u;                           // (32-bit tallies, folded into the 64-bit counters at events)
+            n_rej += (disp && !acc) ? 1u : 0u;
         }
-        sn += n; done += n; ev_left -= n;
-        if (LOG && own && c.lane == 0) {
-            a.accept_log[(log_row0 + done - n) * C + chain] = flagsA;
-            if (n == 2) a.accept_log[(log_row0 + done - 1) * C + chain] = flagsB;
+        if (!disp) {                                          // volume trial: no sentinel is out, the row is consistent
+            const double rn = u01(w1), ran = u01(w2);
+            th.flush(c);                                      // (fav's ordered sums use the scratch next to the ring; rare anyway)
+            if constexpr (POT == kPotLJ) {
+                flags = scaling_volume ? coop_volume_scaling(c, rn, ran) : coop_volume_full(c, rn, ran);
+            } else flags = coop_volume_full(c, rn, ran);
         }
-        // what the iteration leaves in the row, and what the next one needs from it
-        const bool wrA = dispA, wrB = n == 2;
-        const double valA = accA ? rTA : rnmA, valB = accB ? rTB : rnmB;
-        const uint32_t have = qn - n;                         // trials already drawn for the next iteration
-        const uint32_t nxA = n == 2 ? qnm[2] : qnm[1], nxB = n == 2 ? qnm[3] : qnm[2];   // (no run-time indexing: registers)
-        if (ev_left != 0) {
-            th.push(c);                                       // updateThermo of the (last) step of this iteration
-            pair = pairable(nxA, nxB, have, ev_left);
-            handover(wrA, nmA, valA, wrB, nmB, valB, have >= 1 && nxA < c.N, nxA, pair, nxB, rnmA, rnmB);
+        __syncwarp();                                         // converged again
+
+        double rnm1;
+        if (--ev_left != 0) {
+            th.push(c);                                       // updateThermo :1805 (the state of this step; the sums follow in flush)
+            rnm1 = handover(disp, nm, acc ? rT : rnm, disp1, nm1);
             if (th.fill == kThermoRing) th.flush(c);
         } else {
-            double dummy0, dummy1;
-            handover(wrA, nmA, valA, wrB, nmB, valB, false, 0, false, 0, dummy0, dummy1);   // positions consistent for whatever is due now
+            handover(disp, nm, acc ? rT : rnm, false, 0);     // positions consistent for whatever is due now
             c.cnt[0] += n_acc; c.cnt[1] += n_rej; n_acc = n_rej = 0;
             th.flush(c);
             if (a.eci && sn % a.eci == 0) coop_energy_check(c);                        // Step :1800
@@ -340,15 +254,10 @@ __device__ __forceinline__ void lanes_run_chain(const ChainsDev &S, const StepAr
                 if (relax_on && sn % 10000 == 0 && sn < 1000000ull) coop_relax_volume(c);
             }
             ev_left = until_event();
-            __syncwarp();
-            pair = pairable(nxA, nxB, have, ev_left);
-            handover(false, 0, 0.0, false, 0, 0.0, have >= 1 && nxA < c.N, nxA, pair, nxB, rnmA, rnmB);
+            rnm1 = handover(false, 0, 0.0, disp1, nm1);
         }
-        // shift the queue by the trials just executed
-        if (n == 2) { qnm[0] = qnm[2]; qw1[0] = qw1[2]; qw2[0] = qw2[2]; qnm[1] = qnm[3]; qw1[1] = qw1[3]; qw2[1] = qw2[3]; }
-        else { qnm[0] = qnm[1]; qw1[0] = qw1[1]; qw2[0] = qw2[1]; qnm[1] = qnm[2]; qw1[1] = qw1[2]; qw2[1] = qw2[2];
-               qnm[2] = qnm[3]; qw1[2] = qw1[3]; qw2[2] = qw2[3]; }
-        qn = have;
+        if (LOG && own && c.lane == 0) a.accept_log[(log_row0 + s) * C + chain] = flags;
+        nm = nm1; w1 = w11; w2 = w21; rnm = rnm1; disp = disp1;
     }
 
     th.flush(c);
