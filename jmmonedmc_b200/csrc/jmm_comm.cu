@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,16 +31,23 @@ struct NcclApi {
     std::string error;
 };
 
-NcclApi *nccl_api() {
+void nccl_load(NcclApi &api);
+
+NcclApi *nccl_api() {                       // bound once per process, whichever thread asks first
     static NcclApi api;
-    if (api.lib || !api.error.empty()) return &api;
+    static std::once_flag once;
+    std::call_once(once, [] { nccl_load(api); });
+    return &api;
+}
+
+void nccl_load(NcclApi &api) {
     const char *names[] = {getenv("JMM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
         if (!n || !*n) continue;
         api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (api.lib) break;
     }
-    if (!api.lib) { api.error = std::string("cannot load NCCL (libnccl.so.2): ") + dlerror(); return &api; }
+    if (!api.lib) { api.error = std::string("cannot load NCCL (libnccl.so.2): ") + dlerror(); return; }
     auto sym = [&](const char *name) { void *p = dlsym(api.lib, name); if (!p) api.error = std::string("NCCL symbol missing: ") + name; return p; };
     api.GetUniqueId = (decltype(api.GetUniqueId)) sym("ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank)) sym("ncclCommInitRank");
@@ -48,7 +56,6 @@ NcclApi *nccl_api() {
     api.GetErrorString = (decltype(api.GetErrorString)) sym("ncclGetErrorString");
     api.GetVersion = (decltype(api.GetVersion)) sym("ncclGetVersion");
     if (!api.error.empty()) api.lib = nullptr;
-    return &api;
 }
 
 }  // namespace

@@ -27,6 +27,9 @@
 #ifndef JMM_SWEEP_UNROLL
 #define JMM_SWEEP_UNROLL 2        // iterations of the run-time partner loop in flight (two pair terms each)
 #endif
+#ifndef JMM_SWEEP_NS_MAX
+#define JMM_SWEEP_NS_MAX 160      // longest pause (ns) between two polls of the neighbour hand-shake; 0 = spin
+#endif
 #ifndef JMM_SWEEP_MAXT
 #define JMM_SWEEP_MAXT 768        // __launch_bounds__ of k_sweep_fast (register cap = 65536 / MAXT)
 #endif
@@ -419,7 +422,9 @@ __global__ void __launch_bounds__(JMM_SWEEP_MAXT, 1) k_sweep_fast(const __grid_c
                 // w_lo + j, one vote per poll, the pause doubling up to 160 ns
                 const int v = min(w_lo + lane32, w_hi);
                 unsigned ns = 20;
-                while (!__all_sync(0xffffffffu, ld_acquire_cta(done + v) >= t)) { __nanosleep(ns); ns = min(ns * 2, 160u); }
+                while (!__all_sync(0xffffffffu, ld_acquire_cta(done + v) >= t)) {
+                    if (JMM_SWEEP_NS_MAX > 0) { __nanosleep(ns); ns = min(ns * 2, (unsigned) JMM_SWEEP_NS_MAX); }
+                }
             }
 #endif
             // One Philox block serves the trials 2m and 2m+1 of a half-sweep (words 0,1 and 2,3).
