@@ -577,10 +577,6 @@ def roofline_fp64(E: Env, per_gpu_value: float, flop: float, kernel: str, k_ms, 
     return r
 
 
-C4_KERNEL = {"fast": "k_chains_step_prod_sliced (prod.cuh, one chain per thread) / k_chains_step_lanes (lanes.cuh, G lanes per chain) "
-                     "below 65 536 chains per GPU", "reference": "k_chains_step_prod_sliced (prod.cuh, reference arithmetic)"}
-
-
 def others_block(E: Env) -> dict:
     """C3, C4, C5 in both arithmetic modes, >= 1 s timed each; the fast lines carry e2e and a CPU side-by-side."""
     others = {}
