@@ -13,6 +13,10 @@ cannot run on today's output.  This module restates their arithmetic on the colu
   blocked_autocorrelation / lag_autocorrelation            scripts/Plot_AutoCorrelation.py:15-48
   sort_summary         scripts/Sort_Summary.bash           sort -k1,1g -k2,2g | uniq
 
+Pinned against the scripts themselves: tests/golden/make_golden_analysis.py runs Analyze_Mean.py, Analyze_A_SD.py and
+Plot_AutoCorrelation.py from /root/reference/scripts under a python-2 compatibility shim on a synthetic thermo file, and
+tests/test_analysis_cpu.py compares this module with what they computed.
+
 Host-side numpy only: none of this is on the Monte-Carlo hot path and nothing here touches the GPU.
 `python -m jmmonedmc_b200.analysis DIR` analyses every `P<P>_T<T>*/thermo.dat.mcs` under DIR (the layout of
 scripts/RunJobs.bash:27) and writes the tables into DIR.

@@ -151,3 +151,75 @@ def test_sweep_tables_from_batch_driver_files(tmp_path, thermo):
     srt = (tmp_path / "Summary_sorted.txt").read_text().splitlines()
     assert srt[0].startswith("0.3\t0.9") and srt[1].startswith("0.7\t0.9")
     assert (tmp_path / "DataBlockingResults.chain5.dat").exists()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pinned against the reference's OWN scripts: tests/golden/analysis_scripts holds what scripts/Analyze_Mean.py,
+# Analyze_A_SD.py and Plot_AutoCorrelation.py (read from /root/reference/scripts, run under a python-2 compatibility shim,
+# tests/golden/make_golden_analysis.py) computed on a synthetic thermo file; analysis.py gets the same numbers in the
+# writer's 13-column format.
+SCRIPTS = GOLD / "analysis_scripts"
+
+
+@pytest.fixture(scope="module")
+def script_gold():
+    import json
+    return json.loads((SCRIPTS / "golden.json").read_text())
+
+
+def test_means_and_response_functions_equal_analyze_mean_py(script_gold):
+    g = script_gold["Analyze_Mean"]
+    thermo = A.read_thermo(SCRIPTS / "mean_thermo.dat.mcs")
+    m = A.run_means(thermo, eq_steps=g["eq_steps"], le_start_steps=g["le_start_steps"], interval=g["interval"])
+    header, row = g["LJ_Means.dat"].strip().splitlines()
+    assert header.split("\t") == ["P", "T", "Energy", "Energy2", "Length", "Length2", "LengthEnergy"]          # Analyze_Mean.py:64
+    want = [float(x) for x in row.split("\t")]
+    got = [g["P"], g["T"], m["Energy"], m["Energy2"], m["Length"], m["Length2"], m["LengthEnergy"]]
+    assert np.allclose(got, want, rtol=1e-14, atol=0)
+    t = A.after_equilibration(thermo, g["eq_steps"], g["interval"])
+    bm = A.block_means(t, g["block_size"], g["interval"])
+    plots = g["plots"]
+    assert bm.shape[0] == len(plots["L"]["y"]) == 7
+    lb = g["LEstartBlock"]                                                   # the LE-dependent plots start at this block (:105)
+    assert np.allclose(bm[:, 0], plots["L"]["x"], rtol=1e-14) and np.allclose(bm[:, 3], plots["L"]["y"], rtol=1e-14)
+    assert np.allclose(bm[lb:, 1] * g["epsilon"], plots["E_times_epsilon"]["y"], rtol=1e-13)
+    assert np.allclose(bm[lb:, 2], plots["E2"]["y"], rtol=1e-14) and np.allclose(bm[:, 4], plots["L2"]["y"], rtol=1e-14)
+    assert np.allclose(bm[lb:, 7], plots["LE"]["y"], rtol=1e-14)
+    rf = A.response_functions(g["P"], g["T"], bm[:, 1], bm[:, 2], bm[:, 3], bm[:, 4], bm[:, 7])
+    # differences of large numbers (E2 - E E ~ 30 against 2.3e6): compare at the accuracy the cancellation leaves
+    for name, sl in (("cp", slice(lb, None)), ("betaT", slice(None)), ("betaS", slice(lb, None)), ("alphaP", slice(lb, None)),
+                     ("gammaV", slice(lb, None)), ("muJT", slice(lb, None))):
+        assert np.allclose(rf[name][sl], plots[name]["y"], rtol=1e-9, atol=0), name
+
+
+@pytest.mark.parametrize("case", ["with_uncorrelated_block", "scan_only"])
+def test_data_blocking_equals_analyze_a_sd_py(script_gold, case, tmp_path):
+    g = script_gold["Analyze_A_SD:" + case]
+    thermo = A.read_thermo(SCRIPTS / "sd_thermo.dat.mcs")
+    stderrs, summary = A.data_blocking(thermo, eq_steps=g["eq_steps"], uncorrelated_block_size=g["uncorrelated_block_size"],
+                                       le_start_steps=g["le_start_steps"])
+    A.write_data_blocking(tmp_path / "DataBlockingResults.dat", stderrs)
+    got = (tmp_path / "DataBlockingResults.dat").read_text().splitlines()
+    want = g["DataBlockingResults.dat"].splitlines()
+    assert got[0] == want[0] and len(got) == len(want)                                   # header and block-size ladder
+    G = np.array([[float(x) for x in l.split("\t")] for l in got[1:]]); W = np.array([[float(x) for x in l.split("\t")] for l in want[1:]])
+    assert np.array_equal(G[:, :2], W[:, :2]) and np.allclose(G, W, rtol=1e-9)           # (files hold 10 significant digits)
+    rows = g["Summary_SD_tmp.txt"].strip().splitlines()
+    assert rows[0].split("\t") == ["N", "P", "T", "blockSize", "numBlocks", "SEM_Energy", "SEM_EnergySq", "SEM_Length", "SEM_LengthSq", "SEM_LE"]
+    if case == "with_uncorrelated_block":
+        f = rows[1].split("\t")
+        assert [int(f[3]), int(f[4])] == [int(summary[0]), int(summary[1])]
+        assert np.allclose([float(x) for x in f[5:]], summary[2:], rtol=1e-12)
+    else:
+        assert len(rows) == 1 and summary is None
+
+
+def test_autocorrelations_equal_plot_autocorrelation_py(script_gold):
+    g = script_gold["Plot_AutoCorrelation"]
+    x = np.array(g["x"])
+    want_b, want_l = np.array(g["blocked"], dtype=float), np.array(g["lag"], dtype=float)
+    got_b, got_l = A.blocked_autocorrelation(x), A.lag_autocorrelation(x)
+    assert got_b.shape == want_b.shape and got_l.shape == want_l.shape
+    ok = np.isfinite(want_b)                                                  # two blocks: corrcoef of single points is nan in both
+    assert np.array_equal(np.isfinite(got_b), ok) and np.allclose(got_b[ok], want_b[ok], rtol=1e-12, atol=1e-14)
+    assert np.allclose(got_l, want_l, rtol=1e-12, atol=1e-14)
