@@ -33,38 +33,64 @@ namespace jmm {
 #endif
 constexpr int kLanesMaxWarps = JMM_LANES_MAXW;   // 12 warps per CTA = 168 registers per thread (16 = 128: spills)
 
-// The partner sums of one displacement trial: s6 = sum(b^-6 - a^-6), s12 = sum(b^-12 - a^-12) over the partners of
-// `nm`, strided over the G lanes and closed by an xor butterfly (identical bits in every lane of the group).
-// The slot of the moved particle holds kFarAway while this runs (see lanes_run_chain), so there is no per-partner
-// index test.  NPL > 0: every lane visits exactly NPL slots p = lane + G i of a row padded to NPL*G positions (pads
-// hold kFarAway for ever); needs NBN < 0.  NPL == 0: run-time bounds (NBN >= 0 or an unusual N).
+// Two sums over the G lanes with one value per lane after the first exchange: even lanes carry s12, odd lanes s6
+// (log2 G + 1 shuffles of ONE double instead of log2 G of two).  Commutative additions: every lane of the group ends up
+// with the same bits.  Full-warp mask: the callers keep the warp converged here.
+template <int G>
+__device__ __forceinline__ void lanes_butterfly(uint32_t lane, double &s6, double &s12) {
+    if constexpr (G == 1) return;
+    const bool odd = lane & 1;
+    const double give = odd ? s12 : s6, keep = odd ? s6 : s12;
+    double v = keep + __shfl_xor_sync(0xffffffffu, give, 1, G);
+#pragma unroll
+    for (int o = 2; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    const double other = __shfl_xor_sync(0xffffffffu, v, 1, G);
+    s12 = odd ? other : v;
+    s6 = odd ? v : other;
+}
+
+// This lane's share of the partner sums of one displacement trial: s6 = sum(b^-6 - a^-6), s12 = sum(b^-12 - a^-12) over
+// the NPL slots p = lane + G i of the (padded) row held in rr[].  The slot of the moved particle holds kFarAway while
+// this runs, so there is no per-partner index test.  (Also the loop warps of team.cuh.)
+template <int POT, int G, int NPL>
+__device__ __forceinline__ void lanes_row_sums(const Coop<POT, G> &c, const double (&rr)[NPL], uint32_t nm, double rnm, double rT,
+                                               double &s6, double &s12) {
+    double a[NPL], b[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const double r = rr[i];
+        if constexpr (POT == kPotLJcut) {
+            const bool left = c.lane + G * i < nm;
+            a[i] = left ? rnm - r : r - rnm; b[i] = left ? rT - r : r - rT;
+        } else { a[i] = r - rnm; b[i] = r - rT; }
+    }
+    s6 = 0; s12 = 0;
+    constexpr int H = NPL > 10 ? NPL / 2 : NPL;               // at most ten chains in flight (registers)
+    if constexpr (H == NPL) lj_partners<POT == kPotLJcut, NPL>(a, b, c.cutoff, s6, s12);
+    else {
+        double a1[H], b1[H], a2[NPL - H], b2[NPL - H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) { a1[i] = a[i]; b1[i] = b[i]; }
+#pragma unroll
+        for (int i = H; i < NPL; ++i) { a2[i - H] = a[i]; b2[i - H] = b[i]; }
+        lj_partners<POT == kPotLJcut, H>(a1, b1, c.cutoff, s6, s12);
+        lj_partners<POT == kPotLJcut, NPL - H>(a2, b2, c.cutoff, s6, s12);
+    }
+}
+
+// The partner sums of one displacement trial, strided over the G lanes and closed by the butterfly (identical bits in
+// every lane of the group).  NPL > 0: every lane visits exactly NPL slots of a row padded to NPL*G positions (pads hold
+// kFarAway for ever); needs NBN < 0.  NPL == 0: run-time bounds (NBN >= 0 or an unusual N).
 template <int POT, int G, int NPL>
 __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32_t nm, double rnm, double rT, double &s6, double &s12) {
     static_assert(POT != kPotHarmonic, "fast arithmetic is an LJ-family optimisation");
-    s6 = 0; s12 = 0;
     if constexpr (NPL > 0) {
-        double a[NPL], b[NPL];
+        double rr[NPL];
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-            const uint32_t p = c.lane + G * i;
-            const double r = c.r[p];
-            if constexpr (POT == kPotLJcut) {
-                const bool left = p < nm;
-                a[i] = left ? rnm - r : r - rnm; b[i] = left ? rT - r : r - rT;
-            } else { a[i] = r - rnm; b[i] = r - rT; }
-        }
-        constexpr int H = NPL > 10 ? NPL / 2 : NPL;           // at most ten chains in flight (registers)
-        if constexpr (H == NPL) lj_partners<POT == kPotLJcut, NPL>(a, b, c.cutoff, s6, s12);
-        else {
-            double a1[H], b1[H], a2[NPL - H], b2[NPL - H];
-#pragma unroll
-            for (int i = 0; i < H; ++i) { a1[i] = a[i]; b1[i] = b[i]; }
-#pragma unroll
-            for (int i = H; i < NPL; ++i) { a2[i - H] = a[i]; b2[i - H] = b[i]; }
-            lj_partners<POT == kPotLJcut, H>(a1, b1, c.cutoff, s6, s12);
-            lj_partners<POT == kPotLJcut, NPL - H>(a2, b2, c.cutoff, s6, s12);
-        }
+        for (int i = 0; i < NPL; ++i) rr[i] = c.r[c.lane + G * i];
+        lanes_row_sums<POT, G, NPL>(c, rr, nm, rnm, rT, s6, s12);
     } else {
+        s6 = 0; s12 = 0;
         const uint32_t N = c.N;
         const uint32_t lo = (c.nbn < 0 || (uint32_t) c.nbn > nm) ? 0u : nm - (uint32_t) c.nbn;
         const uint32_t hi = (c.nbn < 0 || nm + (uint32_t) c.nbn > N - 1) ? N - 1 : nm + (uint32_t) c.nbn;
@@ -78,20 +104,9 @@ __device__ __forceinline__ void lanes_partner_sums(const Coop<POT, G> &c, uint32
                 lj_partner<false>(r - rnm, r - rT, c.cutoff, s6, s12);
             }
         }
+        __syncwarp();                             // (run-time partner bounds: the groups may have left the loop apart)
     }
-    // Two sums over the G lanes with one value per lane after the first exchange: even lanes carry s12, odd lanes s6
-    // (G + 2 log2 G... shuffles of one double instead of two per round).  Commutative additions: every lane of the group
-    // ends up with the same bits.  Full-warp mask: the step loop keeps the warp converged here (lanes_run_chain).
-    if constexpr (G == 1) return;
-    if constexpr (NPL == 0) __syncwarp();         // (run-time partner bounds: the groups may have left the loop apart)
-    const bool odd = c.lane & 1;
-    const double give = odd ? s12 : s6, keep = odd ? s6 : s12;
-    double v = keep + __shfl_xor_sync(0xffffffffu, give, 1, G);
-#pragma unroll
-    for (int o = 2; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
-    const double other = __shfl_xor_sync(0xffffffffu, v, 1, G);
-    s12 = odd ? other : v;
-    s6 = odd ? v : other;
+    lanes_butterfly<G>(c.lane, s6, s12);
 }
 
 // One chain (the G lanes of its group) advanced by `count` steps starting after step sn0.

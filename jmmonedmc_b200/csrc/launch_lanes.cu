@@ -3,6 +3,7 @@
 
 #include "handle.h"
 #include "lanes.cuh"
+#include "team.cuh"
 
 using namespace jmm;
 
@@ -46,6 +47,40 @@ static cudaError_t launch_lanes_npl(jmm_handle *h, const StepArgs &a) {
     return cudaGetLastError();
 }
 
+// team.cuh: eight loop warps + one bookkeeper warp per 32 chains (N in 73 ... 80, NBN < 0)
+template <int POT>
+static cudaError_t launch_team(jmm_handle *h, const StepArgs &a) {
+    constexpr int NT = 2;                                        // teams per CTA (18 warps, one CTA per SM)
+    auto kern = a.accept_log ? k_chains_step_team<POT, NT, true> : k_chains_step_team<POT, NT, false>;
+    cudaError_t e;
+    const unsigned ntiles = nblk(h->S.nchains, kTeamChains);
+    const size_t smem = NT * sizeof(TeamShared);
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
+    int per_sm = 0, nsm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT * kTeamWarps * 32, smem)) != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const unsigned ctas = (unsigned) std::max(1, per_sm * nsm);
+    const unsigned slots = ctas * NT;
+    const double waves = (double) ntiles / slots;
+    const double fill = waves / ceil(waves);
+    uint32_t chunk = (uint32_t) a.nsteps;
+    if ((getenv("JMM_FORCE_SLICE") || (fill < 0.93 && ntiles > (unsigned) nsm)) && !getenv("JMM_NO_SLICE") && a.nsteps >= 16)
+        chunk = (uint32_t) std::max<uint64_t>(8, (a.nsteps + 11) / 12);
+    if (const char *ev = getenv("JMM_SLICE_CHUNK")) chunk = (uint32_t) std::max(1, atoi(ev));
+    const uint32_t nchunks = (uint32_t) ((a.nsteps + chunk - 1) / chunk);
+    if (h->work_words < (size_t) ntiles + 1) {
+        if (h->d_work) cudaFree(h->d_work);
+        h->d_work = nullptr; h->work_words = 0;
+        if ((e = cudaMalloc((void **) &h->d_work, ((size_t) ntiles + 1) * sizeof(unsigned int))) != cudaSuccess) return e;
+        h->work_words = (size_t) ntiles + 1;
+    }
+    if ((e = cudaMemsetAsync(h->d_work, 0, ((size_t) ntiles + 1) * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
+    const unsigned grid = std::min(ctas, nblk((uint64_t) ntiles * nchunks, NT));
+    kern<<<grid, NT * kTeamWarps * 32, smem, h->stream>>>(h->S, a, chunk, ntiles, nchunks, h->d_work, h->d_work + 1);
+    h->launches++;
+    return cudaGetLastError();
+}
+
 template <int POT, int G>
 static cudaError_t launch_lanes_g(jmm_handle *h, const StepArgs &a) {
     // the fully unrolled partner loop exists for one row length per G (N in (G (NPL-1), G NPL], NBN < 0): the
@@ -82,6 +117,10 @@ void jmm_lanes_shape(jmm_handle *h, int g) {
 }
 
 cudaError_t jmm_launch_lanes(jmm_handle *h, const StepArgs &a) {
+    // warp-specialised teams (team.cuh) for the shape they are built for; JMM_TEAM=0/1 overrides
+    bool team = h->lanes_g == 8 && h->lanes_npl == kTeamNPL;
+    if (const char *e = getenv("JMM_TEAM")) team = team && atoi(e) != 0; else team = false;   // (opt-in until measured)
+    if (team) return h->cfg.pot == JMM_POT_LJ ? launch_team<kPotLJ>(h, a) : launch_team<kPotLJcut>(h, a);
     if (h->cfg.pot == JMM_POT_LJ) return launch_lanes_pot<kPotLJ>(h, a);
     return launch_lanes_pot<kPotLJcut>(h, a);
 }

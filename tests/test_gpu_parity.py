@@ -292,7 +292,7 @@ SWEEP_DECK = dict(N=80, POT="LJ", NBN=-1, CUTOFF=math.inf, ENSEMBLE="NPT", P=0.5
 
 
 @pytest.mark.parametrize("engine", ["prod-reference", "sliced-reference", "coop8-reference", "prod-fast", "sliced-fast",
-                                    "lanes8-fast", "lanes4-fast", "lanes8sliced-fast", "lanes16-fast", "lanes2-fast"])
+                                    "lanes8-fast", "lanes4-fast", "lanes8sliced-fast", "lanes16-fast", "lanes2-fast", "team-fast", "teamsliced-fast"])
 @pytest.mark.parametrize("start", ["from0", "from1e6"])
 def test_sweep_shape_matches_oracle(J, O, engine, start, monkeypatch):
     """The shape bench.py times as C4 (RunJobs deck: N = 80, LJ, NBN -1, NPT, RELAX, ENGCHECK 10000; per-chain P, T set
@@ -307,7 +307,9 @@ def test_sweep_shape_matches_oracle(J, O, engine, start, monkeypatch):
            "coop8": {"JMM_COOP_G": "8"},
            "lanes8": {"JMM_LANES_G": "8"}, "lanes4": {"JMM_LANES_G": "4"}, "lanes16": {"JMM_LANES_G": "16"},
            "lanes2": {"JMM_LANES_G": "2"},
-           "lanes8sliced": {"JMM_LANES_G": "8", "JMM_FORCE_SLICE": "1", "JMM_SLICE_CHUNK": "97"}}[eng]
+           "lanes8sliced": {"JMM_LANES_G": "8", "JMM_FORCE_SLICE": "1", "JMM_SLICE_CHUNK": "97"},
+           "team": {"JMM_LANES_G": "8", "JMM_TEAM": "1"},                     # team.cuh: 7 loop warps + a bookkeeper warp per 28 chains
+           "teamsliced": {"JMM_LANES_G": "8", "JMM_TEAM": "1", "JMM_FORCE_SLICE": "1", "JMM_SLICE_CHUNK": "97"}}[eng]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     d = SWEEP_DECK
@@ -698,16 +700,17 @@ def test_consistent_virial_flag_changes_only_the_virial_bookkeeping(J, O, engine
         J.Handle(jmm_config_from_deck(J, d, rng_kind=J.RNG_TAUS2, mode=J.MODE_TABLE, flags=J.FLAG_CONSISTENT_VIRIAL))
 
 
-@pytest.mark.parametrize("g", ["2", "4", "8", "16"])
+@pytest.mark.parametrize("g", ["2", "4", "8", "16", "team"])
 @pytest.mark.parametrize("pot,N", [("LJcut", 78), ("LJ", 73)])
-def test_lanes_paired_steps_with_padded_rows_match_oracle(J, O, pot, N, g, monkeypatch):
-    """lanes.cuh with the unrolled partner loop (NBN -1, N in (G (NPL-1), G NPL]): rows padded with far-away slots
-    (N = 78 and 73 against 80 slots), two commuting trials per loop iteration (the pair terms between the two moved
-    particles evaluated apart, in the reference's orientation: LJcut's `d <= cutOff` is a test on the SIGNED distance,
-    src/pot.cpp:53), volume trials through fav with the lean ordered sums (LJcut) or qavLJ (LJ), ECheck every 50 steps,
-    device-side adjustments off (DADJ/VADJ beyond the run).  Every chain against the oracle: accept sequence, positions,
-    box and counters bit-identical; totals and sums to 1e-12."""
-    monkeypatch.setenv("JMM_LANES_G", g)
+def test_lanes_with_padded_rows_match_oracle(J, O, pot, N, g, monkeypatch):
+    """lanes.cuh / team.cuh with the unrolled partner loop (NBN -1, N in (G (NPL-1), G NPL]): rows padded with far-away
+    slots (N = 78 and 73 against 80 slots), LJcut's `d <= cutOff` on the SIGNED distance in the reference's orientation
+    (src/pot.cpp:53), volume trials through fav (LJcut) or qavLJ (LJ), ECheck every 50 steps, device-side adjustments off
+    (DADJ/VADJ beyond the run).  Every chain against the oracle: accept sequence, positions, box and counters
+    bit-identical; totals and sums to 1e-12."""
+    monkeypatch.setenv("JMM_LANES_G", "8" if g == "team" else g)
+    if g == "team":
+        monkeypatch.setenv("JMM_TEAM", "1")
     d = dict(N=N, POT=pot, NBN=-1, CUTOFF=2.5 if pot == "LJcut" else math.inf, ENSEMBLE="NPT", P=0.6, T=0.8, MAXSTEP=0.12, MAXDV=1.5,
              ENGCHECK=50, DADJ=10 ** 6, VADJ=10 ** 6, SEED=4242, RELAX=0)
     C, nsteps, id0 = 11, 1200, 77
