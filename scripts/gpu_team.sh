@@ -23,12 +23,10 @@ b "8192 team"                JMM_BENCH_CHAINS=8192 JMM_BENCH_PER_STEP=5000 JMM_T
 b "8192 team sliced"         JMM_BENCH_CHAINS=8192 JMM_BENCH_PER_STEP=5000 JMM_TEAM=1 JMM_FORCE_SLICE=1
 b "16384 lanes G=4"          JMM_BENCH_CHAINS=16384 JMM_BENCH_PER_STEP=5000
 b "16384 team"               JMM_BENCH_CHAINS=16384 JMM_BENCH_PER_STEP=5000 JMM_TEAM=1 JMM_LANES_G=8
-b "32768 lanes G=2"          JMM_BENCH_CHAINS=32768 JMM_BENCH_PER_STEP=5000
-b "32768 team"               JMM_BENCH_CHAINS=32768 JMM_BENCH_PER_STEP=5000 JMM_TEAM=1 JMM_LANES_G=8
 b "8192 team from0"          JMM_BENCH_CHAINS=8192 JMM_BENCH_PER_STEP=10000 JMM_BENCH_FROM_ZERO=1 JMM_TEAM=1
 JMM_TEAM=1 JMM_BENCH_CHAINS=8192 JMM_BENCH_PER_STEP=2000 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_team -s 1 -c 1 -f -o $OUT/prof_c4team_$TAG \
     python bench.py --workload c4 --arith fast --steps 1 --warmup 3 --no-cpu --no-e2e --min-seconds 0 > $OUT/ncu_c4team_$TAG.log 2>&1; tail -1 $OUT/ncu_c4team_$TAG.log | cut -c1-200
-python scripts/ncu_summary.py $OUT/prof_c4team_$TAG.ncu-rep 1172000 > $OUT/prof_c4team_$TAG.txt 2>&1
-python scripts/ncu_lines.py $OUT/prof_c4team_$TAG.ncu-rep 1172000 60 >> $OUT/prof_c4team_$TAG.txt 2>&1
+python scripts/ncu_summary.py $OUT/prof_c4team_$TAG.ncu-rep 4102000 > $OUT/prof_c4team_$TAG.txt 2>&1
+python scripts/ncu_lines.py $OUT/prof_c4team_$TAG.ncu-rep 4102000 60 >> $OUT/prof_c4team_$TAG.txt 2>&1
 rm -f $OUT/prof_c4team_$TAG.ncu-rep
 tail -5 $OUT/bench_$TAG.err
