@@ -322,7 +322,8 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
                 C <= 16384 && !(eb && atoi(eb) == 0))
                 // 1 = k_chains_step_bond (default: 4.43e9 trials/s on C2), 2 = k_chains_step_bond2 (registers-only, deferred
                 // ECheck: 3.99e9 — fewer rendezvous but no fewer instructions, profiles/r2e_c2_*; kept selectable, parity-tested)
-                h->bond = (eb && atoi(eb) == 2) ? 2 : 1;
+                // 3 = k_chains_step_solo (solo.cuh: one chain per thread, a warp per SM)
+                h->bond = (eb && (atoi(eb) == 2 || atoi(eb) == 3)) ? atoi(eb) : 1;
         }
     }
     CKH(cudaStreamSynchronize(h->stream));

@@ -5,6 +5,7 @@
 #include "handle.h"
 #include "coop.cuh"
 #include "bond.cuh"
+#include "solo.cuh"
 
 using namespace jmm;
 
@@ -29,6 +30,18 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
     unsigned threads = 128;
     if (const char *e = getenv("JMM_BOND_BLOCK")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) threads = (unsigned) v; }
     const unsigned per_block = threads / kB2G;
+    if (h->bond == 3) {
+        // k_chains_step_solo: one chain per thread, one warp per CTA (4096 chains = 128 CTAs: a warp per SM)
+        const bool ten = h->S.N == 10;
+        void (*kern)(ChainsDev, StepArgs);
+        if (a.accept_log) kern = inf ? (ten ? k_chains_step_solo<10, true, true> : k_chains_step_solo<0, true, true>)
+                                     : (ten ? k_chains_step_solo<10, true, false> : k_chains_step_solo<0, true, false>);
+        else kern = inf ? (ten ? k_chains_step_solo<10, false, true> : k_chains_step_solo<0, false, true>)
+                        : (ten ? k_chains_step_solo<10, false, false> : k_chains_step_solo<0, false, false>);
+        kern<<<nblk(h->S.nchains, 32), 32, (size_t) h->S.N * 32 * sizeof(double), h->stream>>>(h->S, a);
+        h->launches++;
+        return cudaGetLastError();
+    }
     if (h->bond == 2) {
         // k_chains_step_bond2: the shared row only parks the positions for the rare paths; the thermo ring follows it
         int npad = (int) ((h->S.N + 1) & ~1ull) + kThermoRing * kThermoSlots;

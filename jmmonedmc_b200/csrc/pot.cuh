@@ -104,10 +104,19 @@ __device__ __forceinline__ bool metropolis_accept(double dE, double T, double in
 //   exp(A): exp_neg_approx above, relative error <= 1.6e-7 |A| + 2.4e-7;
 // so |b - bf| <= bf (1.8e-7 N + 1.6e-7 |A| + 2.4e-7).  Four times that is the band; inside it (<= ~1e-5 of the volume
 // trials) the reference expression is evaluated.  NaN fails both comparisons and reaches the exact test, like every
-// s outside (0.5, 2).
+// s outside the window below.
 static __device__ __noinline__ bool volume_accept_exact(double x, double T, double n, double s, double ran) {
     const double bf = exp(-x / T + n * log(s));
     return bf >= 1.0 || bf > ran;
+}
+
+// The band is valid for 2^-6 < s < 2^6: lg2.approx is good to 2^-22.6 absolute on the mantissa part for any normal
+// input, the float result rounds at 2^-24 |log2 s|, and the input rounding (float) s moves ln s by 2^-24, together
+// <= 1.8e-7 + 4.2e-8 |log2 s| on ln s.  (The deck's own maxDVAdjust lets maxdl grow to N/2, :2136, so that a quarter of the
+// volume trials of INPUTstd have s < 0.5: with the (0.5, 2) window of the first version they all paid for exp and log.)
+constexpr double kVolumeBandLo = 0.015625, kVolumeBandHi = 64.0;
+__device__ __forceinline__ double volume_accept_band(double n, double lg, double A) {
+    return 4.0 * ((1.8e-7 + 4.2e-8 * fabs(lg)) * n + 1.6e-7 * fabs(A) + 2.4e-7);
 }
 
 __device__ __forceinline__ bool volume_accept(double x /* dE + P dl */, double T, double invT, double n, double s, double ran) {
@@ -115,8 +124,8 @@ __device__ __forceinline__ bool volume_accept(double x /* dE + P dl */, double T
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float) s));
     const double A = n * ((double) lg * 0.6931471805599453) - x * invT;
     const double b = (double) exp_neg_approx(-A);
-    const double band = 4.0 * (1.8e-7 * n + 1.6e-7 * fabs(A) + 2.4e-7);
-    const bool narrow = s > 0.5 && s < 2.0;
+    const double band = volume_accept_band(n, (double) lg, A);
+    const bool narrow = s > kVolumeBandLo && s < kVolumeBandHi;
     if (narrow && ran < b * (1.0 - band)) return true;
     if (narrow && ran > b * (1.0 + band)) return false;
     return volume_accept_exact(x, T, n, s, ran);

@@ -27,10 +27,8 @@ JMM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 JMM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int round = 0; round < 10; ++round) {
-        // (one 32 x 32 -> 64 multiply per product: IMAD.WIDE.U32 instead of an IMAD.HI + IMAD pair)
-        const uint64_t p0 = (uint64_t) 0xD2511F53u * c0, p1 = (uint64_t) 0xCD9E8D57u * c2;
-        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t) p0;
-        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t) p1;
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
@@ -52,10 +50,8 @@ JMM_HD PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
 JMM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &K) {
 #pragma unroll
     for (int round = 0; round < 10; ++round) {
-        // (one 32 x 32 -> 64 multiply per product: IMAD.WIDE.U32 instead of an IMAD.HI + IMAD pair)
-        const uint64_t p0 = (uint64_t) 0xD2511F53u * c0, p1 = (uint64_t) 0xCD9E8D57u * c2;
-        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t) p0;
-        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t) p1;
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = hi1 ^ c1 ^ K.k[2 * round], n2 = hi0 ^ c3 ^ K.k[2 * round + 1];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }

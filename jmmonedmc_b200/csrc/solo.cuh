@@ -1,0 +1,286 @@
+// k_chains_step_solo — nearest-neighbour bond chains (HARMONIC, NBN 1: the INPUTstd shape, BASELINE config 2) with ONE
+// CHAIN PER THREAD and ONE WARP PER SM.
+//
+// k_chains_step_bond (bond.cuh) gives a chain 16 lanes: 2048 warps for 4096 chains, but almost everything a step does
+// is a scalar of the chain, so 346 warp instructions serve TWO chain-steps and a warp sharing its sub-partition with
+// 3.3 others issues one of them every 5.3 cycles: 1830 cycles per step, whatever the lanes do.  What bounds a launch
+// of 4096 serial Markov chains is the LATENCY of one step, and the cheapest step is the one in which the 32 lanes of a
+// warp do 32 different chains' work with one instruction stream:
+//   * one chain per lane, positions in a [N][32] shared-memory tile (lane = column: conflict-free at any nm);
+//   * no divergence: displacement trial, volume trial (fav) and energy check are straight-line code with selects,
+//     every lane evaluates all of it every step (a warp of 32 chains has a volume trial at 95 % of the steps anyway)
+//     and commits under a predicate; only the 2e-5 events (a Metropolis or volume decision inside the approximation
+//     band, an energy discrepancy) branch, warp-uniformly;
+//   * a warp has a sub-partition (a whole SM) to itself, so the step time is the dependent-issue latency of the
+//     stream divided by the instruction-level parallelism in it — four independent bond terms in the trial, nine in
+//     fav, nine in the check, ten sums, and the Philox block of the NEXT step, which depends on nothing;
+//   * every sum is taken by the thread in the reference's order (pair index order, left and right partner apart,
+//     (acc - old) + new): there is no cross-lane arithmetic at all, so the result is bit-identical to the oracle by
+//     construction, like chains.cuh's.
+// Reference: Step :1758-1811, qad2 :1160-1464 (NBN 1), fav :2161-2293, ECheck :1965-2095, updateThermo :1941-1961,
+// maxDisAdjust / maxDVAdjust :2100-2139 (src/jmmMCState.cpp), phiHarmoniccut src/pot.cpp:110-134.
+#pragma once
+#include "bond.cuh"
+
+namespace jmm {
+
+// NT > 0: N is a compile-time constant (loops unrolled, scaled positions in registers); NT == 0: any N
+template <int NT, bool LOG, bool INF>
+__global__ void __launch_bounds__(32) k_chains_step_solo(ChainsDev S, StepArgs a) {
+    extern __shared__ double solo_smem[];                 // [N][32]
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x;
+    const uint64_t C = S.nchains;
+    const uint64_t c_raw = (uint64_t) blockIdx.x * 32 + lane;
+    const bool own = c_raw < C;
+    const uint64_t chain = own ? c_raw : C - 1;           // (lanes past the last chain shadow it, unsaved)
+    const uint32_t N = NT ? (uint32_t) NT : (uint32_t) S.N;
+    constexpr int NR = NT ? NT : 1;
+    double *r = solo_smem + lane;                         // particle i: r[i * 32]
+
+    double l = S.l[chain], maxStep = S.maxStep[chain], maxdl = S.maxdl[chain];
+    const double P = S.P[chain], T = S.T[chain], invT = 1.0 / T, cutoff = S.cutoff;
+    double half_l = l / 2.0, rho = (double) N / l, two_over_l = 2 / l;
+    double E = S.tot[chain], Vir = S.tot[C + chain];
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = S.acc[k * C + chain];
+    uint64_t cnt[kNCnt];
+#pragma unroll
+    for (int k = 0; k < kNCnt; ++k) cnt[k] = S.cnt[k * C + chain];
+    uint64_t vAErr = S.vAErr[chain], echecks = S.echeck[chain], discrepancies = S.echeck[C + chain];
+    uint32_t t_dacc = 0, t_drej = 0, t_vacc = 0, t_vrej = 0, t_checks = 0;   // 32-bit tallies, folded at adjustments and at the end
+#pragma unroll
+    for (uint32_t i = 0; i < N; ++i) r[i * 32] = S.r[(uint64_t) i * C + chain];
+
+    const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32), cid = (uint32_t)(S.chain_id0 + chain);
+    const uint32_t ntt = (uint32_t) S.numTrialTypes, scale = 0xffffffffu / ntt;
+    uint64_t sn = a.sn0;
+    auto until = [&](uint64_t every) -> uint32_t {
+        if (!every) return 0xffffffffu;
+        const uint64_t left = every - sn % every;
+        return left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left;
+    };
+    uint32_t eci_left = until(a.eci);
+    uint32_t mdai_left = a.adapt_device ? until(a.mdai) : 0xffffffffu;
+    uint32_t mvai_left = a.adapt_device ? until(a.mvai) : 0xffffffffu;
+    const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
+    const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
+    const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
+    uint32_t adapt_span = min(mdai_left, mvai_left), adapt_left = adapt_span;
+
+    auto draw = [&](uint64_t step, uint32_t &nm, uint32_t &w1, uint32_t &w2) {
+        const Philox4 b = philox4x32_10((uint32_t) step, (uint32_t)(step >> 32), cid, kTagTrial, k0, k1);
+        uint32_t k = b.w[0] / scale;                      // gsl_rng_uniform_int rule, see Rng<kRngPhilox>
+        if (k >= ntt) k = b2_redraw(b.w[3], scale, ntt);  // probability ~ ntt / 2^32
+        nm = k; w1 = b.w[1]; w2 = b.w[2];
+    };
+    auto fold = [&]() {
+        cnt[0] += t_dacc; cnt[1] += t_drej; cnt[2] += t_vacc; cnt[3] += t_vrej; echecks += t_checks;
+        t_dacc = t_drej = t_vacc = t_vrej = t_checks = 0;
+    };
+    // totals of the current positions in pair order (fad :907-946, the ECheck reset :2028-2071)
+    auto recompute = [&]() {
+        double e = 0, v = 0;
+        for (uint32_t i = 0; i + 1 < N; ++i) {
+            double pe, pv;
+            b2_phi<INF>(r[(i + 1) * 32] - r[i * 32], cutoff, two_over_l, pe, pv);
+            e += pe; v += pv;
+        }
+        E = e; Vir = v;
+    };
+
+    // ETest of ECheck :1965-2095: the energy again from the positions, in pair order
+    auto etest = [&]() -> double {
+        double et = 0;
+        if constexpr (NT > 0) {
+            double q[NR];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) q[i] = r[i * 32];
+#pragma unroll
+            for (int i = 0; i + 1 < NT; ++i) et += b2_bond_energy<INF>(q[i + 1] - q[i], cutoff);
+        } else {
+            double qi = r[0];
+            for (uint32_t i = 0; i + 1 < N; ++i) { const double qj = r[(i + 1) * 32]; et += b2_bond_energy<INF>(qj - qi, cutoff); qi = qj; }
+        }
+        return et;
+    };
+    // updateThermo :1941-1961 (HARMONIC defines no hypervirial: sums 10 and 11 stay +0)
+    auto thermo = [&]() {
+        acc[0] = acc[0] + rho;     acc[1] = acc[1] + rho * rho;
+        acc[2] = acc[2] + l;       acc[3] = acc[3] + l * l;
+        acc[4] = acc[4] + E;       acc[5] = acc[5] + E * E;
+        acc[6] = acc[6] + l * E;   acc[7] = acc[7] + Vir;
+        acc[8] = acc[8] + Vir * Vir; acc[9] = acc[9] + E * Vir;
+    };
+
+    // The loop is software-pipelined by one step: iteration t first evaluates, side by side and from the SAME state (the
+    // one step t-1 left), the energy check of step t-1, the displacement trial of step t and the volume trial of step t —
+    // three independent instruction streams in one basic block, plus the Philox block of step t+1 — then takes ONE vote on
+    // everything rare (a discrepancy, a decision inside an approximation band), then adds step t-1's sample to the sums
+    // and commits step t.  Order of effects per chain = the reference's: trial, ECheck, updateThermo, adjustments.
+    uint32_t nm, w1, w2;
+    draw(sn + 1, nm, w1, w2);
+    const uint32_t nsteps = (uint32_t) a.nsteps;
+    bool pending = false;                                 // step t-1 is committed; its sample (and `check`: its ECheck) is still due
+    bool check = false;
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        ++sn;                                                                         // incrementStep :1745
+        uint32_t nm1 = 0, w11 = 0, w21 = 0;
+        if (s + 1 < nsteps) draw(sn + 1, nm1, w11, w21);                              // (depends on nothing: fills the stalls below)
+        const bool disp = nm < N;
+        const double rnh = u01_shifted(w1, 1.5);                                      // rn - 0.5, exactly (rng.cuh)
+        const double ran = u01_shifted(w2, 1.0);
+
+        // ---- ECheck of step t-1
+        const double et = check ? etest() : E;
+        const bool bad = fabs(et - E) > 0.0001;
+
+        // ---- displacement trial, qad2 :1160-1464 with NBN 1; a missing neighbour (chain end) contributes an exact 0
+        const uint32_t i0 = disp ? nm : 0u;
+        const bool hasL = i0 > 0, hasR = i0 + 1 < N;
+        const double rnm = r[i0 * 32], rl = r[(hasL ? i0 - 1 : i0) * 32], rr = r[(hasR ? i0 + 1 : i0) * 32];
+        const double rT = rnm + rnh * 2 * maxStep;                                    // :1182-1183
+        const bool wall = fabs(rT) > half_l;                                          // :1188
+        double po0, po1, pn0, pn1, qo0, qo1, qn0, qn1;
+        b2_phi<INF>(rnm - rl, cutoff, two_over_l, po0, po1);
+        b2_phi<INF>(rT - rl, cutoff, two_over_l, pn0, pn1);
+        b2_phi<INF>(rr - rnm, cutoff, two_over_l, qo0, qo1);
+        b2_phi<INF>(rr - rT, cutoff, two_over_l, qn0, qn1);
+        const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0, l1 = hasL ? (0.0 - po1 + pn1) : 0.0;   // :1244
+        const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;   // :1339
+        const double dE = l0 + r0, dV = l1 + r1;                                      // :1354
+        // Metropolis :1367-1377 by the approximation band of metropolis_accept()
+        const double ea = (double) exp_neg_approx(dE * invT);
+        const bool down = dE <= 0;
+        const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+        bool accept_d = down | acc_b;
+        const bool undecided = disp && !wall && !(down | acc_b | rej_b);
+
+        // ---- volume trial, fav :2161-2293: every pair term again on r * lRat1 (evaluated by every lane, committed by those it is for)
+        const bool npt = ntt > N;
+        const double dl = rnh * 2 * maxdl;
+        const double lnew = l + dl;
+        const double lRat1 = lnew / l;
+        const double two_over_lnew = 2 / lnew;
+        const double rho_new = (double) N / lnew;
+        double rs[NR];
+        double t0 = 0, t1 = 0;
+        bool accept_v = false, v_open = false;
+        if (npt) {
+            if constexpr (NT > 0) {
+#pragma unroll
+                for (int i = 0; i < NT; ++i) rs[i] = r[i * 32] * lRat1;
+#pragma unroll
+                for (int i = 0; i + 1 < NT; ++i) {
+                    double pe, pv;
+                    b2_phi<INF>(rs[i + 1] - rs[i], cutoff, two_over_lnew, pe, pv);
+                    t0 += pe; t1 += pv;
+                }
+            } else {
+                double ri = r[0] * lRat1;
+                for (uint32_t i = 0; i + 1 < N; ++i) {
+                    const double rj = r[(i + 1) * 32] * lRat1;
+                    double pe, pv;
+                    b2_phi<INF>(rj - ri, cutoff, two_over_lnew, pe, pv);
+                    t0 += pe; t1 += pv;
+                    ri = rj;
+                }
+            }
+            // volume_accept (pot.cuh) with its exact test under the common vote
+            const double x = t0 - E + P * dl;                                         // :2249
+            float lg;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float) lRat1));
+            const double A = (double) N * ((double) lg * 0.6931471805599453) - x * invT;
+            const double b = (double) exp_neg_approx(-A);
+            const double band = volume_accept_band((double) N, (double) lg, A);
+            const bool narrow = lRat1 > kVolumeBandLo && lRat1 < kVolumeBandHi;
+            const bool v_yes = narrow && ran < b * (1.0 - band), v_no = narrow && ran > b * (1.0 + band);
+            accept_v = v_yes;
+            v_open = !disp && !(v_yes | v_no);
+        }
+
+        // ---- everything rare, one vote
+        if (__any_sync(FULL, bad | undecided | v_open)) {
+            if (bad) {                                                                // :2003-2071: the totals again from the positions
+                discrepancies++;
+                recompute();
+                if (npt && !disp) accept_v = volume_accept_exact(t0 - E + P * dl, T, (double) N, lRat1, ran);
+            } else if (v_open) accept_v = volume_accept_exact(t0 - E + P * dl, T, (double) N, lRat1, ran);
+            if (undecided) accept_d = metropolis_exact(dE, T, ran);
+        }
+        // ---- the sample of step t-1 (updateThermo comes after ECheck, Step :1800-1805)
+        if (pending) thermo();
+        t_checks += check ? 1u : 0u;
+
+        // ---- commit of step t
+        const bool ok_d = disp && !wall && accept_d;                                  // :1384-1394
+        const bool ok_v = npt && !disp && accept_v;                                   // :2257-2275
+        if (ok_d) { r[nm * 32] = rT; E = E + dE; Vir = Vir + dV; }
+        if (ok_v) {
+            l = lnew; half_l = lnew / 2.0; two_over_l = two_over_lnew; rho = rho_new;
+            E = t0; Vir = t1;
+            if constexpr (NT > 0) {
+#pragma unroll
+                for (int i = 0; i < NT; ++i) r[i * 32] = rs[i];
+            } else {
+                for (uint32_t i = 0; i < N; ++i) r[i * 32] = r[i * 32] * lRat1;
+            }
+        }
+        t_dacc += ok_d ? 1u : 0u;
+        t_drej += (disp && !ok_d) ? 1u : 0u;
+        t_vacc += ok_v ? 1u : 0u;
+        t_vrej += (!disp && !ok_v) ? 1u : 0u;
+        pending = true;
+        check = eci32 == 1 || --eci_left == 0;
+        if (check) eci_left = eci32;
+
+        if (LOG && own) {
+            const uint8_t f = disp ? (wall ? kLogWall : (ok_d ? kLogAccepted : 0)) : (uint8_t)(kLogVolume | (ok_v ? kLogAccepted : 0));
+            a.accept_log[(uint64_t) s * C + chain] = f;
+        }
+        if (--adapt_left == 0) {                          // maxDisAdjust / maxDVAdjust steps (src/Main.cpp:145-165)
+            mdai_left -= adapt_span; mvai_left -= adapt_span;
+            const bool dis = mdai_left == 0, vol = mvai_left == 0;
+            fold();
+            if (dis) {                                                                // maxDisAdjust :2100-2115
+                const double actualRatio = (double) cnt[0] / (double)(cnt[0] + cnt[1]);
+                maxStep = maxStep * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+                if (maxStep < 0.002) maxStep = 0.002;
+                else if (maxStep > 0.5) maxStep = 0.5;
+            }
+            if (vol && (cnt[2] + cnt[3] - vAErr) > 0) {                               // maxDVAdjust :2120-2139
+                vAErr = cnt[2] + cnt[3];
+                const double actualRatio = (double) cnt[2] / (double)(cnt[2] + cnt[3]);
+                maxdl = maxdl * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+                if (maxdl < 0.002 * (double) N) maxdl = 0.002 * (double) N;
+                else if (maxdl > 0.10 * (double) N) maxdl = 0.50 * (double) N;
+            }
+            if (dis) mdai_left = mdai32;
+            if (vol) mvai_left = mvai32;
+            adapt_span = adapt_left = min(mdai_left, mvai_left);
+        }
+        nm = nm1; w1 = w11; w2 = w21;
+    }
+    if (pending) {                                        // the last step's check and sample
+        if (check) {
+            ++t_checks;
+            if (fabs(etest() - E) > 0.0001) { discrepancies++; recompute(); }
+        }
+        thermo();
+    }
+    fold();
+    if (!own) return;
+    for (uint32_t i = 0; i < N; ++i) S.r[(uint64_t) i * C + chain] = r[i * 32];
+    S.l[chain] = l; S.maxStep[chain] = maxStep; S.maxdl[chain] = maxdl;
+    S.tot[chain] = E; S.tot[C + chain] = Vir;
+#pragma unroll
+    for (int k = 2; k < kNTot; ++k) S.tot[k * C + chain] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) S.acc[k * C + chain] = acc[k];
+#pragma unroll
+    for (int k = 0; k < kNCnt; ++k) S.cnt[k * C + chain] = cnt[k];
+    S.vAErr[chain] = vAErr; S.echeck[chain] = echecks; S.echeck[C + chain] = discrepancies;
+}
+
+}  // namespace jmm

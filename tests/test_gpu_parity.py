@@ -155,6 +155,7 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
     "coop": {"JMM_COOP_G": "16", "JMM_BOND": "0"},     # coop.cuh, 16 lanes per chain
     "bond": {"JMM_COOP_G": "16", "JMM_BOND": "1"},      # bond.cuh, k_chains_step_bond (HARMONIC NBN 1 decks; others fall to coop.cuh)
     "bond2": {"JMM_COOP_G": "16", "JMM_BOND": "2"},     # bond.cuh, k_chains_step_bond2 (registers-only, deferred ECheck): the default
+    "solo": {"JMM_COOP_G": "16", "JMM_BOND": "3"},      # solo.cuh, k_chains_step_solo (one chain per thread, a warp per SM; HARMONIC NBN 1 decks)
     "coop32": {"JMM_COOP_G": "32"},
     "coop8": {"JMM_COOP_G": "8"},
     "prod": {"JMM_COOP_G": "0"},                        # prod.cuh, one chain per thread, shared tile
@@ -164,7 +165,7 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
 
 
 @pytest.mark.parametrize("name", list(DECKS))
-@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-bond2", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
+@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-bond2", "recompute-solo", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
 def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
     """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
     every chain must equal the oracle bit for bit, including after adjustments and relaxations —
@@ -366,10 +367,14 @@ def test_sweep_shape_matches_oracle(J, O, engine, start, monkeypatch):
         assert oc.relax_calls == relax0 + (1 if start == "from0" else 0)
 
 
-def test_c2_bench_mode_matches_oracle_on_sampled_chains(J, O):
-    """The C2 workload as bench.py runs it (INPUTstd x 4096 chains on bond.cuh), with the step sizes adapted by the
-    host's libm (JMM_ADAPT_HOST: glibc log on both sides, so adaptation cannot hide a difference): 72 chains spread
-    over the launch, 2 500 steps = 25 adjustments of each kind, bit-identical to the oracle."""
+@pytest.mark.parametrize("engine", ["default", "bond", "solo"])
+def test_c2_bench_mode_matches_oracle_on_sampled_chains(J, O, engine, monkeypatch):
+    """The C2 workload as bench.py runs it (INPUTstd x 4096 chains; the default kernel, bond.cuh and solo.cuh), with the
+    step sizes adapted by the host's libm (JMM_ADAPT_HOST: glibc log on both sides, so adaptation cannot hide a
+    difference): 72 chains spread over the launch, 2 500 steps = 25 adjustments of each kind, bit-identical to the oracle."""
+    if engine != "default":
+        for k, v in ENGINES[engine].items():
+            monkeypatch.setenv(k, v)
     d = dict(DECKS["std"])
     C, nsteps = 4096, 2500
     cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C)
