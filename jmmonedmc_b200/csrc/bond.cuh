@@ -157,12 +157,14 @@ __device__ __forceinline__ void b2_adapt(B2Chain &c, const StepArgs &a, bool dis
 }
 
 template <bool LOG, bool INF>
-__global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs a, int npad) {
+__global__ void __launch_bounds__(128) k_chains_step_bond(ChainsDev S, StepArgs a, int npad, const unsigned int *redo = nullptr) {
     extern __shared__ double smem[];
     const uint32_t gib = threadIdx.x / kB2G, lane = threadIdx.x % kB2G;
     const uint64_t chainA = (uint64_t) blockIdx.x * (blockDim.x / kB2G) + gib;
     const uint64_t C = S.nchains;
     if (chainA >= C) return;
+    // after k_chains_step_trio (solo.cuh): only the chains of the 32-chain CTAs that met an energy discrepancy and stored nothing
+    if (redo && !redo[chainA >> 5]) return;
     const uint32_t gmask = 0xffffu << ((threadIdx.x & 31) / kB2G * kB2G);
     B2Chain A;
     b2_load(A, S, chainA, smem + (size_t) gib * npad, lane, gmask);

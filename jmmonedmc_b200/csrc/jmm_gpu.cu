@@ -323,7 +323,8 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
                 // 1 = k_chains_step_bond (default: 4.43e9 trials/s on C2), 2 = k_chains_step_bond2 (registers-only, deferred
                 // ECheck: 3.99e9 — fewer rendezvous but no fewer instructions, profiles/r2e_c2_*; kept selectable, parity-tested)
                 // 3 = k_chains_step_solo (solo.cuh: one chain per thread, a warp per SM)
-                h->bond = (eb && (atoi(eb) == 2 || atoi(eb) == 3)) ? atoi(eb) : 1;
+                // 4 = k_chains_step_trio (solo.cuh: three warps per 32 chains)
+                h->bond = (eb && atoi(eb) >= 2 && atoi(eb) <= 4) ? atoi(eb) : 1;
         }
     }
     CKH(cudaStreamSynchronize(h->stream));

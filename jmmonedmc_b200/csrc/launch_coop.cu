@@ -42,6 +42,38 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
         h->launches++;
         return cudaGetLastError();
     }
+    if (h->bond == 4) {
+        // k_chains_step_trio: three warps per 32 chains (trials | Philox | ECheck + sums); a CTA that meets an energy
+        // discrepancy stores nothing and raises its word in `redo`, and k_chains_step_bond repeats the launch for its chains
+        const bool ten = h->S.N == 10;
+        void (*kern)(ChainsDev, StepArgs, unsigned int *, int);
+        if (a.accept_log) kern = inf ? (ten ? k_chains_step_trio<10, true, true> : k_chains_step_trio<0, true, true>)
+                                     : (ten ? k_chains_step_trio<10, true, false> : k_chains_step_trio<0, true, false>);
+        else kern = inf ? (ten ? k_chains_step_trio<10, false, true> : k_chains_step_trio<0, false, true>)
+                        : (ten ? k_chains_step_trio<10, false, false> : k_chains_step_trio<0, false, false>);
+        cudaError_t e;
+        const unsigned nctas = nblk(h->S.nchains, 32);
+        const size_t smem = sizeof(TrioRings) + (size_t) 2 * h->S.N * 32 * sizeof(double);
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
+        if (h->work_words < (size_t) nctas) {
+            if (h->d_work) cudaFree(h->d_work);
+            h->d_work = nullptr; h->work_words = 0;
+            if ((e = cudaMalloc((void **) &h->d_work, (size_t) nctas * sizeof(unsigned int))) != cudaSuccess) return e;
+            h->work_words = nctas;
+        }
+        if ((e = cudaMemsetAsync(h->d_work, 0, (size_t) nctas * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
+        const char *fr = getenv("JMM_SOLO_FORCE_REDO");
+        kern<<<nctas, 96, smem, h->stream>>>(h->S, a, h->d_work, (fr && atoi(fr) != 0) ? 1 : 0);
+        h->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        int npad = (int) h->S.N;
+        npad += (npad & 1) ? 0 : 1;
+        auto again = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
+                                  : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
+        again<<<nblk(h->S.nchains, 128 / kB2G), 128, (size_t) (128 / kB2G) * npad * sizeof(double), h->stream>>>(h->S, a, npad, h->d_work);
+        h->launches++;
+        return cudaGetLastError();
+    }
     if (h->bond == 2) {
         // k_chains_step_bond2: the shared row only parks the positions for the rare paths; the thermo ring follows it
         int npad = (int) ((h->S.N + 1) & ~1ull) + kThermoRing * kThermoSlots;
@@ -60,7 +92,7 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
     npad += (npad & 1) ? 0 : 1;                                  // odd row length: the groups of a warp hit different banks
     auto kern = a.accept_log ? (inf ? k_chains_step_bond<true, true> : k_chains_step_bond<true, false>)
                              : (inf ? k_chains_step_bond<false, true> : k_chains_step_bond<false, false>);
-    kern<<<nblk(h->S.nchains, per_block), threads, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad);
+    kern<<<nblk(h->S.nchains, per_block), threads, (size_t) per_block * npad * sizeof(double), h->stream>>>(h->S, a, npad, nullptr);
     h->launches++;
     return cudaGetLastError();
 }

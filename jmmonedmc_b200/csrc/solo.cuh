@@ -283,4 +283,314 @@ __global__ void __launch_bounds__(32) k_chains_step_solo(ChainsDev S, StepArgs a
     S.vAErr[chain] = vAErr; S.echeck[chain] = echecks; S.echeck[C + chain] = discrepancies;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_chains_step_trio — the same chains, the step's instruction stream split over THREE warps of a CTA (one per
+// sub-partition of the SM the CTA has to itself).  k_chains_step_solo issues ~560 instructions per step from one
+// warp at 0.35 per cycle (profiles/r2w_c2solo_pipelined.txt: "wait" on dependent instructions); what shortens a step
+// further is taking whatever the NEXT trial does not depend on out of that stream:
+//   * warp P (producer) evaluates the Philox blocks and trial types of the 32 chains, 32 steps at a time, into a
+//     double-buffered ring in shared memory: they depend on (seed, chain, step) only;
+//   * warp T (trials) runs the Markov chains: displacement trial, volume trial, decisions, commit, E / Vir / l,
+//     counters, step-size adjustments.  Per step it leaves a record (what changed, the new value, E, Vir) in a second
+//     ring;
+//   * warp V (verifier) replays the records on its own copy of the positions and does what only LOOKS at a step's
+//     result: ECheck's energy from the positions, its comparison with E, and updateThermo's sums.
+// The rings are handed over 32 steps at a time through named barriers (st.shared, fence, bar.arrive | bar.sync,
+// ld.shared: the producer/consumer use of bar.arrive in the PTX ISA), so no warp polls.
+// An energy discrepancy (ECheck :2003-2071: |ETest - E| > 1e-4, which the reference answers by recomputing the totals
+// on the spot) would change what warp T has long passed.  It cannot be repaired in place, so it is repaired in
+// time: the CTA stores NOTHING, raises its word in `redo`, and the launch is followed by k_chains_step_bond for the
+// chains of the CTAs that raised it (jmm_gpu: launch_step_bond) — from the state the launch started with, through the
+// kernel that takes the reset exactly where the reference takes it.  (E drifts by ~1e-16 per step against a
+// threshold of 1e-4: the path exists for correctness and is exercised by JMM_SOLO_FORCE_REDO=1 in the tests.)
+// Arithmetic = k_chains_step_solo's = the reference's, per chain in the reference's order: bit-identical.
+constexpr int kTrioChunk = 32;                            // steps per ring buffer
+
+__device__ __forceinline__ void trio_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void trio_bar_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+struct TrioRings {                                        // [buffer][step][lane]
+    uint32_t nm[2][kTrioChunk][32], w1[2][kTrioChunk][32], w2[2][kTrioChunk][32];     // P -> T
+    uint32_t code[2][kTrioChunk][32];                                                   // T -> V: 0 nothing, 1 | nm << 8 moved, 2 rescaled
+    double val[2][kTrioChunk][32], e[2][kTrioChunk][32], vir[2][kTrioChunk][32], lnew[2][kTrioChunk][32];
+    int redo;                                                                           // V -> T at the end of the launch
+};
+
+template <int NT, bool LOG, bool INF>
+__global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a, unsigned int *redo, int force_redo) {
+    extern __shared__ __align__(16) unsigned char trio_smem[];
+    constexpr uint32_t FULL = 0xffffffffu;
+    // named barriers: a ring buffer b is FULL (producer arrives, consumer syncs) or FREE (the other way round)
+    constexpr int P_FULL = 1, P_FREE = 3, D_FULL = 5, D_FREE = 7;                       // + buffer index 0/1
+    const uint32_t lane = threadIdx.x & 31, role = threadIdx.x >> 5;                   // 0 = T, 1 = P, 2 = V
+    const uint64_t C = S.nchains;
+    const uint64_t c_raw = (uint64_t) blockIdx.x * 32 + lane;
+    const bool own = c_raw < C;
+    const uint64_t chain = own ? c_raw : C - 1;           // (lanes past the last chain shadow it, unsaved)
+    const uint32_t N = NT ? (uint32_t) NT : (uint32_t) S.N;
+    constexpr int NR = NT ? NT : 1;
+    TrioRings &R = *reinterpret_cast<TrioRings *>(trio_smem);
+    double *tiles = reinterpret_cast<double *>(trio_smem + sizeof(TrioRings));
+    const uint32_t nsteps = (uint32_t) a.nsteps;
+    const uint32_t nchunks = (nsteps + kTrioChunk - 1) / kTrioChunk;
+    const double cutoff = S.cutoff;
+
+    if (role == 1) {
+        // ---------------------------------------------------------------- P: trial types and random words
+        const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32), cid = (uint32_t)(S.chain_id0 + chain);
+        const uint32_t ntt = (uint32_t) S.numTrialTypes, scale = 0xffffffffu / ntt;
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            if (k >= 2) trio_bar_sync(P_FREE + b);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            const uint64_t step0 = a.sn0 + (uint64_t) k * kTrioChunk + 1;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint64_t step = step0 + j;
+                const Philox4 blk = philox4x32_10((uint32_t) step, (uint32_t)(step >> 32), cid, kTagTrial, k0, k1);
+                uint32_t t = blk.w[0] / scale;            // gsl_rng_uniform_int rule, see Rng<kRngPhilox>
+                if (t >= ntt) t = b2_redraw(blk.w[3], scale, ntt);
+                R.nm[b][j][lane] = t; R.w1[b][j][lane] = blk.w[1]; R.w2[b][j][lane] = blk.w[2];
+            }
+            trio_bar_arrive(P_FULL + b);
+        }
+    } else if (role == 2) {
+        // ---------------------------------------------------------------- V: ECheck and updateThermo on a replayed copy
+        double *r = tiles + (size_t) N * 32 + lane;
+        double l = S.l[chain], rho = (double) N / l;
+        double E = S.tot[chain], Vir = S.tot[C + chain];
+        double acc[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] = S.acc[k * C + chain];
+        uint64_t echecks = S.echeck[chain];
+        uint32_t t_checks = 0;
+        for (uint32_t i = 0; i < N; ++i) r[i * 32] = S.r[(uint64_t) i * C + chain];
+        uint64_t sn = a.sn0;
+        const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
+        uint32_t eci_left = 0xffffffffu;
+        if (a.eci) { const uint64_t left = a.eci - sn % a.eci; eci_left = left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left; }
+        bool bad = force_redo != 0;
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            trio_bar_sync(D_FULL + b);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t code = R.code[b][j][lane];
+                const double val = R.val[b][j][lane];
+                if (__any_sync(FULL, code == 2u)) {                                   // an accepted volume trial: r *= lRat1 (:2264-2266)
+                    if (code == 2u) {
+                        l = R.lnew[b][j][lane];
+                        rho = (double) N / l;
+                        for (uint32_t i = 0; i < N; ++i) r[i * 32] = r[i * 32] * val;
+                    }
+                }
+                if (code & 1u) r[(code >> 8) * 32] = val;
+                E = R.e[b][j][lane]; Vir = R.vir[b][j][lane];
+                if (eci32 == 1 || --eci_left == 0) {                                  // ECheck :1965-2095
+                    double et = 0;
+                    if constexpr (NT > 0) {
+                        double q[NR];
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) q[i] = r[i * 32];
+#pragma unroll
+                        for (int i = 0; i + 1 < NT; ++i) et += b2_bond_energy<INF>(q[i + 1] - q[i], cutoff);
+                    } else {
+                        double qi = r[0];
+                        for (uint32_t i = 0; i + 1 < N; ++i) { const double qj = r[(i + 1) * 32]; et += b2_bond_energy<INF>(qj - qi, cutoff); qi = qj; }
+                    }
+                    ++t_checks;
+                    bad = bad || fabs(et - E) > 0.0001;
+                    eci_left = eci32;
+                }
+                acc[0] = acc[0] + rho;     acc[1] = acc[1] + rho * rho;             // updateThermo :1941-1961
+                acc[2] = acc[2] + l;       acc[3] = acc[3] + l * l;
+                acc[4] = acc[4] + E;       acc[5] = acc[5] + E * E;
+                acc[6] = acc[6] + l * E;   acc[7] = acc[7] + Vir;
+                acc[8] = acc[8] + Vir * Vir; acc[9] = acc[9] + E * Vir;
+            }
+            if (k + 2 < nchunks) trio_bar_arrive(D_FREE + b);
+        }
+        const bool any_bad = __any_sync(FULL, bad);
+        if (lane == 0) { R.redo = any_bad ? 1 : 0; if (any_bad) redo[blockIdx.x] = 1u; }
+        __syncthreads();
+        if (!any_bad && own) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) S.acc[k * C + chain] = acc[k];
+            S.echeck[chain] = echecks + t_checks;
+        }
+        return;
+    } else {
+        // ---------------------------------------------------------------- T: the Markov chains
+        double *r = tiles + lane;
+        double l = S.l[chain], maxStep = S.maxStep[chain], maxdl = S.maxdl[chain];
+        const double P = S.P[chain], T = S.T[chain], invT = 1.0 / T;
+        double half_l = l / 2.0, two_over_l = 2 / l;
+        double E = S.tot[chain], Vir = S.tot[C + chain];
+        uint64_t cnt[kNCnt];
+#pragma unroll
+        for (int k = 0; k < kNCnt; ++k) cnt[k] = S.cnt[k * C + chain];
+        uint64_t vAErr = S.vAErr[chain];
+        uint32_t t_dacc = 0, t_drej = 0, t_vacc = 0, t_vrej = 0;
+        for (uint32_t i = 0; i < N; ++i) r[i * 32] = S.r[(uint64_t) i * C + chain];
+        const uint32_t ntt = (uint32_t) S.numTrialTypes;
+        const bool npt = ntt > N;
+        uint64_t sn = a.sn0;
+        auto until = [&](uint64_t every) -> uint32_t {
+            if (!every) return 0xffffffffu;
+            const uint64_t left = every - sn % every;
+            return left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left;
+        };
+        uint32_t mdai_left = a.adapt_device ? until(a.mdai) : 0xffffffffu;
+        uint32_t mvai_left = a.adapt_device ? until(a.mvai) : 0xffffffffu;
+        const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
+        const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
+        uint32_t adapt_span = min(mdai_left, mvai_left), adapt_left = adapt_span;
+        auto fold = [&]() {
+            cnt[0] += t_dacc; cnt[1] += t_drej; cnt[2] += t_vacc; cnt[3] += t_vrej;
+            t_dacc = t_drej = t_vacc = t_vrej = 0;
+        };
+
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            trio_bar_sync(P_FULL + b);
+            if (k >= 2) trio_bar_sync(D_FREE + b);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            for (uint32_t j = 0; j < n; ++j) {
+                ++sn;                                                                 // incrementStep :1745
+                const uint32_t nm = R.nm[b][j][lane];
+                const bool disp = nm < N;
+                const double rnh = u01_shifted(R.w1[b][j][lane], 1.5);                // rn - 0.5, exactly (rng.cuh)
+                const double ran = u01_shifted(R.w2[b][j][lane], 1.0);
+
+                // ---- displacement trial, qad2 :1160-1464 with NBN 1; a missing neighbour contributes an exact 0
+                const uint32_t i0 = disp ? nm : 0u;
+                const bool hasL = i0 > 0, hasR = i0 + 1 < N;
+                const double rnm = r[i0 * 32], rl = r[(hasL ? i0 - 1 : i0) * 32], rr = r[(hasR ? i0 + 1 : i0) * 32];
+                const double rT = rnm + rnh * 2 * maxStep;                            // :1182-1183
+                const bool wall = fabs(rT) > half_l;                                  // :1188
+                double po0, po1, pn0, pn1, qo0, qo1, qn0, qn1;
+                b2_phi<INF>(rnm - rl, cutoff, two_over_l, po0, po1);
+                b2_phi<INF>(rT - rl, cutoff, two_over_l, pn0, pn1);
+                b2_phi<INF>(rr - rnm, cutoff, two_over_l, qo0, qo1);
+                b2_phi<INF>(rr - rT, cutoff, two_over_l, qn0, qn1);
+                const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0, l1 = hasL ? (0.0 - po1 + pn1) : 0.0;   // :1244
+                const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;   // :1339
+                const double dE = l0 + r0, dV = l1 + r1;                              // :1354
+                const double ea = (double) exp_neg_approx(dE * invT);                 // Metropolis :1367-1377, band of metropolis_accept()
+                const bool down = dE <= 0;
+                const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+                bool accept_d = down | acc_b;
+                const bool undecided = disp && !wall && !(down | acc_b | rej_b);
+
+                // ---- volume trial, fav :2161-2293: every pair term again on r * lRat1
+                const double dl = rnh * 2 * maxdl;
+                const double lnew = l + dl;
+                const double lRat1 = lnew / l;
+                const double two_over_lnew = 2 / lnew;
+                double rs[NR];
+                double t0 = 0, t1 = 0;
+                bool accept_v = false, v_open = false;
+                if (npt) {
+                    if constexpr (NT > 0) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) rs[i] = r[i * 32] * lRat1;
+#pragma unroll
+                        for (int i = 0; i + 1 < NT; ++i) {
+                            double pe, pv;
+                            b2_phi<INF>(rs[i + 1] - rs[i], cutoff, two_over_lnew, pe, pv);
+                            t0 += pe; t1 += pv;
+                        }
+                    } else {
+                        double ri = r[0] * lRat1;
+                        for (uint32_t i = 0; i + 1 < N; ++i) {
+                            const double rj = r[(i + 1) * 32] * lRat1;
+                            double pe, pv;
+                            b2_phi<INF>(rj - ri, cutoff, two_over_lnew, pe, pv);
+                            t0 += pe; t1 += pv;
+                            ri = rj;
+                        }
+                    }
+                    const double x = t0 - E + P * dl;                                 // :2249, volume_accept (pot.cuh)
+                    float lg;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float) lRat1));
+                    const double A = (double) N * ((double) lg * 0.6931471805599453) - x * invT;
+                    const double bb = (double) exp_neg_approx(-A);
+                    const double band = volume_accept_band((double) N, (double) lg, A);
+                    const bool narrow = lRat1 > kVolumeBandLo && lRat1 < kVolumeBandHi;
+                    const bool v_yes = narrow && ran < bb * (1.0 - band), v_no = narrow && ran > bb * (1.0 + band);
+                    accept_v = v_yes;
+                    v_open = !disp && !(v_yes | v_no);
+                }
+                if (__any_sync(FULL, undecided | v_open)) {                          // inside an approximation band: the exact expressions
+                    if (v_open) accept_v = volume_accept_exact(t0 - E + P * dl, T, (double) N, lRat1, ran);
+                    if (undecided) accept_d = metropolis_exact(dE, T, ran);
+                }
+
+                // ---- commit, and the record for warp V
+                const bool ok_d = disp && !wall && accept_d;                          // :1384-1394
+                const bool ok_v = npt && !disp && accept_v;                           // :2257-2275
+                if (ok_d) { r[nm * 32] = rT; E = E + dE; Vir = Vir + dV; }
+                if (ok_v) {
+                    l = lnew; half_l = lnew / 2.0; two_over_l = two_over_lnew;
+                    E = t0; Vir = t1;
+                    if constexpr (NT > 0) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) r[i * 32] = rs[i];
+                    } else {
+                        for (uint32_t i = 0; i < N; ++i) r[i * 32] = r[i * 32] * lRat1;
+                    }
+                    R.lnew[b][j][lane] = lnew;
+                }
+                R.code[b][j][lane] = ok_d ? (1u | (nm << 8)) : (ok_v ? 2u : 0u);
+                R.val[b][j][lane] = ok_d ? rT : lRat1;
+                R.e[b][j][lane] = E; R.vir[b][j][lane] = Vir;
+                t_dacc += ok_d ? 1u : 0u;
+                t_drej += (disp && !ok_d) ? 1u : 0u;
+                t_vacc += ok_v ? 1u : 0u;
+                t_vrej += (!disp && !ok_v) ? 1u : 0u;
+                if (LOG && own) {
+                    const uint8_t f = disp ? (wall ? kLogWall : (ok_d ? kLogAccepted : 0)) : (uint8_t)(kLogVolume | (ok_v ? kLogAccepted : 0));
+                    a.accept_log[(uint64_t)(k * kTrioChunk + j) * C + chain] = f;
+                }
+                if (--adapt_left == 0) {                  // maxDisAdjust / maxDVAdjust steps (src/Main.cpp:145-165)
+                    mdai_left -= adapt_span; mvai_left -= adapt_span;
+                    const bool dis = mdai_left == 0, vol = mvai_left == 0;
+                    fold();
+                    if (dis) {                                                        // maxDisAdjust :2100-2115
+                        const double actualRatio = (double) cnt[0] / (double)(cnt[0] + cnt[1]);
+                        maxStep = maxStep * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+                        if (maxStep < 0.002) maxStep = 0.002;
+                        else if (maxStep > 0.5) maxStep = 0.5;
+                    }
+                    if (vol && (cnt[2] + cnt[3] - vAErr) > 0) {                       // maxDVAdjust :2120-2139
+                        vAErr = cnt[2] + cnt[3];
+                        const double actualRatio = (double) cnt[2] / (double)(cnt[2] + cnt[3]);
+                        maxdl = maxdl * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+                        if (maxdl < 0.002 * (double) N) maxdl = 0.002 * (double) N;
+                        else if (maxdl > 0.10 * (double) N) maxdl = 0.50 * (double) N;
+                    }
+                    if (dis) mdai_left = mdai32;
+                    if (vol) mvai_left = mvai32;
+                    adapt_span = adapt_left = min(mdai_left, mvai_left);
+                }
+            }
+            trio_bar_arrive(D_FULL + b);
+            if (k + 2 < nchunks) trio_bar_arrive(P_FREE + b);
+        }
+        fold();
+        __syncthreads();                                  // warp V's verdict
+        if (R.redo || !own) return;
+        for (uint32_t i = 0; i < N; ++i) S.r[(uint64_t) i * C + chain] = r[i * 32];
+        S.l[chain] = l; S.maxStep[chain] = maxStep; S.maxdl[chain] = maxdl;
+        S.tot[chain] = E; S.tot[C + chain] = Vir;
+#pragma unroll
+        for (int k = 2; k < kNTot; ++k) S.tot[k * C + chain] = 0.0;
+#pragma unroll
+        for (int k = 0; k < kNCnt; ++k) S.cnt[k * C + chain] = cnt[k];
+        S.vAErr[chain] = vAErr;
+        return;
+    }
+    __syncthreads();                                      // (warp P: the CTA's final barrier)
+}
+
 }  // namespace jmm

@@ -156,6 +156,8 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
     "bond": {"JMM_COOP_G": "16", "JMM_BOND": "1"},      # bond.cuh, k_chains_step_bond (HARMONIC NBN 1 decks; others fall to coop.cuh)
     "bond2": {"JMM_COOP_G": "16", "JMM_BOND": "2"},     # bond.cuh, k_chains_step_bond2 (registers-only, deferred ECheck): the default
     "solo": {"JMM_COOP_G": "16", "JMM_BOND": "3"},      # solo.cuh, k_chains_step_solo (one chain per thread, a warp per SM; HARMONIC NBN 1 decks)
+    "trio": {"JMM_COOP_G": "16", "JMM_BOND": "4"},      # solo.cuh, k_chains_step_trio (trials | Philox | ECheck + sums in three warps)
+    "trioredo": {"JMM_COOP_G": "16", "JMM_BOND": "4", "JMM_SOLO_FORCE_REDO": "1"},   # ... every CTA reports a discrepancy: bond.cuh repeats the launch
     "coop32": {"JMM_COOP_G": "32"},
     "coop8": {"JMM_COOP_G": "8"},
     "prod": {"JMM_COOP_G": "0"},                        # prod.cuh, one chain per thread, shared tile
@@ -165,7 +167,7 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
 
 
 @pytest.mark.parametrize("name", list(DECKS))
-@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-bond2", "recompute-solo", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
+@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-bond2", "recompute-solo", "recompute-trio", "recompute-trioredo", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
 def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
     """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
     every chain must equal the oracle bit for bit, including after adjustments and relaxations —
@@ -367,7 +369,7 @@ def test_sweep_shape_matches_oracle(J, O, engine, start, monkeypatch):
         assert oc.relax_calls == relax0 + (1 if start == "from0" else 0)
 
 
-@pytest.mark.parametrize("engine", ["default", "bond", "solo"])
+@pytest.mark.parametrize("engine", ["default", "bond", "solo", "trio"])
 def test_c2_bench_mode_matches_oracle_on_sampled_chains(J, O, engine, monkeypatch):
     """The C2 workload as bench.py runs it (INPUTstd x 4096 chains; the default kernel, bond.cuh and solo.cuh), with the
     step sizes adapted by the host's libm (JMM_ADAPT_HOST: glibc log on both sides, so adaptation cannot hide a
