@@ -291,11 +291,13 @@ __global__ void __launch_bounds__(32) k_chains_step_solo(ChainsDev S, StepArgs a
 // further is taking whatever the NEXT trial does not depend on out of that stream:
 //   * warp P (producer) evaluates the Philox blocks and trial types of the 32 chains, 32 steps at a time, into a
 //     double-buffered ring in shared memory: they depend on (seed, chain, step) only;
-//   * warp T (trials) runs the Markov chains: displacement trial, volume trial, decisions, commit, E / Vir / l,
-//     counters, step-size adjustments.  Per step it leaves a record (what changed, the new value, E, Vir) in a second
-//     ring;
+//   * warp T (trials) runs the Markov chains: displacement trial, volume trial, decisions, commit, E and l, counters,
+//     step-size adjustments — ENERGIES ONLY: nothing T decides depends on a virial.  Per step it leaves a record
+//     (what changed, the new value, E) in a second ring;
 //   * warp V (verifier) replays the records on its own copy of the positions and does what only LOOKS at a step's
-//     result: ECheck's energy from the positions, its comparison with E, and updateThermo's sums.
+//     result: the virial (the four old/new bond terms of an accepted move in qad2's order :1244,1339,1354; all bonds
+//     in pair order after an accepted volume change, fav :2212-2240), ECheck's energy from the positions and its
+//     comparison with E, and updateThermo's sums.
 // The rings are handed over 32 steps at a time through named barriers (st.shared, fence, bar.arrive | bar.sync,
 // ld.shared: the producer/consumer use of bar.arrive in the PTX ISA), so no warp polls.
 // An energy discrepancy (ECheck :2003-2071: |ETest - E| > 1e-4, which the reference answers by recomputing the totals
@@ -313,7 +315,7 @@ __device__ __forceinline__ void trio_bar_arrive(int id) { __threadfence_block();
 struct TrioRings {                                        // [buffer][step][lane]
     uint32_t nm[2][kTrioChunk][32], w1[2][kTrioChunk][32], w2[2][kTrioChunk][32];     // P -> T
     uint32_t code[2][kTrioChunk][32];                                                   // T -> V: 0 nothing, 1 | nm << 8 moved, 2 rescaled
-    double val[2][kTrioChunk][32], e[2][kTrioChunk][32], vir[2][kTrioChunk][32], lnew[2][kTrioChunk][32];
+    double val[2][kTrioChunk][32], e[2][kTrioChunk][32], lnew[2][kTrioChunk][32];
     int redo;                                                                           // V -> T at the end of the launch
 };
 
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
     } else if (role == 2) {
         // ---------------------------------------------------------------- V: ECheck and updateThermo on a replayed copy
         double *r = tiles + (size_t) N * 32 + lane;
-        double l = S.l[chain], rho = (double) N / l;
+        double l = S.l[chain], rho = (double) N / l, two_over_l = 2 / l;
         double E = S.tot[chain], Vir = S.tot[C + chain];
         double acc[10];
 #pragma unroll
@@ -377,15 +379,40 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
             for (uint32_t j = 0; j < n; ++j) {
                 const uint32_t code = R.code[b][j][lane];
                 const double val = R.val[b][j][lane];
-                if (__any_sync(FULL, code == 2u)) {                                   // an accepted volume trial: r *= lRat1 (:2264-2266)
+                double pe_unused;
+                {                                                                     // an accepted move: its virial change, qad2 :1244,1339,1354
+                    const bool moved = code & 1u;
+                    const uint32_t i0 = moved ? (code >> 8) : 0u;
+                    const bool hasL = i0 > 0, hasR = i0 + 1 < N;
+                    const double rnm = r[i0 * 32], rl = r[(hasL ? i0 - 1 : i0) * 32], rr = r[(hasR ? i0 + 1 : i0) * 32];
+                    double pe, po1, pn1, qo1, qn1;
+                    b2_phi<INF>(rnm - rl, cutoff, two_over_l, pe, po1);
+                    b2_phi<INF>(val - rl, cutoff, two_over_l, pe, pn1);
+                    b2_phi<INF>(rr - rnm, cutoff, two_over_l, pe, qo1);
+                    b2_phi<INF>(rr - val, cutoff, two_over_l, pe, qn1);
+                    const double l1 = hasL ? (0.0 - po1 + pn1) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;
+                    if (moved) { Vir = Vir + (l1 + r1); r[i0 * 32] = val; }
+                }
+                if (__any_sync(FULL, code == 2u)) {                                   // an accepted volume trial: r *= lRat1 (:2264-2266), Vir from all bonds
                     if (code == 2u) {
                         l = R.lnew[b][j][lane];
                         rho = (double) N / l;
-                        for (uint32_t i = 0; i < N; ++i) r[i * 32] = r[i * 32] * val;
+                        two_over_l = 2 / l;
+                        double v = 0;
+                        double ri = r[0] * val;
+                        r[0] = ri;
+                        for (uint32_t i = 0; i + 1 < N; ++i) {
+                            const double rj = r[(i + 1) * 32] * val;
+                            r[(i + 1) * 32] = rj;
+                            double pv;
+                            b2_phi<INF>(rj - ri, cutoff, two_over_l, pe_unused, pv);
+                            v += pv;
+                            ri = rj;
+                        }
+                        Vir = v;
                     }
                 }
-                if (code & 1u) r[(code >> 8) * 32] = val;
-                E = R.e[b][j][lane]; Vir = R.vir[b][j][lane];
+                E = R.e[b][j][lane];
                 if (eci32 == 1 || --eci_left == 0) {                                  // ECheck :1965-2095
                     double et = 0;
                     if constexpr (NT > 0) {
@@ -417,6 +444,7 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
 #pragma unroll
             for (int k = 0; k < 10; ++k) S.acc[k * C + chain] = acc[k];
             S.echeck[chain] = echecks + t_checks;
+            S.tot[C + chain] = Vir;
         }
         return;
     } else {
@@ -424,8 +452,8 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
         double *r = tiles + lane;
         double l = S.l[chain], maxStep = S.maxStep[chain], maxdl = S.maxdl[chain];
         const double P = S.P[chain], T = S.T[chain], invT = 1.0 / T;
-        double half_l = l / 2.0, two_over_l = 2 / l;
-        double E = S.tot[chain], Vir = S.tot[C + chain];
+        double half_l = l / 2.0;
+        double E = S.tot[chain];
         uint64_t cnt[kNCnt];
 #pragma unroll
         for (int k = 0; k < kNCnt; ++k) cnt[k] = S.cnt[k * C + chain];
@@ -468,14 +496,11 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
                 const double rnm = r[i0 * 32], rl = r[(hasL ? i0 - 1 : i0) * 32], rr = r[(hasR ? i0 + 1 : i0) * 32];
                 const double rT = rnm + rnh * 2 * maxStep;                            // :1182-1183
                 const bool wall = fabs(rT) > half_l;                                  // :1188
-                double po0, po1, pn0, pn1, qo0, qo1, qn0, qn1;
-                b2_phi<INF>(rnm - rl, cutoff, two_over_l, po0, po1);
-                b2_phi<INF>(rT - rl, cutoff, two_over_l, pn0, pn1);
-                b2_phi<INF>(rr - rnm, cutoff, two_over_l, qo0, qo1);
-                b2_phi<INF>(rr - rT, cutoff, two_over_l, qn0, qn1);
-                const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0, l1 = hasL ? (0.0 - po1 + pn1) : 0.0;   // :1244
-                const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;   // :1339
-                const double dE = l0 + r0, dV = l1 + r1;                              // :1354
+                const double po0 = b2_bond_energy<INF>(rnm - rl, cutoff), pn0 = b2_bond_energy<INF>(rT - rl, cutoff);
+                const double qo0 = b2_bond_energy<INF>(rr - rnm, cutoff), qn0 = b2_bond_energy<INF>(rr - rT, cutoff);
+                const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0;                     // :1244
+                const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0;                     // :1339
+                const double dE = l0 + r0;                                            // :1354
                 const double ea = (double) exp_neg_approx(dE * invT);                 // Metropolis :1367-1377, band of metropolis_accept()
                 const bool down = dE <= 0;
                 const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
@@ -486,27 +511,20 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
                 const double dl = rnh * 2 * maxdl;
                 const double lnew = l + dl;
                 const double lRat1 = lnew / l;
-                const double two_over_lnew = 2 / lnew;
                 double rs[NR];
-                double t0 = 0, t1 = 0;
+                double t0 = 0;
                 bool accept_v = false, v_open = false;
                 if (npt) {
                     if constexpr (NT > 0) {
 #pragma unroll
                         for (int i = 0; i < NT; ++i) rs[i] = r[i * 32] * lRat1;
 #pragma unroll
-                        for (int i = 0; i + 1 < NT; ++i) {
-                            double pe, pv;
-                            b2_phi<INF>(rs[i + 1] - rs[i], cutoff, two_over_lnew, pe, pv);
-                            t0 += pe; t1 += pv;
-                        }
+                        for (int i = 0; i + 1 < NT; ++i) t0 += b2_bond_energy<INF>(rs[i + 1] - rs[i], cutoff);
                     } else {
                         double ri = r[0] * lRat1;
                         for (uint32_t i = 0; i + 1 < N; ++i) {
                             const double rj = r[(i + 1) * 32] * lRat1;
-                            double pe, pv;
-                            b2_phi<INF>(rj - ri, cutoff, two_over_lnew, pe, pv);
-                            t0 += pe; t1 += pv;
+                            t0 += b2_bond_energy<INF>(rj - ri, cutoff);
                             ri = rj;
                         }
                     }
@@ -529,10 +547,10 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
                 // ---- commit, and the record for warp V
                 const bool ok_d = disp && !wall && accept_d;                          // :1384-1394
                 const bool ok_v = npt && !disp && accept_v;                           // :2257-2275
-                if (ok_d) { r[nm * 32] = rT; E = E + dE; Vir = Vir + dV; }
+                if (ok_d) { r[nm * 32] = rT; E = E + dE; }
                 if (ok_v) {
-                    l = lnew; half_l = lnew / 2.0; two_over_l = two_over_lnew;
-                    E = t0; Vir = t1;
+                    l = lnew; half_l = lnew / 2.0;
+                    E = t0;
                     if constexpr (NT > 0) {
 #pragma unroll
                         for (int i = 0; i < NT; ++i) r[i * 32] = rs[i];
@@ -543,7 +561,7 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
                 }
                 R.code[b][j][lane] = ok_d ? (1u | (nm << 8)) : (ok_v ? 2u : 0u);
                 R.val[b][j][lane] = ok_d ? rT : lRat1;
-                R.e[b][j][lane] = E; R.vir[b][j][lane] = Vir;
+                R.e[b][j][lane] = E;
                 t_dacc += ok_d ? 1u : 0u;
                 t_drej += (disp && !ok_d) ? 1u : 0u;
                 t_vacc += ok_v ? 1u : 0u;
@@ -582,7 +600,7 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
         if (R.redo || !own) return;
         for (uint32_t i = 0; i < N; ++i) S.r[(uint64_t) i * C + chain] = r[i * 32];
         S.l[chain] = l; S.maxStep[chain] = maxStep; S.maxdl[chain] = maxdl;
-        S.tot[chain] = E; S.tot[C + chain] = Vir;
+        S.tot[chain] = E;                                 // (the virial is warp V's)
 #pragma unroll
         for (int k = 2; k < kNTot; ++k) S.tot[k * C + chain] = 0.0;
 #pragma unroll
