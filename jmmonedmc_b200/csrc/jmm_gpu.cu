@@ -325,11 +325,13 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
                 //     default while every 32-chain CTA is resident at once, two per SM: 7.5e9 trials/s and more on C2),
                 // 1 = k_chains_step_bond (16 lanes per chain: 4.47e9; also what repeats a launch of 4 after an energy discrepancy),
                 // 2 = k_chains_step_bond2 (registers-only, deferred ECheck: 3.99e9, profiles/r2e_c2_*),
-                // 3 = k_chains_step_solo (one warp per 32 chains doing all of it: 4.97e9).  All parity-tested.
+                // 3 = k_chains_step_solo (one warp per 32 chains doing all of it: 4.97e9),
+                // 5 = k_chains_step_crew (five warps per 32 chains: displacement | volume | Philox | virial + sums | ECheck).
+                // All parity-tested.
                 int nsm = 0;
                 cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
                 const int fallback = (C + 31) / 32 <= (uint64_t) 2 * (uint64_t) std::max(nsm, 1) ? 4 : 1;
-                h->bond = (eb && atoi(eb) >= 1 && atoi(eb) <= 4) ? atoi(eb) : fallback;
+                h->bond = (eb && atoi(eb) >= 1 && atoi(eb) <= 5) ? atoi(eb) : fallback;
             }
         }
     }

@@ -42,18 +42,21 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
         h->launches++;
         return cudaGetLastError();
     }
-    if (h->bond == 4) {
-        // k_chains_step_trio: three warps per 32 chains (trials | Philox | ECheck + sums); a CTA that meets an energy
-        // discrepancy stores nothing and raises its word in `redo`, and k_chains_step_bond repeats the launch for its chains
+    if (h->bond == 4 || h->bond == 5) {
+        // solo.cuh, a CTA per 32 chains: k_chains_step_trio (trials | Philox | virial + ECheck + sums) or, with volume trials in
+        // the deck, k_chains_step_crew (displacement | volume | Philox | virial + sums | ECheck).  A CTA that meets an energy
+        // discrepancy stores nothing and raises its word in `redo`; k_chains_step_bond then repeats the launch for its chains.
         const bool ten = h->S.N == 10;
+        const bool crew = h->bond == 5 && (uint64_t) h->S.numTrialTypes > h->S.N;
         void (*kern)(ChainsDev, StepArgs, unsigned int *, int);
-        if (a.accept_log) kern = inf ? (ten ? k_chains_step_trio<10, true, true> : k_chains_step_trio<0, true, true>)
-                                     : (ten ? k_chains_step_trio<10, true, false> : k_chains_step_trio<0, true, false>);
-        else kern = inf ? (ten ? k_chains_step_trio<10, false, true> : k_chains_step_trio<0, false, true>)
-                        : (ten ? k_chains_step_trio<10, false, false> : k_chains_step_trio<0, false, false>);
+#define JMM_PICK(K) (a.accept_log ? (inf ? (ten ? K<10, true, true> : K<0, true, true>) : (ten ? K<10, true, false> : K<0, true, false>)) \
+                                  : (inf ? (ten ? K<10, false, true> : K<0, false, true>) : (ten ? K<10, false, false> : K<0, false, false>)))
+        if (crew) kern = JMM_PICK(k_chains_step_crew); else kern = JMM_PICK(k_chains_step_trio);
+#undef JMM_PICK
         cudaError_t e;
         const unsigned nctas = nblk(h->S.nchains, 32);
-        const size_t smem = sizeof(TrioRings) + (size_t) 2 * h->S.N * 32 * sizeof(double);
+        const size_t smem = crew ? sizeof(CrewShared) + (size_t) 3 * h->S.N * 32 * sizeof(double)
+                                 : sizeof(TrioRings) + (size_t) 2 * h->S.N * 32 * sizeof(double);
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
         if (h->work_words < (size_t) nctas) {
             if (h->d_work) cudaFree(h->d_work);
@@ -63,7 +66,7 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
         }
         if ((e = cudaMemsetAsync(h->d_work, 0, (size_t) nctas * sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
         const char *fr = getenv("JMM_SOLO_FORCE_REDO");
-        kern<<<nctas, 96, smem, h->stream>>>(h->S, a, h->d_work, (fr && atoi(fr) != 0) ? 1 : 0);
+        kern<<<nctas, crew ? 160 : 96, smem, h->stream>>>(h->S, a, h->d_work, (fr && atoi(fr) != 0) ? 1 : 0);
         h->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         int npad = (int) h->S.N;

@@ -611,4 +611,367 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
     __syncthreads();                                      // (warp P: the CTA's final barrier)
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_chains_step_crew — five warps per 32 chains.  In k_chains_step_trio the trial warp evaluates the displacement trial
+// AND the volume trial of every chain at every step (32 chains: some lane has a volume trial at 95 % of the steps),
+// ~270 instructions of which a chain uses one half or the other; and warp V's replay became as long as that.  Here
+//   * warp T evaluates displacement trials only and commits them for the chains whose step is one,
+//   * warp F evaluates volume trials only (fav: every bond on r * lRat1) and commits them for the chains whose step
+//     is one; it owns maxdl, the volume counters and maxDVAdjust, as T owns maxStep, the displacement counters and
+//     maxDisAdjust,
+//   * T and F work on ONE set of positions, E and l in shared memory (a chain's column is touched by exactly one of
+//     them in a step — loads of the other's columns are predicated off) and meet at one named barrier per step,
+//   * warp V replays the records for the virial and updateThermo's sums, warp W replays them for ECheck,
+//   * warp P produces the Philox words, as before.
+// Chunked rings, repair of an energy discrepancy by repeating the launch, arithmetic: as k_chains_step_trio.
+struct CrewShared {                                       // [buffer][step][lane]
+    uint32_t nm[2][kTrioChunk][32], w1[2][kTrioChunk][32], w2[2][kTrioChunk][32];     // P -> T, F
+    uint32_t code[2][kTrioChunk][32];                                                   // T, F -> V, W: 0 nothing, 1 | nm << 8 moved, 2 rescaled
+    double val[2][kTrioChunk][32], e[2][kTrioChunk][32], lnew[2][kTrioChunk][32];
+    double E[32], l[32];                                                                // the chains' live energy and length (T and F)
+    int redo;
+};
+
+__device__ __forceinline__ void crew_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void crew_bar_arrive(int id, int n) { __threadfence_block(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int NT, bool LOG, bool INF>
+__global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepArgs a, unsigned int *redo, int force_redo) {
+    extern __shared__ __align__(16) unsigned char crew_smem[];
+    constexpr uint32_t FULL = 0xffffffffu;
+    // named barriers (+ buffer index 0/1): a ring buffer is FULL (producers arrive, consumers sync) or FREE (the reverse)
+    constexpr int P_FULL = 1, P_FREE = 3, D_FULL = 5, D_FREE = 7, STEP = 9;
+    constexpr int kP = 96, kD = 128;                      // threads at a P barrier (P, T, F) and at a D barrier (T, F, V, W)
+    // warp w runs on sub-partition w % 4: the light producer shares one with the energy checker, T and F have their own
+    enum { ROLE_P = 0, ROLE_T = 1, ROLE_F = 2, ROLE_V = 3, ROLE_W = 4 };
+    const uint32_t lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const uint64_t C = S.nchains;
+    const uint64_t c_raw = (uint64_t) blockIdx.x * 32 + lane;
+    const bool own = c_raw < C;
+    const uint64_t chain = own ? c_raw : C - 1;           // (lanes past the last chain shadow it, unsaved)
+    const uint32_t N = NT ? (uint32_t) NT : (uint32_t) S.N;
+    constexpr int NR = NT ? NT : 1;
+    CrewShared &R = *reinterpret_cast<CrewShared *>(crew_smem);
+    double *tiles = reinterpret_cast<double *>(crew_smem + sizeof(CrewShared));
+    const uint32_t nsteps = (uint32_t) a.nsteps;
+    const uint32_t nchunks = (nsteps + kTrioChunk - 1) / kTrioChunk;
+    const double cutoff = S.cutoff;
+
+    if (role == ROLE_T) {                                 // the live state, before anyone reads it
+        double *r = tiles + lane;
+        for (uint32_t i = 0; i < N; ++i) r[i * 32] = S.r[(uint64_t) i * C + chain];
+        R.E[lane] = S.tot[chain]; R.l[lane] = S.l[chain];
+    }
+    __syncthreads();
+
+    if (role == ROLE_P) {
+        // ---------------------------------------------------------------- P: trial types and random words
+        const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t)(S.seed >> 32), cid = (uint32_t)(S.chain_id0 + chain);
+        const uint32_t ntt = (uint32_t) S.numTrialTypes, scale = 0xffffffffu / ntt;
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            if (k >= 2) crew_bar_sync(P_FREE + b, kP);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            const uint64_t step0 = a.sn0 + (uint64_t) k * kTrioChunk + 1;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint64_t step = step0 + j;
+                const Philox4 blk = philox4x32_10((uint32_t) step, (uint32_t)(step >> 32), cid, kTagTrial, k0, k1);
+                uint32_t t = blk.w[0] / scale;            // gsl_rng_uniform_int rule, see Rng<kRngPhilox>
+                if (t >= ntt) t = b2_redraw(blk.w[3], scale, ntt);
+                R.nm[b][j][lane] = t; R.w1[b][j][lane] = blk.w[1]; R.w2[b][j][lane] = blk.w[2];
+            }
+            crew_bar_arrive(P_FULL + b, kP);
+        }
+    } else if (role == ROLE_V) {
+        // ---------------------------------------------------------------- V: virial and updateThermo on a replayed copy
+        double *r = tiles + (size_t) N * 32 + lane;
+        double l = S.l[chain], rho = (double) N / l, two_over_l = 2 / l;
+        double E = S.tot[chain], Vir = S.tot[C + chain];
+        double acc[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] = S.acc[k * C + chain];
+        for (uint32_t i = 0; i < N; ++i) r[i * 32] = S.r[(uint64_t) i * C + chain];
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            crew_bar_sync(D_FULL + b, kD);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            uint32_t code = R.code[b][0][lane];
+            double val = R.val[b][0][lane], e_rec = R.e[b][0][lane];
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t code1 = j + 1 < n ? R.code[b][j + 1][lane] : 0u;       // (the next record: its latency hides behind this one)
+                const double val1 = j + 1 < n ? R.val[b][j + 1][lane] : 0.0, e1 = j + 1 < n ? R.e[b][j + 1][lane] : 0.0;
+                {                                                                     // an accepted move: its virial change, qad2 :1244,1339,1354
+                    const bool moved = code & 1u;
+                    const uint32_t i0 = moved ? (code >> 8) : 0u;
+                    const bool hasL = i0 > 0, hasR = i0 + 1 < N;
+                    const double rnm = r[i0 * 32], rl = r[(hasL ? i0 - 1 : i0) * 32], rr = r[(hasR ? i0 + 1 : i0) * 32];
+                    double pe, po1, pn1, qo1, qn1;
+                    b2_phi<INF>(rnm - rl, cutoff, two_over_l, pe, po1);
+                    b2_phi<INF>(val - rl, cutoff, two_over_l, pe, pn1);
+                    b2_phi<INF>(rr - rnm, cutoff, two_over_l, pe, qo1);
+                    b2_phi<INF>(rr - val, cutoff, two_over_l, pe, qn1);
+                    const double l1 = hasL ? (0.0 - po1 + pn1) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;
+                    if (moved) { Vir = Vir + (l1 + r1); r[i0 * 32] = val; }
+                }
+                if (__any_sync(FULL, code == 2u)) {                                   // an accepted volume trial: r *= lRat1 (:2264-2266), Vir from all bonds
+                    if (code == 2u) {
+                        l = R.lnew[b][j][lane];
+                        rho = (double) N / l;
+                        two_over_l = 2 / l;
+                        double v = 0;
+                        double ri = r[0] * val;
+                        r[0] = ri;
+                        for (uint32_t i = 0; i + 1 < N; ++i) {
+                            const double rj = r[(i + 1) * 32] * val;
+                            r[(i + 1) * 32] = rj;
+                            double pe, pv;
+                            b2_phi<INF>(rj - ri, cutoff, two_over_l, pe, pv);
+                            v += pv;
+                            ri = rj;
+                        }
+                        Vir = v;
+                    }
+                }
+                E = e_rec;
+                acc[0] = acc[0] + rho;     acc[1] = acc[1] + rho * rho;             // updateThermo :1941-1961
+                acc[2] = acc[2] + l;       acc[3] = acc[3] + l * l;
+                acc[4] = acc[4] + E;       acc[5] = acc[5] + E * E;
+                acc[6] = acc[6] + l * E;   acc[7] = acc[7] + Vir;
+                acc[8] = acc[8] + Vir * Vir; acc[9] = acc[9] + E * Vir;
+                code = code1; val = val1; e_rec = e1;
+            }
+            if (k + 2 < nchunks) crew_bar_arrive(D_FREE + b, kD);
+        }
+        __syncthreads();                                  // warp W's verdict
+        if (!R.redo && own) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) S.acc[k * C + chain] = acc[k];
+            S.tot[C + chain] = Vir;
+        }
+        return;
+    } else if (role == ROLE_W) {
+        // ---------------------------------------------------------------- W: ECheck :1965-2095 on a replayed copy
+        double *r = tiles + (size_t) 2 * N * 32 + lane;
+        for (uint32_t i = 0; i < N; ++i) r[i * 32] = S.r[(uint64_t) i * C + chain];
+        const uint64_t echecks = S.echeck[chain];
+        uint32_t t_checks = 0;
+        const uint32_t eci32 = a.eci > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.eci;
+        uint32_t eci_left = 0xffffffffu;
+        if (a.eci) { const uint64_t left = a.eci - a.sn0 % a.eci; eci_left = left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left; }
+        bool bad = force_redo != 0;
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            crew_bar_sync(D_FULL + b, kD);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t code = R.code[b][j][lane];
+                const double val = R.val[b][j][lane], E = R.e[b][j][lane];
+                if (__any_sync(FULL, code == 2u)) {
+                    if (code == 2u) for (uint32_t i = 0; i < N; ++i) r[i * 32] = r[i * 32] * val;
+                }
+                if (code & 1u) r[(code >> 8) * 32] = val;
+                if (eci32 == 1 || --eci_left == 0) {
+                    double et = 0;
+                    if constexpr (NT > 0) {
+                        double q[NR];
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) q[i] = r[i * 32];
+#pragma unroll
+                        for (int i = 0; i + 1 < NT; ++i) et += b2_bond_energy<INF>(q[i + 1] - q[i], cutoff);
+                    } else {
+                        double qi = r[0];
+                        for (uint32_t i = 0; i + 1 < N; ++i) { const double qj = r[(i + 1) * 32]; et += b2_bond_energy<INF>(qj - qi, cutoff); qi = qj; }
+                    }
+                    ++t_checks;
+                    bad = bad || fabs(et - E) > 0.0001;
+                    eci_left = eci32;
+                }
+            }
+            if (k + 2 < nchunks) crew_bar_arrive(D_FREE + b, kD);
+        }
+        const bool any_bad = __any_sync(FULL, bad);
+        if (lane == 0) { R.redo = any_bad ? 1 : 0; if (any_bad) redo[blockIdx.x] = 1u; }
+        __syncthreads();
+        if (!any_bad && own) S.echeck[chain] = echecks + t_checks;
+        return;
+    } else if (role == ROLE_T) {
+        // ---------------------------------------------------------------- T: displacement trials, qad2 :1160-1464 with NBN 1
+        double *r = tiles + lane;
+        double maxStep = S.maxStep[chain];
+        const double T = S.T[chain], invT = 1.0 / T;
+        uint64_t cnt0 = S.cnt[chain], cnt1 = S.cnt[C + chain];
+        uint32_t t_acc = 0, t_rej = 0;
+        const uint32_t mdai32 = a.mdai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mdai;
+        uint32_t mdai_left = 0xffffffffu;
+        if (a.adapt_device && a.mdai) { const uint64_t left = a.mdai - a.sn0 % a.mdai; mdai_left = left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left; }
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            crew_bar_sync(P_FULL + b, kP);
+            if (k >= 2) crew_bar_sync(D_FREE + b, kD);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            uint32_t nm = R.nm[b][0][lane], w1 = R.w1[b][0][lane], w2 = R.w2[b][0][lane];
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t nm1 = j + 1 < n ? R.nm[b][j + 1][lane] : 0u, w11 = j + 1 < n ? R.w1[b][j + 1][lane] : 0u,
+                               w21 = j + 1 < n ? R.w2[b][j + 1][lane] : 0u;
+                const bool disp = nm < N;
+                const double rnh = u01_shifted(w1, 1.5);                              // rn - 0.5, exactly (rng.cuh)
+                const double ran = u01_shifted(w2, 1.0);
+                const uint32_t i0 = disp ? nm : 0u;
+                const bool hasL = i0 > 0, hasR = i0 + 1 < N;
+                // (a chain on a volume trial belongs to warp F in this step: its column is not read)
+                const double E = disp ? R.E[lane] : 0.0, half_l = disp ? R.l[lane] / 2.0 : 0.0;
+                const double rnm = disp ? r[i0 * 32] : 0.0, rl = disp ? r[(hasL ? i0 - 1 : i0) * 32] : 0.0, rr = disp ? r[(hasR ? i0 + 1 : i0) * 32] : 0.0;
+                const double rT = rnm + rnh * 2 * maxStep;                            // :1182-1183
+                const bool wall = fabs(rT) > half_l;                                  // :1188
+                const double po0 = b2_bond_energy<INF>(rnm - rl, cutoff), pn0 = b2_bond_energy<INF>(rT - rl, cutoff);
+                const double qo0 = b2_bond_energy<INF>(rr - rnm, cutoff), qn0 = b2_bond_energy<INF>(rr - rT, cutoff);
+                const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0;                     // :1244
+                const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0;                     // :1339
+                const double dE = l0 + r0;                                            // :1354
+                const double ea = (double) exp_neg_approx(dE * invT);                 // Metropolis :1367-1377, band of metropolis_accept()
+                const bool down = dE <= 0;
+                const bool acc_b = ran < ea - kMetropolisBand, rej_b = ran > ea + kMetropolisBand;
+                bool accept_d = down | acc_b;
+                const bool undecided = disp && !wall && !(down | acc_b | rej_b);
+                if (__any_sync(FULL, undecided)) {
+                    if (undecided) accept_d = metropolis_exact(dE, T, ran);
+                }
+                const bool ok_d = disp && !wall && accept_d;                          // :1384-1394
+                const double Enew = ok_d ? E + dE : E;
+                if (ok_d) { r[nm * 32] = rT; R.E[lane] = Enew; }
+                if (disp) {
+                    R.code[b][j][lane] = ok_d ? (1u | (nm << 8)) : 0u;
+                    R.val[b][j][lane] = rT;
+                    R.e[b][j][lane] = Enew;
+                    if (LOG && own) a.accept_log[(uint64_t)(k * kTrioChunk + j) * C + chain] = wall ? kLogWall : (ok_d ? kLogAccepted : 0);
+                }
+                t_acc += ok_d ? 1u : 0u;
+                t_rej += (disp && !ok_d) ? 1u : 0u;
+                if (--mdai_left == 0) {                                               // maxDisAdjust :2100-2115 (src/Main.cpp:145-155)
+                    cnt0 += t_acc; cnt1 += t_rej; t_acc = t_rej = 0;
+                    const double actualRatio = (double) cnt0 / (double)(cnt0 + cnt1);
+                    maxStep = maxStep * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+                    if (maxStep < 0.002) maxStep = 0.002;
+                    else if (maxStep > 0.5) maxStep = 0.5;
+                    mdai_left = mdai32;
+                }
+                nm = nm1; w1 = w11; w2 = w21;
+                crew_bar_sync(STEP, 64);                                              // warp F has committed its chains' step
+            }
+            crew_bar_arrive(D_FULL + b, kD);
+            if (k + 2 < nchunks) crew_bar_arrive(P_FREE + b, kP);
+        }
+        cnt0 += t_acc; cnt1 += t_rej;
+        __syncthreads();                                  // warp W's verdict
+        if (R.redo || !own) return;
+        for (uint32_t i = 0; i < N; ++i) S.r[(uint64_t) i * C + chain] = r[i * 32];
+        S.l[chain] = R.l[lane]; S.maxStep[chain] = maxStep;
+        S.tot[chain] = R.E[lane];                         // (the virial is warp V's)
+#pragma unroll
+        for (int k = 2; k < kNTot; ++k) S.tot[k * C + chain] = 0.0;
+        S.cnt[chain] = cnt0; S.cnt[C + chain] = cnt1;
+        return;
+    } else {
+        // ---------------------------------------------------------------- F: volume trials, fav :2161-2293
+        double *r = tiles + lane;
+        double maxdl = S.maxdl[chain];
+        const double P = S.P[chain], T = S.T[chain], invT = 1.0 / T;
+        uint64_t cnt2 = S.cnt[2 * C + chain], cnt3 = S.cnt[3 * C + chain], vAErr = S.vAErr[chain];
+        uint32_t t_acc = 0, t_rej = 0;
+        const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
+        uint32_t mvai_left = 0xffffffffu;
+        if (a.adapt_device && a.mvai) { const uint64_t left = a.mvai - a.sn0 % a.mvai; mvai_left = left > 0xfffffffeull ? 0xffffffffu : (uint32_t) left; }
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const int b = k & 1;
+            crew_bar_sync(P_FULL + b, kP);
+            if (k >= 2) crew_bar_sync(D_FREE + b, kD);
+            const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
+            uint32_t nm = R.nm[b][0][lane], w1 = R.w1[b][0][lane], w2 = R.w2[b][0][lane];
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t nm1 = j + 1 < n ? R.nm[b][j + 1][lane] : 0u, w11 = j + 1 < n ? R.w1[b][j + 1][lane] : 0u,
+                               w21 = j + 1 < n ? R.w2[b][j + 1][lane] : 0u;
+                const bool vol = !(nm < N);
+                const double rnh = u01_shifted(w1, 1.5);                              // rn - 0.5, exactly (rng.cuh)
+                const double ran = u01_shifted(w2, 1.0);
+                // (a chain on a displacement trial belongs to warp T in this step: its column is not read; 1.0 keeps the arithmetic finite)
+                const double E = vol ? R.E[lane] : 0.0, l = vol ? R.l[lane] : 1.0;
+                const double dl = rnh * 2 * maxdl;
+                const double lnew = l + dl;
+                const double lRat1 = lnew / l;
+                double rs[NR];
+                double t0 = 0;
+                if constexpr (NT > 0) {
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) rs[i] = (vol ? r[i * 32] : 0.0) * lRat1;
+#pragma unroll
+                    for (int i = 0; i + 1 < NT; ++i) t0 += b2_bond_energy<INF>(rs[i + 1] - rs[i], cutoff);
+                } else {
+                    double ri = (vol ? r[0] : 0.0) * lRat1;
+                    for (uint32_t i = 0; i + 1 < N; ++i) {
+                        const double rj = (vol ? r[(i + 1) * 32] : 0.0) * lRat1;
+                        t0 += b2_bond_energy<INF>(rj - ri, cutoff);
+                        ri = rj;
+                    }
+                }
+                const double x = t0 - E + P * dl;                                     // :2249, volume_accept (pot.cuh)
+                float lg;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float) lRat1));
+                const double A = (double) N * ((double) lg * 0.6931471805599453) - x * invT;
+                const double bb = (double) exp_neg_approx(-A);
+                const double band = volume_accept_band((double) N, (double) lg, A);
+                const bool narrow = lRat1 > kVolumeBandLo && lRat1 < kVolumeBandHi;
+                const bool v_yes = narrow && ran < bb * (1.0 - band), v_no = narrow && ran > bb * (1.0 + band);
+                bool accept_v = v_yes;
+                const bool v_open = vol && !(v_yes | v_no);
+                if (__any_sync(FULL, v_open)) {                                       // inside the approximation band: the exact expression
+                    if (v_open) accept_v = volume_accept_exact(x, T, (double) N, lRat1, ran);
+                }
+                const bool ok_v = vol && accept_v;                                    // :2257-2275
+                if (ok_v) {
+                    R.l[lane] = lnew; R.E[lane] = t0;
+                    if constexpr (NT > 0) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) r[i * 32] = rs[i];
+                    } else {
+                        for (uint32_t i = 0; i < N; ++i) r[i * 32] = r[i * 32] * lRat1;
+                    }
+                    R.lnew[b][j][lane] = lnew;
+                }
+                if (vol) {
+                    R.code[b][j][lane] = ok_v ? 2u : 0u;
+                    R.val[b][j][lane] = lRat1;
+                    R.e[b][j][lane] = ok_v ? t0 : E;
+                    if (LOG && own) a.accept_log[(uint64_t)(k * kTrioChunk + j) * C + chain] = (uint8_t)(kLogVolume | (ok_v ? kLogAccepted : 0));
+                }
+                t_acc += ok_v ? 1u : 0u;
+                t_rej += (vol && !ok_v) ? 1u : 0u;
+                if (--mvai_left == 0) {                                               // maxDVAdjust :2120-2139 (src/Main.cpp:156-165)
+                    cnt2 += t_acc; cnt3 += t_rej; t_acc = t_rej = 0;
+                    if ((cnt2 + cnt3 - vAErr) > 0) {
+                        vAErr = cnt2 + cnt3;
+                        const double actualRatio = (double) cnt2 / (double)(cnt2 + cnt3);
+                        maxdl = maxdl * a.log_ideal / log(0.672924 * (actualRatio + 0.0644284));
+                        if (maxdl < 0.002 * (double) N) maxdl = 0.002 * (double) N;
+                        else if (maxdl > 0.10 * (double) N) maxdl = 0.50 * (double) N;
+                    }
+                    mvai_left = mvai32;
+                }
+                nm = nm1; w1 = w11; w2 = w21;
+                crew_bar_sync(STEP, 64);                                              // warp T has committed its chains' step
+            }
+            crew_bar_arrive(D_FULL + b, kD);
+            if (k + 2 < nchunks) crew_bar_arrive(P_FREE + b, kP);
+        }
+        cnt2 += t_acc; cnt3 += t_rej;
+        __syncthreads();                                  // warp W's verdict
+        if (R.redo || !own) return;
+        S.maxdl[chain] = maxdl;
+        S.cnt[2 * C + chain] = cnt2; S.cnt[3 * C + chain] = cnt3;
+        S.vAErr[chain] = vAErr;
+        return;
+    }
+    __syncthreads();                                      // (warp P: the CTA's final barrier)
+}
+
 }  // namespace jmm

@@ -1,7 +1,7 @@
 #!/bin/bash
 # solo.cuh (one chain per thread, a warp per SM) against bond.cuh on the C2 workload: parity, throughput, profile.
 OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r2v}
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 300 --timeout-method thread -k "solo or trio or c2_bench" > $OUT/pytest_solo_$TAG.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 300 --timeout-method thread -k "solo or trio or crew or c2_bench" > $OUT/pytest_solo_$TAG.log 2>&1
 tail -5 $OUT/pytest_solo_$TAG.log
 grep -n "FAILED\|Error\|assert \|Timeout" $OUT/pytest_solo_$TAG.log | head -20
 b() {  # label, env...
@@ -20,7 +20,8 @@ PY
 b "bond (16 lanes/chain)"  JMM_BOND=1
 b "solo (1 thread/chain)"  JMM_BOND=3
 b "trio (3 warps/32 chains)" JMM_BOND=4
-JMM_BOND=${PROF_BOND:-4} timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_chains_step_(solo|trio)" -s 1 -c 1 -f -o $OUT/prof_c2solo_$TAG \
+b "crew (5 warps/32 chains)" JMM_BOND=5
+JMM_BOND=${PROF_BOND:-5} timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_chains_step_(solo|trio|crew)" -s 1 -c 1 -f -o $OUT/prof_c2solo_$TAG \
     python bench.py --steps 1 --warmup 2 --no-extras > $OUT/ncu_c2solo_$TAG.log 2>&1; tail -1 $OUT/ncu_c2solo_$TAG.log | cut -c1-200
 python scripts/ncu_summary.py $OUT/prof_c2solo_$TAG.ncu-rep 25600000 > $OUT/prof_c2solo_$TAG.txt 2>&1
 python scripts/ncu_lines.py $OUT/prof_c2solo_$TAG.ncu-rep 25600000 70 >> $OUT/prof_c2solo_$TAG.txt 2>&1

@@ -158,6 +158,8 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
     "solo": {"JMM_COOP_G": "16", "JMM_BOND": "3"},      # solo.cuh, k_chains_step_solo (one chain per thread, a warp per SM; HARMONIC NBN 1 decks)
     "trio": {"JMM_COOP_G": "16", "JMM_BOND": "4"},      # solo.cuh, k_chains_step_trio (trials | Philox | ECheck + sums in three warps)
     "trioredo": {"JMM_COOP_G": "16", "JMM_BOND": "4", "JMM_SOLO_FORCE_REDO": "1"},   # ... every CTA reports a discrepancy: bond.cuh repeats the launch
+    "crew": {"JMM_COOP_G": "16", "JMM_BOND": "5"},      # solo.cuh, k_chains_step_crew (displacement | volume | Philox | virial + sums | ECheck)
+    "crewredo": {"JMM_COOP_G": "16", "JMM_BOND": "5", "JMM_SOLO_FORCE_REDO": "1"},
     "coop32": {"JMM_COOP_G": "32"},
     "coop8": {"JMM_COOP_G": "8"},
     "prod": {"JMM_COOP_G": "0"},                        # prod.cuh, one chain per thread, shared tile
@@ -167,7 +169,7 @@ ENGINES = {   # which kernel serves a JMM_MODE_RECOMPUTE + Philox handle (jmm_gp
 
 
 @pytest.mark.parametrize("name", list(DECKS))
-@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-bond2", "recompute-solo", "recompute-trio", "recompute-trioredo", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
+@pytest.mark.parametrize("mode", ["recompute", "table", "recompute-coop", "recompute-bond", "recompute-bond2", "recompute-solo", "recompute-trio", "recompute-trioredo", "recompute-crew", "recompute-crewredo", "recompute-coop32", "recompute-coop8", "recompute-prod", "recompute-sliced", "recompute-generic"])
 def test_philox_many_chains_bit_exact(J, O, name, mode, monkeypatch):
     """Production stream, several chains per launch, host-side adaptation (glibc log on both sides):
     every chain must equal the oracle bit for bit, including after adjustments and relaxations —
@@ -369,7 +371,7 @@ def test_sweep_shape_matches_oracle(J, O, engine, start, monkeypatch):
         assert oc.relax_calls == relax0 + (1 if start == "from0" else 0)
 
 
-@pytest.mark.parametrize("engine", ["default", "bond", "solo", "trio"])
+@pytest.mark.parametrize("engine", ["default", "bond", "solo", "trio", "crew"])
 def test_c2_bench_mode_matches_oracle_on_sampled_chains(J, O, engine, monkeypatch):
     """The C2 workload as bench.py runs it (INPUTstd x 4096 chains; the default kernel, bond.cuh and solo.cuh), with the
     step sizes adapted by the host's libm (JMM_ADAPT_HOST: glibc log on both sides, so adaptation cannot hide a
