@@ -321,16 +321,17 @@ extern "C" jmm_status jmm_create(const jmm_config *cfg, jmm_handle **out) {
             if (h->coop_g && cfg->pot == JMM_POT_HARMONIC && cfg->nbn == 1 && N - 1 <= 16 && !(h->cfg.relax > 0) &&
                 C <= 16384 && !(eb && atoi(eb) == 0))
             {
-                // 4 = k_chains_step_trio (solo.cuh: three warps per 32 chains — trials | Philox | virial, ECheck, sums; the
-                //     default while every 32-chain CTA is resident at once, two per SM: 7.5e9 trials/s and more on C2),
-                // 1 = k_chains_step_bond (16 lanes per chain: 4.47e9; also what repeats a launch of 4 after an energy discrepancy),
-                // 2 = k_chains_step_bond2 (registers-only, deferred ECheck: 3.99e9, profiles/r2e_c2_*),
+                // 5 = k_chains_step_crew (solo.cuh: five warps per 32 chains — displacement | volume | Philox | virial + sums |
+                //     ECheck; 1.13e10 trial moves/s on C2) — the default while every 32-chain CTA is resident at once (two per
+                //     SM); a deck without volume trials (NLT) runs 4 instead,
+                // 4 = k_chains_step_trio (three warps per 32 chains: trials | Philox | virial + ECheck + sums; 9.15e9),
                 // 3 = k_chains_step_solo (one warp per 32 chains doing all of it: 4.97e9),
-                // 5 = k_chains_step_crew (five warps per 32 chains: displacement | volume | Philox | virial + sums | ECheck).
-                // All parity-tested.
+                // 2 = k_chains_step_bond2 (registers-only, deferred ECheck: 3.99e9, profiles/r2e_c2_*),
+                // 1 = k_chains_step_bond (16 lanes per chain: 4.47e9; also what repeats a launch of 4 / 5 after an energy
+                //     discrepancy, and what more than 2 x SMs x 32 chains get).  All parity-tested.
                 int nsm = 0;
                 cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
-                const int fallback = (C + 31) / 32 <= (uint64_t) 2 * (uint64_t) std::max(nsm, 1) ? 4 : 1;
+                const int fallback = (C + 31) / 32 <= (uint64_t) 2 * (uint64_t) std::max(nsm, 1) ? 5 : 1;
                 h->bond = (eb && atoi(eb) >= 1 && atoi(eb) <= 5) ? atoi(eb) : fallback;
             }
         }

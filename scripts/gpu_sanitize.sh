@@ -19,7 +19,11 @@ lj = dict(N=12, pot=J.POT_LJ, nbn=-1, P=1.0, T=0.9, maxStep=0.1, maxdl=0.1, eci=
 ljc = dict(N=24, pot=J.POT_LJCUT, nbn=3, cutoff=2.5, P=0.5, T=0.7, maxStep=0.15, maxdl=0.4, eci=5, mdai=20, mvai=30, seed=7, relax=1)
 which = os.environ.get("SAN_CASE", "all")
 cases = {
- "bond": lambda: run(config(nchains=37, **std)),
+ "bond": lambda: (os.environ.__setitem__("JMM_BOND", "1"), run(config(nchains=37, **std)), os.environ.pop("JMM_BOND")),
+ "solo": lambda: (os.environ.__setitem__("JMM_BOND", "3"), run(config(nchains=37, **std), 150), os.environ.pop("JMM_BOND")),
+ "trio": lambda: (os.environ.__setitem__("JMM_BOND", "4"), run(config(nchains=37, **std), 150), run(config(nchains=37, adapt=J.ADAPT_DEVICE, **std), 150), os.environ.pop("JMM_BOND")),
+ "crew": lambda: (os.environ.__setitem__("JMM_BOND", "5"), run(config(nchains=37, **std), 150), run(config(nchains=37, adapt=J.ADAPT_DEVICE, **std), 150),
+                  os.environ.__setitem__("JMM_SOLO_FORCE_REDO", "1"), run(config(nchains=37, **std), 70), os.environ.pop("JMM_SOLO_FORCE_REDO"), os.environ.pop("JMM_BOND")),
  "bond2": lambda: (os.environ.__setitem__("JMM_BOND", "2"), run(config(nchains=37, **std)), os.environ.__setitem__("JMM_BOND", "1")),
  "lanes": lambda: [(os.environ.__setitem__("JMM_LANES_G", g), run(config(nchains=21, arith=J.ARITH_FAST, adapt=J.ADAPT_DEVICE, **lj), 90),
                     run(config(nchains=21, arith=J.ARITH_FAST, **ljc), 90)) for g in ("8", "4", "32")] + [os.environ.pop("JMM_LANES_G")],
@@ -41,7 +45,7 @@ for k, f in cases.items():
     if which in ("all", k): f(); print("case", k, "ok")
 PY
 for tool in memcheck racecheck; do
-  for c in ${SAN_CASES:-bond bond2 lanes lanes80 coop prod sliced generic sweep sweep_shapes}; do
+  for c in ${SAN_CASES:-bond bond2 solo trio crew lanes lanes80 coop prod sliced generic sweep sweep_shapes}; do
     echo "== $tool $c"
     SAN_CASE=$c timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|case|Error|error|hazard|Invalid" | head -8
   done
