@@ -455,7 +455,7 @@ def measure_c2(E: Env, steps: int, warmup: int, with_e2e: bool = True) -> dict:
     h.step(MC_PER_STEP)
     k_ms = h.last_kernel_ms
     out = {"dev_ms": dev_ms, "steps": steps, "trials_rank": trials, "value": E.allsum(trials) / (dev_ms * 1e-3), "per_step_ms": per,
-           "clocks": clocks, "launches": int(launches), "kernel_ms": k_ms, "chains": C}
+           "clocks": clocks, "launches": int(launches), "kernel_ms": k_ms, "chains": C, "engine": h.engine}
     if with_e2e:
         sec, h2d, d2h = e2e_chains(E, h, MC_PER_STEP, steps)
         out["e2e"] = {"value": E.world * C * MC_PER_STEP * steps / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
@@ -636,9 +636,9 @@ def gpu_arm(args) -> None:
                                    "the INPUT_smalltest shape (N=10, LJ, P=1.0, T=0.9): Main.serial.c is LJ only and cannot run the HARMONIC C2 deck")
     except Exception as e:
         serial = {"value": None, "sample": f"failed: {e}"}
-    roof = roofline_fp64(E, m["value"], FLOP_PER_TRIAL, "k_chains_step_bond", m["kernel_ms"], extra={
-        "kernel": "k_chains_step_bond (bond.cuh: HARMONIC NBN 1)",
-        "note": "serial Markov chains: latency-bound, see DESIGN.md §roofline",
+    roof = roofline_fp64(E, m["value"], FLOP_PER_TRIAL, m["engine"], m["kernel_ms"], extra={
+        "kernel": m["engine"] + " (HARMONIC NBN 1: solo.cuh / bond.cuh)",
+        "note": "serial Markov chains: bound by the latency of one step, see DESIGN.md §3.1",
         "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
                 "bytes_per_launch": C * BYTES_PER_CHAIN_PER_LAUNCH}})

@@ -249,6 +249,9 @@ int32_t    jmm_nccl_version(void);
  * jmm_sweep / jmm_energy kernel(s) in ms (CUDA events on the handle's stream) */
 uint64_t   jmm_kernel_launches(const jmm_handle *h);
 double     jmm_last_kernel_ms(const jmm_handle *h);
+/* name of the kernel family jmm_step (jmm_sweep for a checkerboard handle) launches for this handle, e.g.
+ * "k_chains_step_crew", "k_chains_step_lanes<G=8>", "k_chains_step_prod"; a static string */
+const char *jmm_engine(const jmm_handle *h);
 /* run on this CUDA stream (cudaStream_t as void*) instead of the handle's own */
 jmm_status jmm_set_stream(jmm_handle *h, void *cuda_stream);
 /* pinned host memory for the caller's staging buffers (cudaHostAlloc / cudaFreeHost) */

@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
         "jmm_checkpoint_load": (C.c_int32, [H, C.c_char_p]),
         "jmm_kernel_launches": (C.c_uint64, [H]),
         "jmm_last_kernel_ms": (C.c_double, [H]),
+        "jmm_engine": (C.c_char_p, [H]),
         "jmm_set_stream": (C.c_int32, [H, C.c_void_p]),
         "jmm_host_alloc": (C.c_void_p, [C.c_uint64]),
         "jmm_host_free": (None, [C.c_void_p]),
@@ -338,6 +339,11 @@ class Handle:
     @property
     def last_kernel_ms(self):
         return float(self.L.jmm_last_kernel_ms(self.h))
+
+    @property
+    def engine(self) -> str:
+        """Name of the kernel family jmm_step / jmm_sweep launches for this handle (jmm_engine)."""
+        return self.L.jmm_engine(self.h).decode()
 
     def set_stream(self, cuda_stream_ptr):
         _check(self.L.jmm_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

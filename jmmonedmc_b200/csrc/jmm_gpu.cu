@@ -529,6 +529,37 @@ extern "C" jmm_status jmm_set_step_number(jmm_handle *h, uint64_t sn) {
 extern "C" uint64_t jmm_stream_cursor(const jmm_handle *h) { return h ? h->cursor : 0; }
 extern "C" uint64_t jmm_kernel_launches(const jmm_handle *h) { return h ? h->launches : 0; }
 
+extern "C" const char *jmm_engine(const jmm_handle *h) {          // mirrors launch_step_table / jmm_launch_coop / jmm_launch_lanes
+    if (!h) return "";
+    if (h->cfg.mode == JMM_MODE_CHECKERBOARD) return h->cfg.arith == JMM_ARITH_FAST ? "k_sweep_fast" : "k_sweep";
+    if (h->cfg.mode == JMM_MODE_TABLE) return "k_chains_step<TABLE>";
+    if (h->lanes_g) {
+        const char *t = getenv("JMM_TEAM");
+        if (t && atoi(t) != 0 && h->lanes_g == 8 && h->lanes_npl == 10) return "k_chains_step_team";
+        switch (h->lanes_g) {
+            case 2: return "k_chains_step_lanes<G=2>";
+            case 4: return "k_chains_step_lanes<G=4>";
+            case 8: return "k_chains_step_lanes<G=8>";
+            case 16: return "k_chains_step_lanes<G=16>";
+            default: return "k_chains_step_lanes<G=32>";
+        }
+    }
+    if (h->coop_g) {
+        if (h->cfg.pot == JMM_POT_HARMONIC && h->bond) {
+            switch (h->bond) {
+                case 5: return (uint64_t) h->S.numTrialTypes > h->S.N ? "k_chains_step_crew" : "k_chains_step_trio";
+                case 4: return "k_chains_step_trio";
+                case 3: return "k_chains_step_solo";
+                case 2: return "k_chains_step_bond2";
+                default: return "k_chains_step_bond";
+            }
+        }
+        return "k_chains_step_coop";
+    }
+    if (h->cfg.rng_kind == JMM_RNG_PHILOX && h->pos_in_smem && h->block == 32 && !getenv("JMM_NO_PROD")) return "k_chains_step_prod";
+    return "k_chains_step";
+}
+
 extern "C" double jmm_last_kernel_ms(const jmm_handle *hc) {
     jmm_handle *h = const_cast<jmm_handle *>(hc);
     if (!h || !h->ev0 || !h->ev1) return -1.0;

@@ -55,7 +55,7 @@ static cudaError_t launch_step_bond(jmm_handle *h, const StepArgs &a) {
 #undef JMM_PICK
         cudaError_t e;
         const unsigned nctas = nblk(h->S.nchains, 32);
-        const size_t smem = crew ? sizeof(CrewShared) + (size_t) 3 * h->S.N * 32 * sizeof(double)
+        const size_t smem = crew ? sizeof(CrewShared) + (size_t) 4 * h->S.N * 32 * sizeof(double)   // live, V's copy, W's copy, zeros
                                  : sizeof(TrioRings) + (size_t) 2 * h->S.N * 32 * sizeof(double);
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e;
         if (h->work_words < (size_t) nctas) {

@@ -380,7 +380,9 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
                 const uint32_t code = R.code[b][j][lane];
                 const double val = R.val[b][j][lane];
                 double pe_unused;
-                {                                                                     // an accepted move: its virial change, qad2 :1244,1339,1354
+                {   // an accepted move: its virial change, qad2 :1244,1339,1354.  (Keeping every bond's term in shared memory and reading
+                    // the two OLD ones from there instead of evaluating them was measured: 1.00e10 against 1.13e10 — the loads and
+                    // their write-backs sit on the step's dependency chain, profiles/r2zd_*, r2ze_c2_crew_ab.jsonl.)
                     const bool moved = code & 1u;
                     const uint32_t i0 = moved ? (code >> 8) : 0u;
                     const bool hasL = i0 > 0, hasR = i0 + 1 < N;
@@ -621,10 +623,16 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
 //     is one; it owns maxdl, the volume counters and maxDVAdjust, as T owns maxStep, the displacement counters and
 //     maxDisAdjust,
 //   * T and F work on ONE set of positions, E and l in shared memory (a chain's column is touched by exactly one of
-//     them in a step — loads of the other's columns are predicated off) and meet at one named barrier per step,
+//     them in a step — the other reads a column of zeros instead) and meet at one named barrier per step,
 //   * warp V replays the records for the virial and updateThermo's sums, warp W replays them for ECheck,
 //   * warp P produces the Philox words, as before.
 // Chunked rings, repair of an energy discrepancy by repeating the launch, arithmetic: as k_chains_step_trio.
+#ifndef JMM_CREW_ZEROCOL
+#define JMM_CREW_ZEROCOL 1        // 1: T / F read a column of zeros for the other's chains; 0: predicated loads
+#endif
+#ifndef JMM_CREW_BANDFMA
+#define JMM_CREW_BANDFMA 1        // 1: the volume band with folded constants; 0: volume_accept_band()
+#endif
 struct CrewShared {                                       // [buffer][step][lane]
     uint32_t nm[2][kTrioChunk][32], w1[2][kTrioChunk][32], w2[2][kTrioChunk][32];     // P -> T, F
     uint32_t code[2][kTrioChunk][32];                                                   // T, F -> V, W: 0 nothing, 1 | nm << 8 moved, 2 rescaled
@@ -658,9 +666,10 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
     const uint32_t nchunks = (nsteps + kTrioChunk - 1) / kTrioChunk;
     const double cutoff = S.cutoff;
 
+    const double *zeros = tiles + (size_t) 3 * N * 32 + lane;   // a column nobody writes: what T reads of F's chains and F of T's
     if (role == ROLE_T) {                                 // the live state, before anyone reads it
         double *r = tiles + lane;
-        for (uint32_t i = 0; i < N; ++i) r[i * 32] = S.r[(uint64_t) i * C + chain];
+        for (uint32_t i = 0; i < N; ++i) { r[i * 32] = S.r[(uint64_t) i * C + chain]; tiles[(size_t) 3 * N * 32 + i * 32 + lane] = 0.0; }
         R.E[lane] = S.tot[chain]; R.l[lane] = S.l[chain];
     }
     __syncthreads();
@@ -701,7 +710,9 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
             for (uint32_t j = 0; j < n; ++j) {
                 const uint32_t code1 = j + 1 < n ? R.code[b][j + 1][lane] : 0u;       // (the next record: its latency hides behind this one)
                 const double val1 = j + 1 < n ? R.val[b][j + 1][lane] : 0.0, e1 = j + 1 < n ? R.e[b][j + 1][lane] : 0.0;
-                {                                                                     // an accepted move: its virial change, qad2 :1244,1339,1354
+                {   // an accepted move: its virial change, qad2 :1244,1339,1354.  (Keeping every bond's term in shared memory and reading
+                    // the two OLD ones from there instead of evaluating them was measured: 1.00e10 against 1.13e10 — the loads and
+                    // their write-backs sit on the step's dependency chain, profiles/r2zd_*, r2ze_c2_crew_ab.jsonl.)
                     const bool moved = code & 1u;
                     const uint32_t i0 = moved ? (code >> 8) : 0u;
                     const bool hasL = i0 > 0, hasR = i0 + 1 < N;
@@ -819,9 +830,14 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                 const double ran = u01_shifted(w2, 1.0);
                 const uint32_t i0 = disp ? nm : 0u;
                 const bool hasL = i0 > 0, hasR = i0 + 1 < N;
-                // (a chain on a volume trial belongs to warp F in this step: its column is not read)
+                // (a chain on a volume trial belongs to warp F in this step: T reads the column of zeros instead of its positions)
                 const double E = disp ? R.E[lane] : 0.0, half_l = disp ? R.l[lane] / 2.0 : 0.0;
+#if JMM_CREW_ZEROCOL
+                const double *rc = disp ? r : zeros;
+                const double rnm = rc[i0 * 32], rl = rc[(hasL ? i0 - 1 : i0) * 32], rr = rc[(hasR ? i0 + 1 : i0) * 32];
+#else
                 const double rnm = disp ? r[i0 * 32] : 0.0, rl = disp ? r[(hasL ? i0 - 1 : i0) * 32] : 0.0, rr = disp ? r[(hasR ? i0 + 1 : i0) * 32] : 0.0;
+#endif
                 const double rT = rnm + rnh * 2 * maxStep;                            // :1182-1183
                 const bool wall = fabs(rT) > half_l;                                  // :1188
                 const double po0 = b2_bond_energy<INF>(rnm - rl, cutoff), pn0 = b2_bond_energy<INF>(rT - rl, cutoff);
@@ -877,6 +893,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
         double *r = tiles + lane;
         double maxdl = S.maxdl[chain];
         const double P = S.P[chain], T = S.T[chain], invT = 1.0 / T;
+        const double band_0 = 1.0000001 * 4.0 * (1.8e-7 * (double) N + 2.4e-7), band_lg = 1.0000001 * 4.0 * 4.2e-8 * (double) N;
         uint64_t cnt2 = S.cnt[2 * C + chain], cnt3 = S.cnt[3 * C + chain], vAErr = S.vAErr[chain];
         uint32_t t_acc = 0, t_rej = 0;
         const uint32_t mvai32 = a.mvai > 0xfffffffeull ? 0xffffffffu : (uint32_t) a.mvai;
@@ -894,8 +911,14 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                 const bool vol = !(nm < N);
                 const double rnh = u01_shifted(w1, 1.5);                              // rn - 0.5, exactly (rng.cuh)
                 const double ran = u01_shifted(w2, 1.0);
-                // (a chain on a displacement trial belongs to warp T in this step: its column is not read; 1.0 keeps the arithmetic finite)
+                // (a chain on a displacement trial belongs to warp T in this step: F reads the column of zeros; l = 1 keeps the arithmetic finite)
                 const double E = vol ? R.E[lane] : 0.0, l = vol ? R.l[lane] : 1.0;
+#if JMM_CREW_ZEROCOL
+                const double *rc = vol ? r : zeros;
+#define JMM_CREW_LD(i) rc[(i) * 32]
+#else
+#define JMM_CREW_LD(i) (vol ? r[(i) * 32] : 0.0)
+#endif
                 const double dl = rnh * 2 * maxdl;
                 const double lnew = l + dl;
                 const double lRat1 = lnew / l;
@@ -903,13 +926,13 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                 double t0 = 0;
                 if constexpr (NT > 0) {
 #pragma unroll
-                    for (int i = 0; i < NT; ++i) rs[i] = (vol ? r[i * 32] : 0.0) * lRat1;
+                    for (int i = 0; i < NT; ++i) rs[i] = JMM_CREW_LD(i) * lRat1;
 #pragma unroll
                     for (int i = 0; i + 1 < NT; ++i) t0 += b2_bond_energy<INF>(rs[i + 1] - rs[i], cutoff);
                 } else {
-                    double ri = (vol ? r[0] : 0.0) * lRat1;
+                    double ri = JMM_CREW_LD(0) * lRat1;
                     for (uint32_t i = 0; i + 1 < N; ++i) {
-                        const double rj = (vol ? r[(i + 1) * 32] : 0.0) * lRat1;
+                        const double rj = JMM_CREW_LD(i + 1) * lRat1;
                         t0 += b2_bond_energy<INF>(rj - ri, cutoff);
                         ri = rj;
                     }
@@ -919,7 +942,12 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                 asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float) lRat1));
                 const double A = (double) N * ((double) lg * 0.6931471805599453) - x * invT;
                 const double bb = (double) exp_neg_approx(-A);
+                // volume_accept_band() with its constants folded (two FMAs: the band only has to be no SMALLER than the bound)
+#if JMM_CREW_BANDFMA
+                const double band = __fma_rn(6.4e-7, fabs(A), __fma_rn(band_lg, (double) fabsf(lg), band_0));
+#else
                 const double band = volume_accept_band((double) N, (double) lg, A);
+#endif
                 const bool narrow = lRat1 > kVolumeBandLo && lRat1 < kVolumeBandHi;
                 const bool v_yes = narrow && ran < bb * (1.0 - band), v_no = narrow && ran > bb * (1.0 + band);
                 bool accept_v = v_yes;

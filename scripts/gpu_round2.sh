@@ -42,9 +42,9 @@ JMM_BENCH_CHAINS=8192 timeout 600 python bench.py --workload c4 --arith fast --s
 # launch list (cold-cache, serialised: shares only)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_launches_$TAG.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_bond -s 3 -c 1 -f -o $OUT/prof_c2_$TAG \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_crew -s 3 -c 1 -f -o $OUT/prof_c2_$TAG \
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_c2_$TAG.log 2>&1; tail -1 $OUT/ncu_c2_$TAG.log | cut -c1-200
-condense prof_c2_$TAG 409600000 k_chains_step_bond          # unit = one warp step (2048 warps x 200 000 steps)
+condense prof_c2_$TAG 25600000 k_chains_step_crew           # unit = one step of a 32-chain CTA (128 CTAs x 200 000 steps)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_prod -s 1 -c 1 -f -o $OUT/prof_c4fast_$TAG \
     python bench.py --workload c4 --arith fast --steps 1 --warmup 3 --no-cpu --no-e2e --min-seconds 0 > $OUT/ncu_c4fast_$TAG.log 2>&1; tail -1 $OUT/ncu_c4fast_$TAG.log | cut -c1-200
 condense prof_c4fast_$TAG 40960000 k_chains_step_prod_sliced  # unit = one warp step (2048 tiles x 20 000 steps)
@@ -62,5 +62,5 @@ done
 timeout 200 ncu --set full --clock-control none -k regex:k_fp64_peak -s 2 -c 1 -f -o $OUT/prof_fp64peak_$TAG \
     python -c "import jmmonedmc_b200 as J; print(J.lib().jmm_fp64_peak_tflops(0))" > $OUT/ncu_fp64peak_$TAG.log 2>&1; tail -2 $OUT/ncu_fp64peak_$TAG.log | cut -c1-200
 condense prof_fp64peak_$TAG 1 k_fp64_peak
-SAN_CASES="bond2 lanes lanes80" bash scripts/gpu_sanitize.sh > $OUT/sanitizer_$TAG.txt 2>&1; tail -14 $OUT/sanitizer_$TAG.txt
+SAN_CASES="solo trio crew bond2 lanes lanes80" bash scripts/gpu_sanitize.sh > $OUT/sanitizer_$TAG.txt 2>&1; tail -14 $OUT/sanitizer_$TAG.txt
 ls -la $OUT | tail -30
