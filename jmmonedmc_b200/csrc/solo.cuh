@@ -892,6 +892,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
         // ---------------------------------------------------------------- F: volume trials, fav :2161-2293
         double *r = tiles + lane;
         double maxdl = S.maxdl[chain];
+        double l = S.l[chain];                                // (F is the only one to change a chain's length: a register, mirrored in R.l for T)
         const double P = S.P[chain], T = S.T[chain], invT = 1.0 / T;
         const double band_0 = 1.0000001 * 4.0 * (1.8e-7 * (double) N + 2.4e-7), band_lg = 1.0000001 * 4.0 * 4.2e-8 * (double) N;
         uint64_t cnt2 = S.cnt[2 * C + chain], cnt3 = S.cnt[3 * C + chain], vAErr = S.vAErr[chain];
@@ -905,23 +906,24 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
             if (k >= 2) crew_bar_sync(D_FREE + b, kD);
             const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
             uint32_t nm = R.nm[b][0][lane], w1 = R.w1[b][0][lane], w2 = R.w2[b][0][lane];
+            // the trial length and its ratio (:2170-2172) depend on nothing warp T does: those of step j+1 are evaluated BEFORE
+            // the barrier that ends step j, so that the division's latency is spent while waiting for T
+            double dl = u01_shifted(w1, 1.5) * 2 * maxdl;                             // (rn - 0.5) * 2 * maxdl
+            double lnew = l + dl;
+            double lRat1 = lnew / l;
             for (uint32_t j = 0; j < n; ++j) {
                 const uint32_t nm1 = j + 1 < n ? R.nm[b][j + 1][lane] : 0u, w11 = j + 1 < n ? R.w1[b][j + 1][lane] : 0u,
                                w21 = j + 1 < n ? R.w2[b][j + 1][lane] : 0u;
                 const bool vol = !(nm < N);
-                const double rnh = u01_shifted(w1, 1.5);                              // rn - 0.5, exactly (rng.cuh)
                 const double ran = u01_shifted(w2, 1.0);
-                // (a chain on a displacement trial belongs to warp T in this step: F reads the column of zeros; l = 1 keeps the arithmetic finite)
-                const double E = vol ? R.E[lane] : 0.0, l = vol ? R.l[lane] : 1.0;
+                // (a chain on a displacement trial belongs to warp T in this step: F reads the column of zeros instead of its positions)
+                const double E = vol ? R.E[lane] : 0.0;
 #if JMM_CREW_ZEROCOL
                 const double *rc = vol ? r : zeros;
 #define JMM_CREW_LD(i) rc[(i) * 32]
 #else
 #define JMM_CREW_LD(i) (vol ? r[(i) * 32] : 0.0)
 #endif
-                const double dl = rnh * 2 * maxdl;
-                const double lnew = l + dl;
-                const double lRat1 = lnew / l;
                 double rs[NR];
                 double t0 = 0;
                 if constexpr (NT > 0) {
@@ -957,6 +959,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                 }
                 const bool ok_v = vol && accept_v;                                    // :2257-2275
                 if (ok_v) {
+                    l = lnew;
                     R.l[lane] = lnew; R.E[lane] = t0;
                     if constexpr (NT > 0) {
 #pragma unroll
@@ -986,6 +989,9 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                     mvai_left = mvai32;
                 }
                 nm = nm1; w1 = w11; w2 = w21;
+                dl = u01_shifted(w1, 1.5) * 2 * maxdl;
+                lnew = l + dl;
+                lRat1 = lnew / l;
                 crew_bar_sync(STEP, 64);                                              // warp T has committed its chains' step
             }
             crew_bar_arrive(D_FULL + b, kD);
