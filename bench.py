@@ -44,7 +44,7 @@ sys.path.insert(0, str(ROOT))
 
 C2 = dict(N=10, P=0.7, T=0.4, pot="HARMONIC", nbn=1, maxStep=0.1, maxdl=1.0, eci=1, mdai=100, mvai=100, seed=125,
           nchains=4096)
-MC_PER_STEP = 200000          # ~80-190 ms per bench step: ten timed steps give the clock sampler >= 1 s
+MC_PER_STEP = 400000          # ~145 ms per bench step on the crew kernel: ten timed steps give the clock sampler >= 1 s
 METRIC = "MC trial moves/sec"
 UNIT = "trial moves/s"
 WORKLOAD = "C2: test/INPUTstd deck (N=10, HARMONIC, NBN 1, NPT, ENGCHECK 1, DADJ/VADJ 100) x 4096 chains per GPU"

@@ -44,7 +44,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_launches_$TAG.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_crew -s 3 -c 1 -f -o $OUT/prof_c2_$TAG \
     python bench.py --steps 2 --warmup 3 --no-extras > $OUT/ncu_c2_$TAG.log 2>&1; tail -1 $OUT/ncu_c2_$TAG.log | cut -c1-200
-condense prof_c2_$TAG 25600000 k_chains_step_crew           # unit = one step of a 32-chain CTA (128 CTAs x 200 000 steps)
+condense prof_c2_$TAG 51200000 k_chains_step_crew           # unit = one step of a 32-chain CTA (128 CTAs x 400 000 steps)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_chains_step_prod -s 1 -c 1 -f -o $OUT/prof_c4fast_$TAG \
     python bench.py --workload c4 --arith fast --steps 1 --warmup 3 --no-cpu --no-e2e --min-seconds 0 > $OUT/ncu_c4fast_$TAG.log 2>&1; tail -1 $OUT/ncu_c4fast_$TAG.log | cut -c1-200
 condense prof_c4fast_$TAG 40960000 k_chains_step_prod_sliced  # unit = one warp step (2048 tiles x 20 000 steps)

@@ -740,3 +740,19 @@ def test_lanes_with_padded_rows_match_oracle(J, O, pot, N, g, monkeypatch):
         assert bits_equal(s["l"][c:c + 1], [oc.l]) and np.array_equal(s["counters"][c], oc.counters)
         assert totals_close(s["totals"][c], oc.totals, 1e-12), f"chain {c}: totals"
         assert np.allclose(s["accum"][c], oc.accum, rtol=1e-11, atol=1e-9)
+
+def test_engine_names_follow_the_dispatch(J, monkeypatch):
+    """jmm_engine(): the kernel family jmm_step launches for a handle (what bench.py prints beside its roofline)."""
+    for k in ("JMM_BOND", "JMM_COOP_G", "JMM_LANES_G", "JMM_TEAM", "JMM_NO_PROD"):
+        monkeypatch.delenv(k, raising=False)
+    def engine(deck, **kw):
+        cfg = jmm_config_from_deck(J, DECKS[deck], rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, **kw)
+        with J.Handle(cfg) as h:
+            return h.engine
+    assert engine("std", nchains=64) == "k_chains_step_crew"              # HARMONIC, NBN 1, NPT: five warps per 32 chains
+    assert engine("std", nchains=12000) == "k_chains_step_bond"           # more CTAs than two per SM hold
+    assert engine("small", nchains=64) == "k_chains_step_coop"
+    assert engine("small", nchains=64, arith=J.ARITH_FAST).startswith("k_chains_step_lanes")
+    assert engine("small", nchains=70000) == "k_chains_step_prod"
+    monkeypatch.setenv("JMM_BOND", "4")
+    assert engine("std", nchains=64) == "k_chains_step_trio"
