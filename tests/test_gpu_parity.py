@@ -398,6 +398,35 @@ def test_c2_bench_mode_matches_oracle_on_sampled_chains(J, O, engine, monkeypatc
         assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
 
 
+@pytest.mark.parametrize("engine", ["default", "trio"])
+def test_c2_one_long_launch_matches_oracle(J, O, engine, monkeypatch):
+    """One jmm_step of 1 000 000 steps (no adjustments in the deck, so nothing splits the launch): 31 250 hand-overs of each
+    ring of solo.cuh's kernels, a million step barriers between the displacement and the volume warp, ECheck on every step.
+    4096 chains on the GPU, 17 of them spread over the launch compared with the oracle bit for bit."""
+    if engine != "default":
+        for k, v in ENGINES[engine].items():
+            monkeypatch.setenv(k, v)
+    d = dict(DECKS["std"], DADJ=0, VADJ=0)
+    C, nsteps = 4096, 1_000_000
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C)
+    with J.Handle(cfg) as h:
+        if engine == "default":
+            assert h.engine == "k_chains_step_crew"
+        h.start()
+        l0 = h.kernel_launches
+        h.step(nsteps)
+        assert h.kernel_launches - l0 == 2                         # the kernel + its (empty) repair launch
+        s = h.get_state()
+        checks, disc = h.echeck_stats()
+    assert disc == 0
+    for c in list(range(0, C, 293)) + [31, 32, 4095]:
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=c))
+        oc.start(); oc.run(nsteps)
+        assert bits_equal(s["r"][c], oc.r), f"chain {c}: positions"
+        assert bits_equal(s["l"][c:c + 1], [oc.l]) and np.array_equal(s["counters"][c], oc.counters)
+        assert bits_equal(s["totals"][c][:2], oc.totals[:2]) and bits_equal(s["accum"][c][:10], oc.accum[:10])
+
+
 def test_device_adaptation_matches_until_first_adjust_then_statistically(J, O):
     d = dict(DECKS["std"])
     C = 64
