@@ -624,11 +624,15 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
 //     maxDisAdjust,
 //   * T and F work on ONE set of positions, E and l in shared memory (a chain's column is touched by exactly one of
 //     them in a step — the other reads a column of zeros instead) and meet at one named barrier per step,
-//   * warp V replays the records for the virial and updateThermo's sums, warp W replays them for ECheck,
+//   * warp V replays the records for the virial after a volume change and for updateThermo's sums (the virial change of a
+//     move comes from T, which holds the four distances and waits for F anyway), warp W replays them for ECheck,
 //   * warp P produces the Philox words, as before.
 // Chunked rings, repair of an energy discrepancy by repeating the launch, arithmetic: as k_chains_step_trio.
 #ifndef JMM_CREW_ZEROCOL
 #define JMM_CREW_ZEROCOL 1        // 1: T / F read a column of zeros for the other's chains; 0: predicated loads
+#endif
+#ifndef JMM_CREW_DV_IN_T
+#define JMM_CREW_DV_IN_T 1        // 1: warp T, which holds the four distances of a move, also evaluates its virial change; 0: warp V does
 #endif
 #ifndef JMM_CREW_BANDFMA
 #define JMM_CREW_BANDFMA 1        // 1: the volume band with folded constants; 0: volume_accept_band()
@@ -637,6 +641,7 @@ struct CrewShared {                                       // [buffer][step][lane
     uint32_t nm[2][kTrioChunk][32], w1[2][kTrioChunk][32], w2[2][kTrioChunk][32];     // P -> T, F
     uint32_t code[2][kTrioChunk][32];                                                   // T, F -> V, W: 0 nothing, 1 | nm << 8 moved, 2 rescaled
     double val[2][kTrioChunk][32], e[2][kTrioChunk][32], lnew[2][kTrioChunk][32];
+    double dv[2][kTrioChunk][32];                                                       // T -> V: the virial change of a move
     double E[32], l[32];                                                                // the chains' live energy and length (T and F)
     int redo;
 };
@@ -707,9 +712,16 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
             const uint32_t n = min((uint32_t) kTrioChunk, nsteps - k * kTrioChunk);
             uint32_t code = R.code[b][0][lane];
             double val = R.val[b][0][lane], e_rec = R.e[b][0][lane];
+#if JMM_CREW_DV_IN_T
+            double dv = R.dv[b][0][lane];
+#endif
             for (uint32_t j = 0; j < n; ++j) {
                 const uint32_t code1 = j + 1 < n ? R.code[b][j + 1][lane] : 0u;       // (the next record: its latency hides behind this one)
                 const double val1 = j + 1 < n ? R.val[b][j + 1][lane] : 0.0, e1 = j + 1 < n ? R.e[b][j + 1][lane] : 0.0;
+#if JMM_CREW_DV_IN_T
+                const double dv1 = j + 1 < n ? R.dv[b][j + 1][lane] : 0.0;
+                if (code & 1u) { Vir = Vir + dv; r[(code >> 8) * 32] = val; }         // an accepted move: qad2 :1354,1390 (the change is warp T's)
+#else
                 {   // an accepted move: its virial change, qad2 :1244,1339,1354.  (Keeping every bond's term in shared memory and reading
                     // the two OLD ones from there instead of evaluating them was measured: 1.00e10 against 1.13e10 — the loads and
                     // their write-backs sit on the step's dependency chain, profiles/r2zd_*, r2ze_c2_crew_ab.jsonl.)
@@ -725,6 +737,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                     const double l1 = hasL ? (0.0 - po1 + pn1) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;
                     if (moved) { Vir = Vir + (l1 + r1); r[i0 * 32] = val; }
                 }
+#endif
                 if (__any_sync(FULL, code == 2u)) {                                   // an accepted volume trial: r *= lRat1 (:2264-2266), Vir from all bonds
                     if (code == 2u) {
                         l = R.lnew[b][j][lane];
@@ -751,6 +764,9 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                 acc[6] = acc[6] + l * E;   acc[7] = acc[7] + Vir;
                 acc[8] = acc[8] + Vir * Vir; acc[9] = acc[9] + E * Vir;
                 code = code1; val = val1; e_rec = e1;
+#if JMM_CREW_DV_IN_T
+                dv = dv1;
+#endif
             }
             if (k + 2 < nchunks) crew_bar_arrive(D_FREE + b, kD);
         }
@@ -831,7 +847,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                 const uint32_t i0 = disp ? nm : 0u;
                 const bool hasL = i0 > 0, hasR = i0 + 1 < N;
                 // (a chain on a volume trial belongs to warp F in this step: T reads the column of zeros instead of its positions)
-                const double E = disp ? R.E[lane] : 0.0, half_l = disp ? R.l[lane] / 2.0 : 0.0;
+                const double E = disp ? R.E[lane] : 0.0, lT = disp ? R.l[lane] : 1.0, half_l = lT / 2.0;
 #if JMM_CREW_ZEROCOL
                 const double *rc = disp ? r : zeros;
                 const double rnm = rc[i0 * 32], rl = rc[(hasL ? i0 - 1 : i0) * 32], rr = rc[(hasR ? i0 + 1 : i0) * 32];
@@ -840,8 +856,21 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
 #endif
                 const double rT = rnm + rnh * 2 * maxStep;                            // :1182-1183
                 const bool wall = fabs(rT) > half_l;                                  // :1188
+#if JMM_CREW_DV_IN_T
+                // energy AND virial of the four bond terms: nothing T decides depends on the virial, but T holds the distances,
+                // has the time (it waits for F), and warp V would have to load and rebuild them (190 instructions per step there)
+                const double two_over_l = 2 / lT;
+                double po0, po1, pn0, pn1, qo0, qo1, qn0, qn1;
+                b2_phi<INF>(rnm - rl, cutoff, two_over_l, po0, po1);
+                b2_phi<INF>(rT - rl, cutoff, two_over_l, pn0, pn1);
+                b2_phi<INF>(rr - rnm, cutoff, two_over_l, qo0, qo1);
+                b2_phi<INF>(rr - rT, cutoff, two_over_l, qn0, qn1);
+                const double l1 = hasL ? (0.0 - po1 + pn1) : 0.0, r1 = hasR ? (0.0 - qo1 + qn1) : 0.0;
+                const double dV = l1 + r1;
+#else
                 const double po0 = b2_bond_energy<INF>(rnm - rl, cutoff), pn0 = b2_bond_energy<INF>(rT - rl, cutoff);
                 const double qo0 = b2_bond_energy<INF>(rr - rnm, cutoff), qn0 = b2_bond_energy<INF>(rr - rT, cutoff);
+#endif
                 const double l0 = hasL ? (0.0 - po0 + pn0) : 0.0;                     // :1244
                 const double r0 = hasR ? (0.0 - qo0 + qn0) : 0.0;                     // :1339
                 const double dE = l0 + r0;                                            // :1354
@@ -860,6 +889,9 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
                     R.code[b][j][lane] = ok_d ? (1u | (nm << 8)) : 0u;
                     R.val[b][j][lane] = rT;
                     R.e[b][j][lane] = Enew;
+#if JMM_CREW_DV_IN_T
+                    R.dv[b][j][lane] = dV;
+#endif
                     if (LOG && own) a.accept_log[(uint64_t)(k * kTrioChunk + j) * C + chain] = wall ? kLogWall : (ok_d ? kLogAccepted : 0);
                 }
                 t_acc += ok_d ? 1u : 0u;

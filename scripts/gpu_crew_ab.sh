@@ -14,9 +14,9 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-b "all three on (tree)"
-for v in Z0 V0 B0 ZV0 ALL0; do
+b "tree"
+for v in ${AB_VARIANTS:-DV0 FAKE}; do
   b "variant $v" JMM_LIBJMMGPU=$PWD/jmmonedmc_b200/variants/libjmmgpu_$v.so
 done
-b "all three on (again)"
+b "tree (again)"
 tail -3 $OUT/bench_$TAG.err
