@@ -427,6 +427,27 @@ def test_c2_one_long_launch_matches_oracle(J, O, engine, monkeypatch):
         assert bits_equal(s["totals"][c][:2], oc.totals[:2]) and bits_equal(s["accum"][c][:10], oc.accum[:10])
 
 
+def test_c2_two_ctas_per_sm_match_oracle(J, O):
+    """8192 chains of the INPUTstd shape = 256 CTAs of k_chains_step_crew on 148 SMs: two CTAs share an SM, its shared memory and
+    its sixteen named barriers.  50 000 steps with host-side adjustments every 100; 20 sampled chains equal the oracle bit for bit."""
+    d = dict(DECKS["std"])
+    C, nsteps = 8192, 50_000
+    cfg = jmm_config_from_deck(J, d, rng_kind=J.RNG_PHILOX, mode=J.MODE_RECOMPUTE, adapt=J.ADAPT_HOST, nchains=C)
+    with J.Handle(cfg) as h:
+        assert h.engine == "k_chains_step_crew"
+        h.start()
+        h.step(nsteps)
+        s = h.get_state()
+        ms, mv = h.get_step_sizes()
+    for c in list(range(5, C, 431)) + [8191]:
+        oc = O.Chain(O.config_from_deck(d, rng_kind=O.RNG_PHILOX, mode=O.MODE_RECOMPUTE, chain_id=c))
+        oc.start(); oc.run(nsteps)
+        assert bits_equal(s["r"][c], oc.r), f"chain {c}: positions"
+        assert bits_equal(s["l"][c:c + 1], [oc.l]) and np.array_equal(s["counters"][c], oc.counters)
+        assert bits_equal(s["totals"][c][:2], oc.totals[:2]) and bits_equal(s["accum"][c][:10], oc.accum[:10])
+        assert bits_equal([ms[c], mv[c]], list(oc.step_sizes))
+
+
 def test_device_adaptation_matches_until_first_adjust_then_statistically(J, O):
     d = dict(DECKS["std"])
     C = 64
