@@ -308,9 +308,19 @@ __global__ void __launch_bounds__(32) k_chains_step_solo(ChainsDev S, StepArgs a
 // threshold of 1e-4: the path exists for correctness and is exercised by JMM_SOLO_FORCE_REDO=1 in the tests.)
 // Arithmetic = k_chains_step_solo's = the reference's, per chain in the reference's order: bit-identical.
 constexpr int kTrioChunk = 32;                            // steps per ring buffer
+// The warps of a CTA meet at named barriers from DIFFERENT places in the code (producer and consumer loops).  That is what
+// barrier.sync / barrier.arrive WITHOUT .aligned are for (PTX ISA: .aligned = every thread of the warp executes the same barrier
+// instruction, and tools such as compute-sanitizer synccheck hold the whole CTA to it); bar.sync is the .aligned form.
+#ifndef JMM_BAR_SYNC
+#define JMM_BAR_SYNC "barrier.sync"
+#define JMM_BAR_ARRIVE "barrier.arrive"
+#endif
 
-__device__ __forceinline__ void trio_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void trio_bar_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void trio_bar_sync(int id) { asm volatile(JMM_BAR_SYNC " %0, 64;" ::"r"(id) : "memory"); }
+// the CTA-wide rendezvous at the end of the launch is reached from three places (one per role): a NAMED barrier with the thread
+// count, which is defined per barrier resource, not __syncthreads(), which the programming model wants at one place
+__device__ __forceinline__ void trio_bar_all() { asm volatile(JMM_BAR_SYNC " 9, 96;" ::: "memory"); }
+__device__ __forceinline__ void trio_bar_arrive(int id) { __threadfence_block(); asm volatile(JMM_BAR_ARRIVE " %0, 64;" ::"r"(id) : "memory"); }
 
 struct TrioRings {                                        // [buffer][step][lane]
     uint32_t nm[2][kTrioChunk][32], w1[2][kTrioChunk][32], w2[2][kTrioChunk][32];     // P -> T
@@ -441,7 +451,7 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
         }
         const bool any_bad = __any_sync(FULL, bad);
         if (lane == 0) { R.redo = any_bad ? 1 : 0; if (any_bad) redo[blockIdx.x] = 1u; }
-        __syncthreads();
+        trio_bar_all();
         if (!any_bad && own) {
 #pragma unroll
             for (int k = 0; k < 10; ++k) S.acc[k * C + chain] = acc[k];
@@ -598,7 +608,7 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
             if (k + 2 < nchunks) trio_bar_arrive(P_FREE + b);
         }
         fold();
-        __syncthreads();                                  // warp V's verdict
+        trio_bar_all();                                  // warp V's verdict
         if (R.redo || !own) return;
         for (uint32_t i = 0; i < N; ++i) S.r[(uint64_t) i * C + chain] = r[i * 32];
         S.l[chain] = l; S.maxStep[chain] = maxStep; S.maxdl[chain] = maxdl;
@@ -610,7 +620,7 @@ __global__ void __launch_bounds__(96) k_chains_step_trio(ChainsDev S, StepArgs a
         S.vAErr[chain] = vAErr;
         return;
     }
-    __syncthreads();                                      // (warp P: the CTA's final barrier)
+    trio_bar_all();                                      // (warp P: the CTA's final barrier)
 }
 
 
@@ -646,15 +656,15 @@ struct CrewShared {                                       // [buffer][step][lane
     int redo;
 };
 
-__device__ __forceinline__ void crew_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void crew_bar_arrive(int id, int n) { __threadfence_block(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void crew_bar_sync(int id, int n) { asm volatile(JMM_BAR_SYNC " %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void crew_bar_arrive(int id, int n) { __threadfence_block(); asm volatile(JMM_BAR_ARRIVE " %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int NT, bool LOG, bool INF>
 __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepArgs a, unsigned int *redo, int force_redo) {
     extern __shared__ __align__(16) unsigned char crew_smem[];
     constexpr uint32_t FULL = 0xffffffffu;
     // named barriers (+ buffer index 0/1): a ring buffer is FULL (producers arrive, consumers sync) or FREE (the reverse)
-    constexpr int P_FULL = 1, P_FREE = 3, D_FULL = 5, D_FREE = 7, STEP = 9;
+    constexpr int P_FULL = 1, P_FREE = 3, D_FULL = 5, D_FREE = 7, STEP = 9, FINAL = 10;   // (FINAL: reached from five places, hence named)
     constexpr int kP = 96, kD = 128;                      // threads at a P barrier (P, T, F) and at a D barrier (T, F, V, W)
     // warp w runs on sub-partition w % 4: the light producer shares one with the energy checker, T and F have their own
     enum { ROLE_P = 0, ROLE_T = 1, ROLE_F = 2, ROLE_V = 3, ROLE_W = 4 };
@@ -770,7 +780,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
             }
             if (k + 2 < nchunks) crew_bar_arrive(D_FREE + b, kD);
         }
-        __syncthreads();                                  // warp W's verdict
+        crew_bar_sync(FINAL, 160);                                  // warp W's verdict
         if (!R.redo && own) {
 #pragma unroll
             for (int k = 0; k < 10; ++k) S.acc[k * C + chain] = acc[k];
@@ -819,7 +829,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
         }
         const bool any_bad = __any_sync(FULL, bad);
         if (lane == 0) { R.redo = any_bad ? 1 : 0; if (any_bad) redo[blockIdx.x] = 1u; }
-        __syncthreads();
+        crew_bar_sync(FINAL, 160);
         if (!any_bad && own) S.echeck[chain] = echecks + t_checks;
         return;
     } else if (role == ROLE_T) {
@@ -911,7 +921,7 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
             if (k + 2 < nchunks) crew_bar_arrive(P_FREE + b, kP);
         }
         cnt0 += t_acc; cnt1 += t_rej;
-        __syncthreads();                                  // warp W's verdict
+        crew_bar_sync(FINAL, 160);                                  // warp W's verdict
         if (R.redo || !own) return;
         for (uint32_t i = 0; i < N; ++i) S.r[(uint64_t) i * C + chain] = r[i * 32];
         S.l[chain] = R.l[lane]; S.maxStep[chain] = maxStep;
@@ -1030,14 +1040,14 @@ __global__ void __launch_bounds__(160, 1) k_chains_step_crew(ChainsDev S, StepAr
             if (k + 2 < nchunks) crew_bar_arrive(P_FREE + b, kP);
         }
         cnt2 += t_acc; cnt3 += t_rej;
-        __syncthreads();                                  // warp W's verdict
+        crew_bar_sync(FINAL, 160);                                  // warp W's verdict
         if (R.redo || !own) return;
         S.maxdl[chain] = maxdl;
         S.cnt[2 * C + chain] = cnt2; S.cnt[3 * C + chain] = cnt3;
         S.vAErr[chain] = vAErr;
         return;
     }
-    __syncthreads();                                      // (warp P: the CTA's final barrier)
+    crew_bar_sync(FINAL, 160);                                      // (warp P: the CTA's final barrier)
 }
 
 }  // namespace jmm
