@@ -58,7 +58,7 @@ struct TeamShared {                                       // one per team, in dy
     uint32_t nvalid;                                      // chains of the tile that exist (the rest re-run the last one, unsaved)
 };
 
-__device__ __forceinline__ void team_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void team_bar_sync(int id, int n) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }   // (non-aligned: reached from different places by the two roles)
 __device__ __forceinline__ void team_st_release(uint32_t *p, uint32_t v) {
     asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"((uint32_t) __cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
