@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(32) k_chains_step_solo(ChainsDev S, StepArgs a
 //     result: the virial (the four old/new bond terms of an accepted move in qad2's order :1244,1339,1354; all bonds
 //     in pair order after an accepted volume change, fav :2212-2240), ECheck's energy from the positions and its
 //     comparison with E, and updateThermo's sums.
-// The rings are handed over 32 steps at a time through named barriers (st.shared, fence, bar.arrive | bar.sync,
-// ld.shared: the producer/consumer use of bar.arrive in the PTX ISA), so no warp polls.
+// The rings are handed over 32 steps at a time through named barriers (st.shared, fence, barrier.arrive | barrier.sync,
+// ld.shared: the producer/consumer use of barrier.arrive in the PTX ISA), so no warp polls.
 // An energy discrepancy (ECheck :2003-2071: |ETest - E| > 1e-4, which the reference answers by recomputing the totals
 // on the spot) would change what warp T has long passed.  It cannot be repaired in place, so it is repaired in
 // time: the CTA stores NOTHING, raises its word in `redo`, and the launch is followed by k_chains_step_bond for the
